@@ -1,0 +1,44 @@
+"""Shared loaders for the golden cases (inputs + reference outputs)."""
+import json
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+from rufus_b200 import fastq, synth
+
+BUNDLED = ("Child", "Mother", "Father")
+EDGE = ("Subj", "CtlA", "CtlB")
+
+
+def golden(case):
+    return json.load(open(os.path.join(GOLDEN, case, "golden.json")))
+
+
+def load_case(case):
+    """-> (golden dict, {sample: (mate1 Reads, mate2 Reads)}), first sample = subject."""
+    g = golden(case)
+    reads = {}
+    if case == "testRun":
+        for s in BUNDLED:
+            reads[s] = tuple(fastq.read_fastq(os.path.join(GOLDEN, case, f"{s}.mate{m}.fastq.gz")) for m in (1, 2))
+    elif case == "edge":
+        for s in EDGE:
+            reads[s] = tuple(fastq.read_fastq(os.path.join(GOLDEN, case, f"{s}.mate{m}.fastq")) for m in (1, 2))
+    else:
+        import hashlib
+        sy = g["synth"]
+        trio, _ = synth.make_trio(sy["seed"], sy["genome_len"], sy["n_pairs"])
+        for s in synth.SAMPLES:
+            s1, q1, s2, q2 = trio[s]
+            md5 = hashlib.md5(s1.tobytes() + q1.tobytes() + s2.tobytes() + q2.tobytes()).hexdigest()
+            assert md5 == sy["input_md5"][s], "synthetic generator drifted from the committed golden inputs"
+            r1, r2 = fastq.from_matrix(s1, q1), fastq.from_matrix(s2, q2)
+            r1.names = [f"@{s[0]}{i:09d}".encode() for i in range(len(r1))]
+            r2.names = list(r1.names)
+            reads[s] = (r1, r2)
+    return g, reads
+
+
+def both_mates(pair):
+    return fastq.concat(pair[0], pair[1])

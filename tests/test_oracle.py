@@ -1,0 +1,85 @@
+"""Pin the CPU oracle (oracle/rufus_oracle.c) to outputs of the reference's own
+binaries (tests/golden/*/golden.json, made by tests/golden/make_golden.py)."""
+import gzip
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from cases import both_mates, load_case
+from conftest import GOLDEN, ROOT
+from rufus_b200 import kmer
+
+import sys
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle  # noqa: E402
+
+CASES = ["testRun", "edge", "synth_k25", "synth_k31"]
+
+
+def _dump_bytes(keys, counts, k):
+    lines = sorted(kmer.dump_text(keys, counts, k))
+    return ("\n".join(lines) + "\n").encode() if lines else b""
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_count_histo_subtract_filter_match_reference(case):
+    g, reads = load_case(case)
+    k = g["k"]
+    names = list(reads)
+    tabs = {}
+    for i, s in enumerate(names):
+        r = both_mates(reads[s])
+        lower = g["L"] if i == 0 else g["ctlL"]
+        keys, counts = oracle.count(r.seq, r.offs, k, True, lower)
+        tabs[s] = (keys, counts)
+        gs = g["samples"][s]
+        assert keys.size == gs["n_distinct"]
+        assert hashlib.md5(_dump_bytes(keys, counts, k)).hexdigest() == gs["dump_sorted_md5"]
+        h, base = oracle.histo(counts)
+        assert h.size == gs["histo_rows"] == 10002 and base == 0
+        nz = {int(i): int(v) for i, v in enumerate(h) if v}
+        assert nz == {int(a): b for a, b in gs["histo_nonzero"].items()}
+        text = "".join(f"{i} {v}\n" for i, v in enumerate(h))
+        assert hashlib.md5(text.encode()).hexdigest() == gs["histo_md5"]
+        dump_gz = os.path.join(GOLDEN, case, s + ".dump.sorted.gz")
+        if os.path.exists(dump_gz):
+            assert gzip.open(dump_gz).read() == _dump_bytes(keys, counts, k)
+    subj = names[0]
+    mk, mc = oracle.merge_unique([tabs[s] for s in names])
+    assert sorted(kmer.dump_text(mk, mc, k, "\t")) == g["merge_sorted"]
+    hk, hc = oracle.hashlist(tabs[subj], [tabs[s] for s in names[1:]], g["min_cov"], g["max_cov"])
+    assert sorted(kmer.dump_text(hk, hc, k)) == g["hashlist_sorted"]
+    rset = oracle.rufus_set_from_kmers(kmer.keys_to_text(hk, k))
+    m1, m2 = reads[subj]
+    keep = oracle.filter_pairs(m1.seq, m1.qual, m1.offs, m2.seq, m2.qual, m2.offs, k, g["minq"], g["thresh"], rset)
+    got = sorted(m1.names[i].decode() for i in np.flatnonzero(keep))
+    assert got == g["pulled_mate1_names_sorted"]
+    hits = oracle.filter_single(m1.seq, m1.qual, m1.offs, k, g["minq"], rset)
+    got = sorted(f"{m1.names[i].decode()}:MH{hits[i]}" for i in np.flatnonzero(hits >= g["thresh"]))
+    assert got == g["single_names_sorted"]
+
+
+def test_rufus_pack_known_answers():
+    # Util.cpp:51-84: base i at bits (2i, 2i+1): A 00, C bit(2i+1), G bit(2i), T both.
+    L = oracle.lib()
+    assert L.ro_rufus_pack(b"A", 1) == 0
+    assert L.ro_rufus_pack(b"C", 1) == 2
+    assert L.ro_rufus_pack(b"G", 1) == 1
+    assert L.ro_rufus_pack(b"T", 1) == 3
+    assert L.ro_rufus_pack(b"AC", 2) == 8
+    assert L.ro_rufus_pack(b"xT", 2) == 12     # unknown byte == 'A'
+    assert L.ro_rufus_pack(b"c", 1) == 0       # lower case is NOT recognised by RUFUS
+
+
+def test_count_semantics_small():
+    seq = np.frombuffer(b"ACGTNacgtAC", dtype=np.uint8)
+    offs = np.array([0, 5, 11], dtype=np.uint64)
+    keys, counts = oracle.count(seq, offs, 3, True, 1)
+    txt = dict(zip(kmer.keys_to_text(keys, 3), counts.tolist()))
+    # read1 ACGT|N -> ACG(canon ACG), CGT(canon ACG); read2 acgtAC -> ACG,ACG(cgt),GTA,TAC(canon GTA)
+    assert txt == {"ACG": 4, "GTA": 2}
+    keys, counts = oracle.count(seq, offs, 3, False, 1)
+    txt = dict(zip(kmer.keys_to_text(keys, 3), counts.tolist()))
+    assert txt == {"ACG": 2, "CGT": 2, "GTA": 1, "TAC": 1}
