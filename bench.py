@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — Gbases/s through k-mer count + subtract + read pull (k=25, synthetic
+30x trio of 150 bp reads), BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        our CUDA path
+  python bench.py --impl reference [...]                     the reference's CPU path
+
+One step = one pass of the hot path over one batch: count the three samples
+(1 M reads x 150 bp each, per GPU) -> subject histogram -> subtract -> pull the
+subject's read pairs. `value` = bases of all samples counted / device time with
+inputs resident in HBM; `e2e` = the same pass through the host-buffer C ABI
+(H2D of the reads and D2H of the results inside the timed region).
+N > 1 (torchrun): weak scaling, every rank brings its own 1 M reads/sample; k-mers
+are routed to their hash-prefix shard with one NCCL all-to-all per sample.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gbases/sec through k-mer count+filter (k=25, 30x trio)"
+K, READ_LEN, MIN_COV, MINQ, THRESH = 25, 150, 5, 15, 1
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception as e:  # nvidia-smi missing
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit()]
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- data
+def make_data(n_pairs, genome_len, seed, slice_id):
+    from rufus_b200 import synth
+    t0 = time.time()
+    trio, _ = synth.make_trio(seed, genome_len, n_pairs, slice_id=slice_id)
+    log(f"synthetic trio: {n_pairs} pairs/sample, genome {genome_len}, {time.time() - t0:.1f}s")
+    return trio
+
+
+# --------------------------------------------------------------------------- CPU reference
+def cpu_reference_pass(trio, n_pairs, workdir, threads):
+    """One pass of the reference's own commands on the first n_pairs pairs
+    of every sample. Returns (seconds, bases, kind, info)."""
+    from rufus_b200 import synth
+    refbin = os.path.join(ROOT, "oracle", "_ref")
+    jf = os.path.join(refbin, "jellyfish")
+    have_ref = os.path.exists(jf) and os.path.exists(os.path.join(refbin, "RUFUS.Filter"))
+    bases = 0
+    if have_ref:
+        fq = {}
+        for s in synth.SAMPLES:     # untimed: materialise the FASTQ files the reference reads
+            s1, q1, s2, q2 = (a[:n_pairs] for a in trio[s])
+            p1, p2 = os.path.join(workdir, f"{s}.m1.fq"), os.path.join(workdir, f"{s}.m2.fq")
+            open(p1, "wb").write(synth.fastq_bytes(s1, q1, prefix=s[0]))
+            open(p2, "wb").write(synth.fastq_bytes(s2, q2, prefix=s[0]))
+            fq[s] = (p1, p2)
+            bases += 2 * n_pairs * READ_LEN
+        t0 = time.time()
+        T = max(1, threads)
+        for s in synth.SAMPLES:
+            # RunJellyForRUFUS.sh:29 (right-sized -s: results are independent of -s) and :37
+            subprocess.run(f"cat {fq[s][0]} {fq[s][1]} | {jf} count --disk -m {K} -L 2 -s 256M -t {T} "
+                           f"-o {s}.Jhash -C /dev/stdin && {jf} histo -f -o {s}.Jhash.histo {s}.Jhash",
+                           shell=True, check=True, cwd=workdir, executable="/bin/bash")
+        # runRufus.sh:925-926 + CheckJellyHashList.sh:12
+        subprocess.run(f"{jf} merge Child.Jhash Mother.Jhash Father.Jhash > merge.out && "
+                       f"{jf} query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) Child.Jhash | "
+                       f"awk -v var={MIN_COV} ' $2 >= var ' | awk -v var=150 ' $2 <= var ' > HashList",
+                       shell=True, check=True, cwd=workdir, executable="/bin/bash")
+        # runRufus.sh:981
+        subprocess.run(f"{refbin}/RUFUS.Filter HashList {fq['Child'][0]} {fq['Child'][1]} out {K} {MINQ} {THRESH} {T} "
+                       "> /dev/null", shell=True, check=True, cwd=workdir, executable="/bin/bash")
+        dt = time.time() - t0
+        n_hash = sum(1 for _ in open(os.path.join(workdir, "HashList")))
+        n_pull = sum(1 for _ in open(os.path.join(workdir, "out.Mutations.Mate1.fastq"))) // 4
+        return dt, bases, "reference", {"hashlist": n_hash, "pulled": n_pull, "cores": T}
+    # fall back to the C port of the reference algorithm (single thread)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import oracle
+    from rufus_b200 import kmer
+    t0 = time.time()
+    tabs = []
+    for s in synth.SAMPLES:
+        s1, q1, s2, q2 = (a[:n_pairs] for a in trio[s])
+        both = np.concatenate([s1, s2])
+        offs = np.arange(both.shape[0] + 1, dtype=np.uint64) * READ_LEN
+        tabs.append(oracle.count(both.reshape(-1), offs, K, True, 2))
+        oracle.histo(tabs[-1][1])
+        bases += both.size
+    hk, hc = oracle.hashlist(tabs[0], tabs[1:], MIN_COV, 150)
+    s1, q1, s2, q2 = (a[:n_pairs] for a in trio["Child"])
+    offs = np.arange(n_pairs + 1, dtype=np.uint64) * READ_LEN
+    keep = oracle.filter_pairs(s1, q1, offs, s2, q2, offs, K, MINQ, THRESH,
+                               oracle.rufus_set_from_kmers(kmer.keys_to_text(hk, K)))
+    return time.time() - t0, bases, "port", {"hashlist": int(hk.size), "pulled": int(keep.sum()), "cores": 1}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n_pairs = args.ref_pairs
+    trio = make_data(n_pairs, args.genome, args.seed, None if world == 1 else 0)
+    threads = os.cpu_count() or 1
+    times, kind, info, bases = [], None, None, 0
+    for i in range(args.warmup + args.steps):
+        wd = tempfile.mkdtemp(prefix="rg_ref_")
+        try:
+            dt, bases, kind, info = cpu_reference_pass(trio, n_pairs, wd, threads)
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+        log(f"reference pass {i}: {dt:.2f}s")
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    val = bases / (ms / 1e3) / 1e9
+    sample = f"first {n_pairs} pairs/sample of the workload ({bases / 1e6:.0f} Mbases), jellyfish -s 256M"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gbases/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": workload_config(args, world),
+           "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": info["cores"], "kind": kind, "sample": sample},
+           "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"synthetic trio, {2 * args.pairs} x {READ_LEN} bp reads per sample per GPU, k={K}, "
+                        f"genome {args.genome} bp (30x per GPU slice), count 3 samples -> histo -> subtract "
+                        f"(min {MIN_COV}, max {150 * world}) -> pull subject pairs (MinQ {MINQ})",
+            "reads_per_sample_per_gpu": 2 * args.pairs, "read_len": READ_LEN, "k": K, "samples": 3,
+            "partition": f"hash-prefix x{world}" if world > 1 else "single GPU",
+            "l2": "inputs (450 MB reads + GB-scale tables) larger than L2; no flush needed"}
+
+
+# --------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--pairs", type=int, default=500_000, help="read pairs per sample per GPU")
+    ap.add_argument("--genome", type=int, default=5_000_000)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs/sample of the CPU baseline sample")
+    ap.add_argument("--mode", default="tiled", choices=["tiled", "direct"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import torch
+    from rufus_b200 import api, pipeline, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    trio = make_data(args.pairs, args.genome, args.seed, None if world == 1 else rank)
+    ctx = api.Context(local_rank)
+    ctx.use_stream(torch.cuda.current_stream().cuda_stream)
+    mode = api.MODE_TILED if args.mode == "tiled" else api.MODE_DIRECT
+
+    # resident inputs: per sample both mates as one [n_reads*150] stream; subject mates + quals for the pull
+    streams = []
+    for s in synth.SAMPLES:
+        s1, _, s2, _ = trio[s]
+        streams.append(torch.from_numpy(np.concatenate([s1, s2]).reshape(-1)).to(dev))
+    subj = tuple(torch.from_numpy(a.reshape(-1)).to(dev) for a in trio["Child"])
+    bases_per_step = sum(int(s.numel()) for s in streams)
+    # distinct k-mers per shard: genomic/world + ~7.5 error k-mers per read
+    est = int((2.2 * args.genome) / world + 16 * args.pairs)
+    pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, 150 * world, MINQ, THRESH,
+                                   mode=mode, rank=rank, world=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        r = pipe.step()
+    st0 = pipe.tables[0].stats()
+    log(f"rank {rank}: warm; mutant k-mers {r['n_mutant']}, pulled {r['n_kept']}, subject table {st0}")
+    n_occ = [t.stats()["occurrences"] for t in pipe.tables]
+
+    sampler = ClockSampler(local_rank)
+    ctx.profile_reset()
+    ctx.profile(True)
+    launches0 = ctx.launches
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        r = pipe.step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    value = bases_per_step * world / (ms_step / 1e3) / 1e9
+
+    # ---- roofline of the count stage (dominant): partition_kernel + tile_insert_kernel per sample push
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    kern = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in prof.items()}
+    if world == 1:
+        names = ["partition_kernel", "tile_insert_kernel"] if mode == api.MODE_TILED else ["count_direct_kernel"]
+    else:
+        names = ["extract_parts_kernel<count>", "extract_parts_kernel<scatter>", "partition_keys_kernel",
+                 "tile_insert_kernel"] if mode == api.MODE_TILED else ["extract_parts_kernel<count>",
+                                                                      "extract_parts_kernel<scatter>",
+                                                                      "insert_keys_kernel"]
+    count_ms = sum(kern[n]["ms_avg"] for n in names if n in kern)
+    n_occ_avg = float(np.mean(n_occ)) * (1 if world == 1 else 1.0)
+    bases_per_push = bases_per_step / 3
+    alg_bytes = bases_per_push + 16.0 * (n_occ_avg if world == 1 else bases_per_push * (READ_LEN - K + 1) / READ_LEN)
+    achieved = alg_bytes / (count_ms / 1e3) / 1e9 if count_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = sum(tj[n] for n in names)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "+".join(names),
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": count_ms,
+                "note": "one 'launch' = the count of one sample (150 Mbases): B + 16*n bytes (SURVEY 8d)"}
+
+    out = {"metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
+           "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "kernels_ms": kern,
+           "result": {"n_mutant_kmers": r["n_mutant"], "n_pulled_pairs_rank0": r["n_kept"]}}
+
+    # ---- e2e: same pass through the host-buffer C ABI (H2D + D2H inside the timed region)
+    if not args.no_e2e:
+        pipe.free()
+        del pipe
+        torch.cuda.empty_cache()
+        nl = np.full((2 * args.pairs, 1), 10, np.uint8)
+        host_streams = []
+        for s in synth.SAMPLES:
+            s1, _, s2, _ = trio[s]
+            a = torch.from_numpy(np.concatenate([np.concatenate([s1, s2]), nl], axis=1).reshape(-1)).pin_memory()
+            host_streams.append(a.numpy())
+        pairs_host = tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in trio["Child"])
+        tables = [api.KmerTable(ctx, K, True, est, mode) for _ in host_streams]
+        h2d = sum(a.size for a in host_streams) + sum(a.size for a in pairs_host) + 2 * 8 * (args.pairs + 1)
+        res = None
+        e2e_steps = max(3, args.steps // 2)
+        for i in range(2):
+            res = pipeline.host_step(ctx, K, host_streams, pairs_host, READ_LEN, est, MIN_COV, 150, MINQ, THRESH,
+                                     mode=mode, tables=tables)
+        barrier()
+        e0.record()
+        for i in range(e2e_steps):
+            res = pipeline.host_step(ctx, K, host_streams, pairs_host, READ_LEN, est, MIN_COV, 150, MINQ, THRESH,
+                                     mode=mode, tables=tables)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1) / e2e_steps
+        if world > 1:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        d2h = res["histo"].nbytes + res["hashlist"][0].nbytes + res["hashlist"][1].nbytes + res["keep"].nbytes
+        out["e2e"] = {"value": bases_per_step * world / (ms_e2e / 1e3) / 1e9, "unit": "Gbases/s",
+                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                      "steps": e2e_steps,
+                      "note": "rg_count_push/rg_histo/rg_subtract/rg_filter_pairs on pinned host buffers"
+                              + ("; ranks run independent replicas in the e2e leg" if world > 1 else "")}
+        for t in tables:
+            t.free()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        wd = tempfile.mkdtemp(prefix="rg_cpu_")
+        try:
+            dt, b, kind, info = cpu_reference_pass(trio, args.ref_pairs, wd, os.cpu_count() or 1)
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+        out["cpu_baseline"] = {"value": b / dt / 1e9, "unit": "Gbases/s", "cores": info["cores"], "kind": kind,
+                               "sample": f"first {args.ref_pairs} pairs/sample ({b / 1e6:.0f} Mbases) of the same "
+                                         f"workload, {dt:.1f}s wall, jellyfish -s 256M; hashlist {info['hashlist']}, "
+                                         f"pulled {info['pulled']}"}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+/* rufus_gpu.h — C ABI of librufus_gpu.so: the B200 (sm_100a) implementation of
+ * RUFUS's k-mer count -> subtract -> read-pull hot path.
+ *
+ * The reference has no linked API for this path: its boundary is the argv +
+ * file contract of the binaries bound at runRufus.sh:748-759.
+ * Each entry point below replaces the inner work of one of those binaries; the
+ * CLI shims under tools/ re-create their argv on top of this ABI, and
+ * INTEGRATION.md shows how runRufus.sh is pointed at them.
+ *
+ * Conventions: plain pointers and sizes only. Functions returning int give 0 on
+ * success and a negative code on failure; functions returning a pointer give
+ * NULL on failure; rg_last_error() (thread-local) holds the message. The caller
+ * owns every host buffer; the library owns device memory behind the opaque
+ * handles. There is NO CPU fallback: without a CUDA device rg_init fails.
+ *
+ * K-mer encodings (citations relative to /root/reference/):
+ *  - "jf key"   : Jellyfish packing, first base in the most-significant 2 bits of
+ *                 a 2k-bit integer, A0 C1 G2 T3 (mer_dna.hpp:46-63,330-354);
+ *                 canonical = min(forward, reverse complement) (mer_iterator.hpp:59).
+ *  - "rufus key": Util::HashToLong packing, base i at bits (2i,2i+1), A0 G1 C2 T3,
+ *                 any other byte == A (src/Util.cpp:51-84). Used by the read filter only.
+ */
+#ifndef RUFUS_GPU_H
+#define RUFUS_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rg_ctx rg_ctx;
+typedef struct rg_table rg_table;
+typedef struct rg_set rg_set;
+
+/* insert strategies for rg_count_begin */
+#define RG_MODE_AUTO 0
+#define RG_MODE_DIRECT 1 /* global-memory CAS/atomic insert straight from the extraction kernel */
+#define RG_MODE_TILED 2  /* radix partition by hash prefix -> shared-memory tile tables (TMA load/store) */
+
+#define RG_ERR_ARG (-1)
+#define RG_ERR_CUDA (-2)
+#define RG_ERR_FULL (-3)
+#define RG_ERR_IO (-4)
+#define RG_ERR_SMALL (-5) /* caller's output buffer too small; needed size is reported */
+
+const char* rg_last_error(void);
+const char* rg_version(void);
+
+/* ---- context: one per GPU / process ---------------------------------- */
+rg_ctx* rg_init(int device);
+void rg_shutdown(rg_ctx* ctx);
+/* Run on the caller's CUDA stream (a cudaStream_t passed as void*), e.g. torch's
+ * current stream, so the caller's events time our kernels. NULL = library stream. */
+int rg_set_stream(rg_ctx* ctx, void* cuda_stream);
+int rg_sync(rg_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t rg_launch_count(rg_ctx* ctx);
+
+/* Per-kernel device timing (CUDA events on the launch stream around each of our
+ * kernels). Off by default. rg_profile_get: total ms and launch count of the
+ * kernel called `name` since the last reset; returns 0 if known. */
+int rg_profile_enable(rg_ctx* ctx, int on);
+int rg_profile_reset(rg_ctx* ctx);
+int rg_profile_get(rg_ctx* ctx, const char* name, double* total_ms, uint64_t* n_launches);
+/* names of all profiled kernels, '\n'-separated, into buf (truncated to cap) */
+int rg_profile_names(rg_ctx* ctx, char* buf, uint64_t cap);
+
+/* plain device-memory helpers for callers that keep inputs resident in HBM */
+void* rg_dev_alloc(rg_ctx* ctx, uint64_t bytes);
+void rg_dev_free(rg_ctx* ctx, void* dptr);
+int rg_h2d(rg_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
+int rg_d2h(rg_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
+
+/* ---- K2/K3: k-mer extraction + counting -------------------------------
+ * replaces `jellyfish count -m k [-C] -s est ...` (count_main.cc:148-157,214-354;
+ * mer_iterator.hpp:61-89; large_hash_array.hpp:298-302,513-601). Counting is per
+ * occurrence; any byte outside ACGTacgt restarts the window. */
+rg_table* rg_count_begin(rg_ctx* ctx, int k, int canonical, uint64_t est_distinct, int mode);
+/* HOST stream of sequence bytes, reads delimited by any non-ACGT byte (e.g. the
+ * sequence lines of a FASTQ joined by '\n' — what mer_overlap_sequence_parser.hpp:179-207
+ * builds with 'N' separators). */
+int rg_count_push(rg_table* t, const char* host_stream, uint64_t n_bytes);
+/* HOST concatenated reads + offsets (n_reads+1 entries); no separators needed. */
+int rg_count_push_reads(rg_table* t, const char* host_seq, const uint64_t* host_offs, uint64_t n_reads);
+/* DEVICE-resident stream (16-byte aligned). read_stride > 0: a read starts every
+ * read_stride bytes (fixed-length reads without separators); 0: separators only. */
+int rg_count_push_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride);
+/* Finish counting: flush staged keys, resolve spills. */
+int rg_count_end(rg_table* t);
+void rg_table_free(rg_table* t);
+/* Empty the table for re-use (keeps its allocation and geometry). */
+int rg_table_clear(rg_table* t);
+/* Release the counting-time staging buffers (bucket slabs, H2D staging); the table stays usable. */
+int rg_table_trim(rg_table* t);
+/* n_distinct (count>=1), total occurrences, slots allocated */
+int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occurrences, uint64_t* n_slots);
+int rg_table_k(rg_table* t);
+int rg_table_canonical(rg_table* t);
+
+/* Multi-GPU building blocks (hash-prefix sharding): extract+partition
+ * into `n_parts` contiguous buckets by the top bits of the mixing hash, for an
+ * all-to-all between ranks, and insert received packed keys. All DEVICE pointers.
+ * part_offsets_dev: n_parts+1 uint64 written by the library. keys_out_dev needs
+ * room for one uint64 per window (n_bytes). */
+int rg_extract_partition_dev(rg_ctx* ctx, int k, int canonical, const char* dev_stream, uint64_t n_bytes,
+                             uint32_t read_stride, uint32_t n_parts, uint64_t* keys_out_dev,
+                             uint64_t* part_offsets_dev);
+/* which partition (0..n_parts-1) owns a jf key — same function the kernels use */
+uint32_t rg_key_partition(uint64_t jf_key, uint32_t n_parts);
+int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_keys);
+/* restrict a table to the keys of shard `part` of `n_parts` (tile numbering is global) */
+int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts);
+
+/* ---- H1: histogram ------------------------------------------------------
+ * replaces `jellyfish histo -l low -h high -i 1` (histo_main.cc:34-44,64-84) over
+ * the entries a `-L min_count` dump would hold. out (HOST) has high+2-base rows
+ * where base = (low<=1 ? 0 : low-1); see rg_histo_rows. */
+uint64_t rg_histo_rows(uint64_t low, uint64_t high);
+int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint64_t* out_host);
+
+/* ---- K5: dump -----------------------------------------------------------
+ * entries with min_count <= count <= max_count (sorted_dumper.hpp:94) as jf keys +
+ * uint32 counts (binary_dumper.hpp:44-48), unordered. Returns n written, or
+ * RG_ERR_SMALL with *needed set when cap is too small. */
+int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* keys_host, uint32_t* counts_host,
+                uint64_t cap, uint64_t* needed);
+/* load (key,count) records — e.g. a parsed .Jhash — into a device table */
+rg_table* rg_table_from_pairs(rg_ctx* ctx, int k, int canonical, const uint64_t* keys_host,
+                              const uint32_t* counts_host, uint64_t n);
+/* `jellyfish query` (query_main.cc:44-51; binary_dumper.hpp:156-197): count of each jf key,
+ * 0 when absent or below min_count. Host in/out. */
+int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_count, uint32_t* counts_host);
+
+/* ---- S1: subtraction ----------------------------------------------------
+ * modified `jellyfish merge` (src/modifiedJellyfish/jellyfish/merge_files.cc:86-154):
+ * every key present (count >= mins[i]) in EXACTLY ONE table i with count >= floor.
+ * which_host (optional) receives the table index of each emitted key. */
+int64_t rg_merge_unique(rg_table* const* tabs, const uint64_t* mins, int n_tabs, uint64_t floor,
+                        uint64_t* keys_host, uint32_t* counts_host, int32_t* which_host, uint64_t cap,
+                        uint64_t* needed);
+/* fused merge + CheckJellyHashList.sh:12 (query subject | awk >=min | awk <=max):
+ * { (x, c_S(x)) : c_S(x) >= max(subj_min, floor), x absent (count < other_min[i]) from
+ * every other table, min_cov <= c_S(x) <= max_cov }. One scan of the subject table. */
+int64_t rg_subtract(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
+                    int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_host,
+                    uint32_t* counts_host, uint64_t cap, uint64_t* needed);
+/* same, result left on the device as an rg_set-ready list; returns n (device-timed path) */
+int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
+                        int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_dev,
+                        uint32_t* counts_dev, uint64_t cap);
+
+/* ---- F1/F2: read pull ---------------------------------------------------
+ * RUFUS.Filter (src/RUFUS.Filter.cpp:121-143,196-277) and RUFUS.Filter.single
+ * (src/RUFUS.Filter.ss.cpp:100-121,164-201). */
+uint64_t rg_rufus_pack(const char* s, int len);            /* Util.cpp:51-84 */
+int rg_rufus_revcomp(const char* s, int len, char* out);   /* Util.cpp:187-210; returns new length */
+/* the Mutations set from HashList text lines; paired=1 uses RUFUS.Filter.cpp's
+ * column rules (' ' first), 0 RUFUS.Filter.ss.cpp's ('\t' first) */
+rg_set* rg_set_from_hashlist_text(rg_ctx* ctx, const char* text, uint64_t n_bytes, int k, int paired);
+rg_set* rg_set_from_rufus_keys(rg_ctx* ctx, const uint64_t* rufus_keys_host, uint64_t n, int k);
+/* from canonical jf keys (e.g. rg_subtract output): inserts k-mer and reverse complement */
+rg_set* rg_set_from_jf_keys(rg_ctx* ctx, const uint64_t* jf_keys_host, uint64_t n, int k);
+rg_set* rg_set_from_jf_keys_dev(rg_ctx* ctx, const uint64_t* jf_keys_dev, uint64_t n, int k);
+uint64_t rg_set_size(rg_set* s);
+void rg_set_free(rg_set* s);
+/* per-read hit counts; all DEVICE pointers. skip_last=1: paired tool's `i < length()-1` bound */
+int rg_filter_hits_dev(rg_set* s, const char* seq_dev, const char* qual_dev, const uint64_t* offs_dev,
+                       uint64_t n_reads, uint64_t n_bytes, int minq, int skip_last, int32_t* hits_dev);
+/* fixed-length reads (every read read_len bytes, no offsets array needed) */
+int rg_filter_hits_fixed_dev(rg_set* s, const char* seq_dev, const char* qual_dev, uint32_t read_len,
+                             uint64_t n_reads, int minq, int skip_last, int32_t* hits_dev);
+/* paired pull on DEVICE-resident fixed-length mates: hits per mate + keep mask, all device */
+int rg_filter_pairs_fixed_dev(rg_set* s, const char* s1_dev, const char* q1_dev, const char* s2_dev,
+                              const char* q2_dev, uint32_t read_len, uint64_t n_pairs, int minq, int thresh,
+                              int32_t* hits1_dev, int32_t* hits2_dev, uint8_t* keep_dev);
+/* keep[i] = hits(mate1)>=thresh || hits(mate2)>=thresh; HOST buffers */
+int rg_filter_pairs(rg_set* s, const char* s1, const char* q1, const uint64_t* o1, const char* s2, const char* q2,
+                    const uint64_t* o2, uint64_t n_pairs, int minq, int thresh, uint8_t* keep_host);
+/* single-end: hits per read, last base included; HOST buffers */
+int rg_filter_single(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint64_t n_reads,
+                     int minq, int32_t* hits_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1005 @@
+// rg_api.cu — the C ABI of librufus_gpu.so (include/rufus_gpu.h): context,
+// table lifetime/growth, host<->device staging. No CPU compute path exists here:
+// every entry point ends in a kernel launch from rg_count.cu / rg_ops.cu / rg_filter.cu.
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "rg_internal.cuh"
+
+static thread_local std::string g_err;
+void rg_set_error(const std::string& msg) { g_err = msg; }
+
+extern "C" {
+
+const char* rg_last_error(void) { return g_err.c_str(); }
+const char* rg_version(void) { return "rufus_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------
+rg_ctx* rg_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    rg_set_error(std::string("rg_init: no CUDA device (") + cudaGetErrorString(e) +
+                 "); librufus_gpu has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    rg_set_error("rg_init: bad device index");
+    return nullptr;
+  }
+  RG_CUDA_OKP(cudaSetDevice(device));
+  rg_ctx* ctx = new rg_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  RG_CUDA_OKP(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  RG_CUDA_OKP(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  RG_CUDA_OKP(cudaMallocHost(&ctx->h_scratch, 256 * sizeof(uint64_t)));
+  RG_CUDA_OKP(cudaMalloc(&ctx->d_scratch, 256 * sizeof(uint64_t)));
+  return ctx;
+}
+
+void rg_shutdown(rg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFreeHost(ctx->h_scratch);
+  cudaFree(ctx->d_scratch);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int rg_set_stream(rg_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RG_ERR_ARG;
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return 0;
+}
+
+int rg_sync(rg_ctx* ctx) {
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+uint64_t rg_launch_count(rg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static void prof_collect(rg_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->prof) {
+    for (auto& ev : kv.second.pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+        kv.second.ms += ms;
+        kv.second.n++;
+      }
+      ctx->event_pool.push_back(ev.first);
+      ctx->event_pool.push_back(ev.second);
+    }
+    kv.second.pending.clear();
+  }
+}
+
+int rg_profile_enable(rg_ctx* ctx, int on) {
+  if (!ctx) return RG_ERR_ARG;
+  prof_collect(ctx);
+  ctx->profiling = on != 0;
+  return 0;
+}
+
+int rg_profile_reset(rg_ctx* ctx) {
+  if (!ctx) return RG_ERR_ARG;
+  prof_collect(ctx);
+  ctx->prof.clear();
+  return 0;
+}
+
+int rg_profile_get(rg_ctx* ctx, const char* name, double* total_ms, uint64_t* n_launches) {
+  if (!ctx || !name) return RG_ERR_ARG;
+  prof_collect(ctx);
+  auto it = ctx->prof.find(name);
+  if (it == ctx->prof.end()) return RG_ERR_ARG;
+  if (total_ms) *total_ms = it->second.ms;
+  if (n_launches) *n_launches = it->second.n;
+  return 0;
+}
+
+int rg_profile_names(rg_ctx* ctx, char* buf, uint64_t cap) {
+  if (!ctx || !buf || cap == 0) return RG_ERR_ARG;
+  std::string s;
+  for (auto& kv : ctx->prof) s += kv.first + "\n";
+  const uint64_t n = std::min<uint64_t>(cap - 1, s.size());
+  memcpy(buf, s.data(), n);
+  buf[n] = 0;
+  return 0;
+}
+
+void* rg_dev_alloc(rg_ctx* ctx, uint64_t bytes) {
+  void* p = nullptr;
+  cudaSetDevice(ctx->device);
+  RG_CUDA_OKP(cudaMalloc(&p, bytes ? bytes : 16));
+  return p;
+}
+void rg_dev_free(rg_ctx* ctx, void* p) {
+  if (p) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+  }
+}
+int rg_h2d(rg_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  RG_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+int rg_d2h(rg_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  RG_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// table internals
+// ---------------------------------------------------------------------------
+static int read_scalars(rg_ctx* ctx, const uint64_t* d, int n, uint64_t* out) {
+  RG_CUDA_OK(cudaMemcpyAsync(ctx->h_scratch, d, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) out[i] = ctx->h_scratch[i];
+  return 0;
+}
+
+static int table_alloc_tiles(rg_table* t, uint32_t n_tiles) {
+  rg_ctx* ctx = t->ctx;
+  const uint64_t slots = (uint64_t)n_tiles << RG_TILE_BITS;
+  RG_CUDA_OK(cudaMalloc(&t->keys, slots * 8));
+  RG_CUDA_OK(cudaMalloc(&t->counts, slots * 4));
+  RG_CUDA_OK(cudaMemsetAsync(t->keys, 0xFF, slots * 8, ctx->stream));
+  RG_CUDA_OK(cudaMemsetAsync(t->counts, 0, slots * 4, ctx->stream));
+  t->n_tiles = n_tiles;
+  t->n_tiles_global = n_tiles * t->shard_parts;
+  t->tile_first = n_tiles * t->shard_part;
+  return 0;
+}
+
+static uint32_t tiles_for(uint64_t est_distinct) {
+  // aim for <= 50 % load
+  uint64_t n = (est_distinct * 2 + RG_TILE_SLOTS - 1) >> RG_TILE_BITS;
+  if (n < 1) n = 1;
+  if (n > (1u << 24)) n = 1u << 24;
+  return (uint32_t)n;
+}
+
+// double the tile count and re-insert every (key,count)
+static int table_grow(rg_table* t) {
+  rg_ctx* ctx = t->ctx;
+  uint64_t* old_keys = t->keys;
+  uint32_t* old_counts = t->counts;
+  const uint64_t old_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  t->keys = nullptr;
+  t->counts = nullptr;
+  int rc = table_alloc_tiles(t, t->n_tiles * 2);
+  if (rc) return rc;
+  // bucket staging is sized per tile count: drop it, it is rebuilt on the next push
+  if (t->part_cursor) { cudaFree(t->part_cursor); t->part_cursor = nullptr; }
+  if (t->part_keys) { cudaFree(t->part_keys); t->part_keys = nullptr; t->part_cap = 0; }
+  rc = rg_launch_rehash(t, old_keys, old_counts, old_slots);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(old_keys);
+  cudaFree(old_counts);
+  return 0;
+}
+
+// after a push: resolve keys that found their tile (or bucket) full
+static int table_resolve_spill(rg_table* t) {
+  rg_ctx* ctx = t->ctx;
+  for (int round = 0; round < 8; ++round) {
+    uint64_t st[3];
+    int rc = read_scalars(ctx, t->d_status, 3, st);
+    if (rc) return rc;
+    if (st[1] != 0) {
+      rg_set_error("count: " + std::to_string(st[1]) + " keys do not belong to this table's shard");
+      return RG_ERR_ARG;
+    }
+    if (st[2] != 0) {
+      rg_set_error("count: rehash overflow");
+      return RG_ERR_FULL;
+    }
+    if (st[0] == 0) return 0;
+    if (st[0] > t->spill_cap) {
+      rg_set_error("count: table full and spill list overflowed (" + std::to_string(st[0]) +
+                   " keys); raise est_distinct");
+      return RG_ERR_FULL;
+    }
+    // move the spill aside, clear the counter, then make room when the tiles themselves were full
+    uint64_t* tmp = nullptr;
+    RG_CUDA_OK(cudaMalloc(&tmp, st[0] * 8));
+    RG_CUDA_OK(cudaMemcpyAsync(tmp, t->spill, st[0] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, 3 * sizeof(uint64_t), ctx->stream));
+    if (round > 0) {
+      rc = table_grow(t);
+      if (rc) { cudaFree(tmp); return rc; }
+    }
+    rc = rg_launch_insert_keys(t, tmp, st[0], nullptr);
+    RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    if (rc) return rc;
+  }
+  rg_set_error("count: could not resolve spill after growing 7 times");
+  return RG_ERR_FULL;
+}
+
+static int ensure_stage(rg_table* t, uint64_t bytes) {
+  if (t->stage_bytes >= bytes) return 0;
+  if (t->stage) {
+    RG_CUDA_OK(cudaStreamSynchronize(t->ctx->stream));
+    cudaFree(t->stage);
+    t->stage = nullptr;
+  }
+  const uint64_t want = (bytes + (1 << 20)) & ~((1ull << 20) - 1);
+  RG_CUDA_OK(cudaMalloc(&t->stage, want));
+  t->stage_bytes = want;
+  return 0;
+}
+
+// (re)size the per-tile bucket slabs for a push of at most n_keys keys and zero the cursors
+static int prepare_buckets(rg_table* t, uint64_t n_keys) {
+  rg_ctx* ctx = t->ctx;
+  // bucket capacity: mean keys per tile + 25 % + slack; overflow goes to the spill list
+  const uint64_t mean = n_keys / t->n_tiles + 1;
+  uint64_t cap = mean + mean / 4 + 1024;
+  cap = (cap + 1) & ~1ull;  // keep slabs 16-byte aligned
+  if (!t->part_cursor) RG_CUDA_OK(cudaMalloc(&t->part_cursor, (uint64_t)t->n_tiles * sizeof(uint32_t)));
+  if (t->part_cap < cap * t->n_tiles) {
+    if (t->part_keys) {
+      RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(t->part_keys);
+      t->part_keys = nullptr;
+    }
+    RG_CUDA_OK(cudaMalloc(&t->part_keys, cap * t->n_tiles * 8));
+    t->part_cap = cap * t->n_tiles;
+  }
+  t->bucket_cap = (uint32_t)(t->part_cap / t->n_tiles);
+  RG_CUDA_OK(cudaMemsetAsync(t->part_cursor, 0, (uint64_t)t->n_tiles * sizeof(uint32_t), ctx->stream));
+  return 0;
+}
+
+static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
+                         const uint32_t* brk) {
+  rg_ctx* ctx = t->ctx;
+  if (n_bytes == 0) return 0;
+  if (((uintptr_t)dev_stream & 15) != 0) {
+    rg_set_error("count: device stream must be 16-byte aligned");
+    return RG_ERR_ARG;
+  }
+  ExtractParams ep;
+  ep.stream = dev_stream;
+  ep.n_bytes = n_bytes;
+  ep.brk = brk;
+  ep.read_stride = read_stride;
+  ep.k = t->k;
+  ep.canonical = t->canonical;
+  int rc;
+  if (t->mode == RG_MODE_TILED) {
+    rc = prepare_buckets(t, n_bytes);
+    if (rc) return rc;
+    rc = rg_launch_partition(t, ep);
+    if (rc) return rc;
+    rc = rg_launch_tile_insert(t);
+    if (rc) return rc;
+  } else {
+    rc = rg_launch_count_direct(t, ep);
+    if (rc) return rc;
+  }
+  t->tiles_dirty = true;
+  return table_resolve_spill(t);
+}
+
+extern "C" {
+
+rg_table* rg_count_begin(rg_ctx* ctx, int k, int canonical, uint64_t est_distinct, int mode) {
+  if (!ctx) {
+    rg_set_error("rg_count_begin: null context");
+    return nullptr;
+  }
+  if (k < 1 || k > 32 || (!canonical && k == 32)) {
+    rg_set_error("rg_count_begin: k must be 1..32 (1..31 when not canonical)");
+    return nullptr;
+  }
+  cudaSetDevice(ctx->device);
+  rg_table* t = new rg_table();
+  t->ctx = ctx;
+  t->k = k;
+  t->canonical = canonical ? 1 : 0;
+  t->mode = (mode == RG_MODE_AUTO) ? RG_MODE_TILED : mode;
+  if (est_distinct == 0) est_distinct = 1ull << 24;
+  uint32_t n_tiles = tiles_for(est_distinct);
+  // tiled insert runs one CTA per tile: make the grid a whole number of waves over the SMs
+  if (t->mode == RG_MODE_TILED && n_tiles > (uint32_t)ctx->sm_count)
+    n_tiles = (n_tiles + ctx->sm_count - 1) / ctx->sm_count * ctx->sm_count;
+  if (table_alloc_tiles(t, n_tiles) != 0) {
+    delete t;
+    return nullptr;
+  }
+  t->spill_cap = 1ull << 22;
+  if (cudaMalloc(&t->spill, t->spill_cap * 8) != cudaSuccess || cudaMalloc(&t->d_status, 8 * sizeof(uint64_t)) != cudaSuccess) {
+    rg_set_error("rg_count_begin: out of device memory");
+    rg_table_free(t);
+    return nullptr;
+  }
+  cudaMemsetAsync(t->d_status, 0, 8 * sizeof(uint64_t), ctx->stream);
+  return t;
+}
+
+int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts) {
+  if (!t || n_parts == 0 || part >= n_parts || t->tiles_dirty) {
+    rg_set_error("rg_table_set_shard: bad arguments (must be called before the first push)");
+    return RG_ERR_ARG;
+  }
+  t->shard_part = part;
+  t->shard_parts = n_parts;
+  t->n_tiles_global = t->n_tiles * n_parts;
+  t->tile_first = t->n_tiles * part;
+  return 0;
+}
+
+int rg_count_push_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride) {
+  if (!t) return RG_ERR_ARG;
+  return push_dev_impl(t, dev_stream, n_bytes, read_stride, nullptr);
+}
+
+int rg_count_push(rg_table* t, const char* host_stream, uint64_t n_bytes) {
+  if (!t) return RG_ERR_ARG;
+  if (n_bytes == 0) return 0;
+  int rc = ensure_stage(t, n_bytes);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaMemcpyAsync(t->stage, host_stream, n_bytes, cudaMemcpyHostToDevice, t->ctx->stream));
+  return push_dev_impl(t, reinterpret_cast<const char*>(t->stage), n_bytes, 0, nullptr);
+}
+
+int rg_count_push_reads(rg_table* t, const char* host_seq, const uint64_t* host_offs, uint64_t n_reads) {
+  if (!t) return RG_ERR_ARG;
+  if (n_reads == 0) return 0;
+  rg_ctx* ctx = t->ctx;
+  const uint64_t base = host_offs[0];
+  const uint64_t n_bytes = host_offs[n_reads] - base;
+  if (n_bytes == 0) return 0;
+  int rc = ensure_stage(t, n_bytes);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaMemcpyAsync(t->stage, host_seq + base, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (t->d_offs_cap < n_reads + 1) {
+    if (t->d_offs) { RG_CUDA_OK(cudaStreamSynchronize(ctx->stream)); cudaFree(t->d_offs); t->d_offs = nullptr; }
+    RG_CUDA_OK(cudaMalloc(&t->d_offs, (n_reads + 1) * 8));
+    t->d_offs_cap = n_reads + 1;
+  }
+  const uint64_t* offs = host_offs;
+  std::vector<uint64_t> rebased;
+  if (base != 0) {
+    rebased.resize(n_reads + 1);
+    for (uint64_t i = 0; i <= n_reads; ++i) rebased[i] = host_offs[i] - base;
+    offs = rebased.data();
+  }
+  RG_CUDA_OK(cudaMemcpyAsync(t->d_offs, offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // `rebased` must outlive the copy
+  const uint64_t words = n_bytes / 32 + 2;
+  if (t->brk_words < words) {
+    if (t->brk) cudaFree(t->brk);
+    RG_CUDA_OK(cudaMalloc(&t->brk, words * 4));
+    t->brk_words = words;
+  }
+  RG_CUDA_OK(cudaMemsetAsync(t->brk, 0, words * 4, ctx->stream));
+  // empty reads at the very end would mark position n_bytes: harmless (bitmap has slack)
+  rc = rg_launch_mark_breaks(ctx, t->d_offs, n_reads, t->brk);
+  if (rc) return rc;
+  return push_dev_impl(t, reinterpret_cast<const char*>(t->stage), n_bytes, 0, t->brk);
+}
+
+int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_keys) {
+  if (!t) return RG_ERR_ARG;
+  int rc;
+  if (t->mode == RG_MODE_TILED && n_keys >= (uint64_t)t->n_tiles * 64) {
+    rc = prepare_buckets(t, n_keys);
+    if (rc == 0) rc = rg_launch_partition_keys(t, dev_keys, n_keys);
+    if (rc == 0) rc = rg_launch_tile_insert(t);
+  } else {
+    rc = rg_launch_insert_keys(t, dev_keys, n_keys, nullptr);
+  }
+  if (rc) return rc;
+  t->tiles_dirty = true;
+  return table_resolve_spill(t);
+}
+
+int rg_count_end(rg_table* t) {
+  if (!t) return RG_ERR_ARG;
+  int rc = table_resolve_spill(t);
+  if (rc) return rc;
+  return 0;
+}
+
+int rg_table_trim(rg_table* t) {
+  if (!t) return RG_ERR_ARG;
+  RG_CUDA_OK(cudaStreamSynchronize(t->ctx->stream));
+  if (t->part_keys) { cudaFree(t->part_keys); t->part_keys = nullptr; t->part_cap = 0; }
+  if (t->stage) { cudaFree(t->stage); t->stage = nullptr; t->stage_bytes = 0; }
+  if (t->brk) { cudaFree(t->brk); t->brk = nullptr; t->brk_words = 0; }
+  if (t->d_offs) { cudaFree(t->d_offs); t->d_offs = nullptr; t->d_offs_cap = 0; }
+  return 0;
+}
+
+int rg_table_clear(rg_table* t) {
+  if (!t) return RG_ERR_ARG;
+  rg_ctx* ctx = t->ctx;
+  const uint64_t slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  // the tiled insert rewrites every tile of an empty table, so only the direct path needs the memset
+  if (t->mode != RG_MODE_TILED) {
+    RG_CUDA_OK(cudaMemsetAsync(t->keys, 0xFF, slots * 8, ctx->stream));
+    RG_CUDA_OK(cudaMemsetAsync(t->counts, 0, slots * 4, ctx->stream));
+  }
+  RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, 8 * sizeof(uint64_t), ctx->stream));
+  t->tiles_dirty = false;
+  return 0;
+}
+
+void rg_table_free(rg_table* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  cudaFree(t->keys);
+  cudaFree(t->counts);
+  cudaFree(t->d_status);
+  cudaFree(t->spill);
+  cudaFree(t->part_keys);
+  cudaFree(t->part_cursor);
+  cudaFree(t->stage);
+  cudaFree(t->brk);
+  cudaFree(t->d_offs);
+  delete t;
+}
+
+int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occ, uint64_t* n_slots) {
+  if (!t) return RG_ERR_ARG;
+  int rc = rg_launch_stats(t, t->ctx->d_scratch);
+  if (rc) return rc;
+  uint64_t v[2];
+  rc = read_scalars(t->ctx, t->ctx->d_scratch, 2, v);
+  if (rc) return rc;
+  if (n_distinct) *n_distinct = v[0];
+  if (n_occ) *n_occ = v[1];
+  if (n_slots) *n_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  return 0;
+}
+
+int rg_table_k(rg_table* t) { return t ? t->k : 0; }
+int rg_table_canonical(rg_table* t) { return t ? t->canonical : 0; }
+
+uint32_t rg_key_partition(uint64_t jf_key, uint32_t n_parts) { return rg_tile_of(rg_mix64(jf_key), n_parts); }
+
+int rg_extract_partition_dev(rg_ctx* ctx, int k, int canonical, const char* dev_stream, uint64_t n_bytes,
+                             uint32_t read_stride, uint32_t n_parts, uint64_t* keys_out_dev,
+                             uint64_t* part_offsets_dev) {
+  if (!ctx || k < 1 || k > 32) return RG_ERR_ARG;
+  ExtractParams ep;
+  ep.stream = dev_stream;
+  ep.n_bytes = n_bytes;
+  ep.brk = nullptr;
+  ep.read_stride = read_stride;
+  ep.k = k;
+  ep.canonical = canonical;
+  return rg_launch_extract_partition(ctx, ep, n_parts, keys_out_dev, part_offsets_dev, ctx->d_scratch + 64);
+}
+
+// ---- histo ----------------------------------------------------------------
+static inline uint64_t histo_base(uint64_t low) { return 1 >= low ? 0 : low - 1; }   // histo_main.cc:64
+uint64_t rg_histo_rows(uint64_t low, uint64_t high) { return (high + 1) + 1 - histo_base(low); }
+
+int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint64_t* out_host) {
+  if (!t || high < low) {
+    rg_set_error("rg_histo: High count value must be >= to low count value");
+    return RG_ERR_ARG;
+  }
+  rg_ctx* ctx = t->ctx;
+  const uint64_t nb = rg_histo_rows(low, high);
+  uint64_t* d_out = nullptr;
+  RG_CUDA_OK(cudaMalloc(&d_out, nb * 8));
+  int rc = rg_launch_histo(t, min_count, histo_base(low), nb, d_out);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d_out, nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { rg_set_error(cudaGetErrorString(e)); rc = RG_ERR_CUDA; }
+  }
+  cudaFree(d_out);
+  return rc;
+}
+
+// ---- dump / query -----------------------------------------------------------
+static int64_t copy_out(rg_ctx* ctx, uint64_t n, const uint64_t* d_keys, const uint32_t* d_counts, uint64_t* keys_host,
+                        uint32_t* counts_host) {
+  if (n) {
+    RG_CUDA_OK(cudaMemcpyAsync(keys_host, d_keys, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RG_CUDA_OK(cudaMemcpyAsync(counts_host, d_counts, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  return (int64_t)n;
+}
+
+int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* keys_host, uint32_t* counts_host,
+                uint64_t cap, uint64_t* needed) {
+  if (!t) return RG_ERR_ARG;
+  rg_ctx* ctx = t->ctx;
+  uint64_t* d_keys = nullptr;
+  uint32_t* d_counts = nullptr;
+  RG_CUDA_OK(cudaMalloc(&d_keys, (cap ? cap : 1) * 8));
+  RG_CUDA_OK(cudaMalloc(&d_counts, (cap ? cap : 1) * 4));
+  int64_t rc = rg_launch_dump(t, min_count ? min_count : 1, max_count, d_keys, d_counts, cap, ctx->d_scratch);
+  uint64_t n = 0;
+  if (rc == 0) rc = read_scalars(ctx, ctx->d_scratch, 1, &n);
+  if (rc == 0) {
+    if (needed) *needed = n;
+    if (n > cap) {
+      rg_set_error("rg_dump: output buffer too small");
+      rc = RG_ERR_SMALL;
+    } else {
+      rc = copy_out(ctx, n, d_keys, d_counts, keys_host, counts_host);
+    }
+  }
+  cudaFree(d_keys);
+  cudaFree(d_counts);
+  return rc;
+}
+
+rg_table* rg_table_from_pairs(rg_ctx* ctx, int k, int canonical, const uint64_t* keys_host,
+                              const uint32_t* counts_host, uint64_t n) {
+  rg_table* t = rg_count_begin(ctx, k, canonical, n ? n : 1, RG_MODE_DIRECT);
+  if (!t) return nullptr;
+  if (n) {
+    uint64_t* dk = nullptr;
+    uint32_t* dc = nullptr;
+    if (cudaMalloc(&dk, n * 8) != cudaSuccess || cudaMalloc(&dc, n * 4) != cudaSuccess) {
+      rg_set_error("rg_table_from_pairs: out of device memory");
+      cudaFree(dk);
+      rg_table_free(t);
+      return nullptr;
+    }
+    cudaMemcpyAsync(dk, keys_host, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(dc, counts_host, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = rg_launch_insert_keys(t, dk, n, dc);
+    t->tiles_dirty = true;
+    if (rc == 0) rc = rg_count_end(t);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(dk);
+    cudaFree(dc);
+    if (rc) {
+      rg_table_free(t);
+      return nullptr;
+    }
+  }
+  return t;
+}
+
+int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_count, uint32_t* counts_host) {
+  if (!t) return RG_ERR_ARG;
+  if (n == 0) return 0;
+  rg_ctx* ctx = t->ctx;
+  uint64_t* dk = nullptr;
+  uint32_t* dc = nullptr;
+  RG_CUDA_OK(cudaMalloc(&dk, n * 8));
+  RG_CUDA_OK(cudaMalloc(&dc, n * 4));
+  int rc = RG_ERR_CUDA;
+  if (cudaMemcpyAsync(dk, keys_host, n * 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess) {
+    rc = rg_launch_query(t, dk, n, min_count, dc);
+    if (rc == 0 && (cudaMemcpyAsync(counts_host, dc, n * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                    cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
+      rg_set_error("rg_query: copy failed");
+      rc = RG_ERR_CUDA;
+    }
+  }
+  cudaFree(dk);
+  cudaFree(dc);
+  return rc;
+}
+
+// ---- subtraction ------------------------------------------------------------
+static int fill_others(OtherTables& ot, rg_table* const* others, const uint64_t* other_min, int n_others, int k) {
+  if (n_others < 0 || n_others > 16) {
+    rg_set_error("subtract: at most 16 control/exclude tables");
+    return RG_ERR_ARG;
+  }
+  ot.n = n_others;
+  for (int i = 0; i < n_others; ++i) {
+    if (!others[i] || others[i]->k != k) {
+      rg_set_error("subtract: tables must share k");
+      return RG_ERR_ARG;
+    }
+    ot.tv[i] = rg_view(others[i]);
+    uint64_t m = other_min ? other_min[i] : 1;
+    ot.min_count[i] = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(m, 1), 0xFFFFFFFFull);
+  }
+  return 0;
+}
+
+int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
+                        int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_dev,
+                        uint32_t* counts_dev, uint64_t cap) {
+  if (!subj) return RG_ERR_ARG;
+  rg_ctx* ctx = subj->ctx;
+  OtherTables ot;
+  int rc = fill_others(ot, others, other_min, n_others, subj->k);
+  if (rc) return rc;
+  // candidates: c >= subj_min (in the subject .Jhash), c >= floor (merge_files.cc:149), min_cov <= c <= max_cov
+  uint64_t lo = std::max<uint64_t>(std::max<uint64_t>(subj_min, floor), 1);
+  if (min_cov > 0) lo = std::max<uint64_t>(lo, (uint64_t)min_cov);
+  if (max_cov < 0) {   // nothing can pass `count <= max`
+    return 0;
+  }
+  const uint64_t hi = (uint64_t)max_cov;
+  rc = rg_launch_subtract(subj, lo, hi, ot, keys_dev, counts_dev, cap, ctx->d_scratch);
+  if (rc) return rc;
+  uint64_t n = 0;
+  rc = read_scalars(ctx, ctx->d_scratch, 1, &n);
+  if (rc) return rc;
+  if (n > cap) {
+    rg_set_error("rg_subtract: output buffer too small, need " + std::to_string(n));
+    ctx->h_scratch[8] = n;
+    return RG_ERR_SMALL;
+  }
+  return (int64_t)n;
+}
+
+int64_t rg_subtract(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
+                    int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_host,
+                    uint32_t* counts_host, uint64_t cap, uint64_t* needed) {
+  if (!subj) return RG_ERR_ARG;
+  rg_ctx* ctx = subj->ctx;
+  uint64_t* dk = nullptr;
+  uint32_t* dc = nullptr;
+  RG_CUDA_OK(cudaMalloc(&dk, (cap ? cap : 1) * 8));
+  RG_CUDA_OK(cudaMalloc(&dc, (cap ? cap : 1) * 4));
+  int64_t n = rg_subtract_dev(subj, subj_min, others, other_min, n_others, floor, min_cov, max_cov, dk, dc, cap);
+  if (n == RG_ERR_SMALL && needed) *needed = ctx->h_scratch[8];
+  if (n >= 0) {
+    if (needed) *needed = (uint64_t)n;
+    n = copy_out(ctx, (uint64_t)n, dk, dc, keys_host, counts_host);
+  }
+  cudaFree(dk);
+  cudaFree(dc);
+  return n;
+}
+
+int64_t rg_merge_unique(rg_table* const* tabs, const uint64_t* mins, int n_tabs, uint64_t floor, uint64_t* keys_host,
+                        uint32_t* counts_host, int32_t* which_host, uint64_t cap, uint64_t* needed) {
+  if (!tabs || n_tabs < 1 || n_tabs > 17) {
+    rg_set_error("rg_merge_unique: 1..17 tables");
+    return RG_ERR_ARG;
+  }
+  uint64_t total = 0;
+  bool small = false;
+  for (int i = 0; i < n_tabs; ++i) {
+    std::vector<rg_table*> others;
+    std::vector<uint64_t> omin;
+    for (int j = 0; j < n_tabs; ++j)
+      if (j != i) {
+        others.push_back(tabs[j]);
+        omin.push_back(mins ? mins[j] : 1);
+      }
+    uint64_t need_i = 0;
+    const uint64_t room = total < cap ? cap - total : 0;
+    int64_t n = rg_subtract(tabs[i], mins ? mins[i] : 1, others.data(), omin.data(), (int)others.size(), floor, 0,
+                            (int64_t)0xFFFFFFFFll, keys_host + std::min(total, cap),
+                            counts_host + std::min(total, cap), room, &need_i);
+    if (n == RG_ERR_SMALL) {
+      small = true;
+      total += need_i;
+      continue;
+    }
+    if (n < 0) return n;
+    if (which_host && !small)
+      for (int64_t q = 0; q < n; ++q) which_host[total + q] = i;
+    total += (uint64_t)n;
+  }
+  if (needed) *needed = total;
+  if (small) {
+    rg_set_error("rg_merge_unique: output buffer too small");
+    return RG_ERR_SMALL;
+  }
+  return (int64_t)total;
+}
+
+// ---- filter -----------------------------------------------------------------
+uint64_t rg_rufus_pack(const char* s, int len) {
+  uint64_t v = 0;
+  for (int i = 0; i < len && i < 32; ++i) {
+    uint64_t c = 0;
+    if (s[i] == 'C') c = 2;
+    else if (s[i] == 'G') c = 1;
+    else if (s[i] == 'T') c = 3;
+    v |= c << (2 * i);
+  }
+  return v;
+}
+
+int rg_rufus_revcomp(const char* s, int len, char* out) {
+  int n = 0;
+  for (int i = len - 1; i >= 0; --i) {
+    const char c = s[i];
+    if (c == 'A') out[n++] = 'T';
+    else if (c == 'C') out[n++] = 'G';
+    else if (c == 'G') out[n++] = 'C';
+    else if (c == 'T') out[n++] = 'A';
+    else if (c == 'N') out[n++] = 'N';
+  }
+  return n;
+}
+
+static rg_set* set_alloc(rg_ctx* ctx, uint64_t n_vals, int k) {
+  if (!ctx || k < 1 || k > 32) {
+    rg_set_error("rg_set: k must be 1..32");
+    return nullptr;
+  }
+  cudaSetDevice(ctx->device);
+  rg_set* s = new rg_set();
+  s->ctx = ctx;
+  s->k = k;
+  uint64_t slots = 1024;
+  while (slots < n_vals * 2 + 2) slots <<= 1;
+  if (slots > (1ull << 31)) {
+    rg_set_error("rg_set: too many k-mers");
+    delete s;
+    return nullptr;
+  }
+  s->slots = (uint32_t)slots;
+  if (cudaMalloc(&s->table, slots * 8) != cudaSuccess || cudaMalloc(&s->bitmap, RG_SET_BITMAP_BITS / 8) != cudaSuccess) {
+    rg_set_error("rg_set: out of device memory");
+    cudaFree(s->table);
+    delete s;
+    return nullptr;
+  }
+  cudaMemsetAsync(s->table, 0xFF, slots * 8, ctx->stream);
+  cudaMemsetAsync(s->bitmap, 0, RG_SET_BITMAP_BITS / 8, ctx->stream);
+  return s;
+}
+
+static int set_finish(rg_set* s, const uint64_t* d_vals, uint64_t n) {
+  rg_ctx* ctx = s->ctx;
+  int rc = rg_launch_set_build(s, d_vals, n);
+  if (rc) return rc;
+  uint64_t d = 0;
+  if (n) {
+    rc = read_scalars(ctx, ctx->d_scratch, 1, &d);
+    if (rc) return rc;
+  }
+  s->n = d + (s->has_all_ones ? 1 : 0);
+  return 0;
+}
+
+rg_set* rg_set_from_rufus_keys(rg_ctx* ctx, const uint64_t* vals_host, uint64_t n, int k) {
+  rg_set* s = set_alloc(ctx, n, k);
+  if (!s) return nullptr;
+  for (uint64_t i = 0; i < n; ++i)
+    if (vals_host[i] == RG_EMPTY) s->has_all_ones = 1;
+  uint64_t* d = nullptr;
+  if (n) {
+    if (cudaMalloc(&d, n * 8) != cudaSuccess) {
+      rg_set_error("rg_set: out of device memory");
+      rg_set_free(s);
+      return nullptr;
+    }
+    cudaMemcpyAsync(d, vals_host, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  int rc = set_finish(s, d, n);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (rc) {
+    rg_set_free(s);
+    return nullptr;
+  }
+  return s;
+}
+
+rg_set* rg_set_from_jf_keys_dev(rg_ctx* ctx, const uint64_t* jf_keys_dev, uint64_t n, int k) {
+  rg_set* s = set_alloc(ctx, 2 * n, k);
+  if (!s) return nullptr;
+  uint64_t* d = nullptr;
+  int rc = 0;
+  if (n) {
+    if (cudaMalloc(&d, 2 * n * 8) != cudaSuccess) {
+      rg_set_error("rg_set: out of device memory");
+      rg_set_free(s);
+      return nullptr;
+    }
+    rc = rg_launch_jf_to_rufus(ctx, jf_keys_dev, n, k, d);
+  }
+  // k == 32: poly-A's reverse complement is the all-ones rufus key; canonical jf key 0 marks it
+  if (rc == 0 && k == 32 && n) {
+    std::vector<uint64_t> h(n);
+    cudaMemcpyAsync(h.data(), jf_keys_dev, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (uint64_t i = 0; i < n; ++i)
+      if (h[i] == 0) s->has_all_ones = 1;
+  }
+  if (rc == 0) rc = set_finish(s, d, 2 * n);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (rc) {
+    rg_set_free(s);
+    return nullptr;
+  }
+  return s;
+}
+
+rg_set* rg_set_from_jf_keys(rg_ctx* ctx, const uint64_t* jf_keys_host, uint64_t n, int k) {
+  uint64_t* d = nullptr;
+  if (n) {
+    RG_CUDA_OKP(cudaMalloc(&d, n * 8));
+    cudaMemcpyAsync(d, jf_keys_host, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  rg_set* s = rg_set_from_jf_keys_dev(ctx, d, n, k);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  return s;
+}
+
+// HashList text -> Mutations set. paired=1: RUFUS.Filter.cpp:121-143 (split on ' ' first),
+// paired=0: RUFUS.Filter.ss.cpp:100-121 (split on '\t' first). Split = Util.cpp:24-33.
+static void split(const std::string& line, char delim, std::vector<std::string>& out) {
+  out.clear();
+  if (line.empty()) return;
+  size_t start = 0;
+  for (;;) {
+    const size_t pos = line.find(delim, start);
+    if (pos == std::string::npos) {
+      if (start < line.size()) out.push_back(line.substr(start));   // getline drops a trailing empty token
+      break;
+    }
+    out.push_back(line.substr(start, pos - start));
+    start = pos + 1;
+  }
+}
+
+rg_set* rg_set_from_hashlist_text(rg_ctx* ctx, const char* text, uint64_t n_bytes, int k, int paired) {
+  std::vector<uint64_t> vals;
+  std::vector<std::string> f;
+  std::vector<char> rc;
+  auto add = [&](const std::string& kmer) {
+    vals.push_back(rg_rufus_pack(kmer.data(), (int)kmer.size()));
+    rc.resize(kmer.size() + 1);
+    const int n = rg_rufus_revcomp(kmer.data(), (int)kmer.size(), rc.data());
+    vals.push_back(rg_rufus_pack(rc.data(), n));
+  };
+  const char first = paired ? ' ' : '\t', second = paired ? '\t' : ' ';
+  uint64_t pos = 0;
+  while (pos < n_bytes) {
+    const char* nl = (const char*)memchr(text + pos, '\n', n_bytes - pos);
+    const uint64_t end = nl ? (uint64_t)(nl - text) : n_bytes;
+    std::string line(text + pos, end - pos);
+    pos = end + 1;
+    split(line, first, f);
+    if (f.size() == 2) add(f[0]);
+    else if (f.size() == 4) add(f[3]);
+    if (f.size() == 1) {
+      split(line, second, f);
+      if (!f.empty()) add(f[0]);
+    }
+  }
+  return rg_set_from_rufus_keys(ctx, vals.data(), vals.size(), k);
+}
+
+uint64_t rg_set_size(rg_set* s) { return s ? s->n : 0; }
+
+void rg_set_free(rg_set* s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->table);
+  cudaFree(s->bitmap);
+  delete s;
+}
+
+int rg_filter_hits_dev(rg_set* s, const char* seq_dev, const char* qual_dev, const uint64_t* offs_dev,
+                       uint64_t n_reads, uint64_t n_bytes, int minq, int skip_last, int32_t* hits_dev) {
+  if (!s || (((uintptr_t)seq_dev | (uintptr_t)qual_dev) & 15)) {
+    rg_set_error("rg_filter_hits_dev: null set or unaligned (16 B) buffers");
+    return RG_ERR_ARG;
+  }
+  return rg_launch_filter_hits(s, seq_dev, qual_dev, offs_dev, 0, n_reads, n_bytes, minq, skip_last, hits_dev);
+}
+
+int rg_filter_hits_fixed_dev(rg_set* s, const char* seq_dev, const char* qual_dev, uint32_t read_len,
+                             uint64_t n_reads, int minq, int skip_last, int32_t* hits_dev) {
+  if (!s || read_len == 0 || (((uintptr_t)seq_dev | (uintptr_t)qual_dev) & 15)) {
+    rg_set_error("rg_filter_hits_fixed_dev: bad arguments");
+    return RG_ERR_ARG;
+  }
+  return rg_launch_filter_hits(s, seq_dev, qual_dev, nullptr, read_len, n_reads, (uint64_t)read_len * n_reads, minq,
+                               skip_last, hits_dev);
+}
+
+int rg_filter_pairs_fixed_dev(rg_set* s, const char* s1, const char* q1, const char* s2, const char* q2,
+                              uint32_t read_len, uint64_t n_pairs, int minq, int thresh, int32_t* hits1_dev,
+                              int32_t* hits2_dev, uint8_t* keep_dev) {
+  int rc = rg_filter_hits_fixed_dev(s, s1, q1, read_len, n_pairs, minq, 1, hits1_dev);
+  if (rc == 0) rc = rg_filter_hits_fixed_dev(s, s2, q2, read_len, n_pairs, minq, 1, hits2_dev);
+  if (rc == 0) rc = rg_launch_keep(s->ctx, hits1_dev, hits2_dev, n_pairs, thresh, keep_dev);
+  return rc;
+}
+
+struct DevReads {
+  char* seq = nullptr;
+  char* qual = nullptr;
+  uint64_t* offs = nullptr;
+  int32_t* hits = nullptr;
+  uint64_t n_bytes = 0;
+  ~DevReads() {
+    cudaFree(seq);
+    cudaFree(qual);
+    cudaFree(offs);
+    cudaFree(hits);
+  }
+};
+
+static int upload_reads(rg_ctx* ctx, DevReads& d, const char* seq, const char* qual, const uint64_t* offs,
+                        uint64_t n_reads) {
+  const uint64_t base = offs[0];
+  d.n_bytes = offs[n_reads] - base;
+  if (base != 0) {
+    rg_set_error("filter: offsets must start at 0");
+    return RG_ERR_ARG;
+  }
+  RG_CUDA_OK(cudaMalloc(&d.seq, d.n_bytes + 16));
+  RG_CUDA_OK(cudaMalloc(&d.qual, d.n_bytes + 16));
+  RG_CUDA_OK(cudaMalloc(&d.offs, (n_reads + 1) * 8));
+  RG_CUDA_OK(cudaMalloc(&d.hits, (n_reads + 1) * 4));
+  RG_CUDA_OK(cudaMemcpyAsync(d.seq, seq, d.n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RG_CUDA_OK(cudaMemcpyAsync(d.qual, qual, d.n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  RG_CUDA_OK(cudaMemcpyAsync(d.offs, offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int rg_filter_pairs(rg_set* s, const char* s1, const char* q1, const uint64_t* o1, const char* s2, const char* q2,
+                    const uint64_t* o2, uint64_t n_pairs, int minq, int thresh, uint8_t* keep_host) {
+  if (!s) return RG_ERR_ARG;
+  if (n_pairs == 0) return 0;
+  rg_ctx* ctx = s->ctx;
+  DevReads a, b;
+  int rc = upload_reads(ctx, a, s1, q1, o1, n_pairs);
+  if (rc == 0) rc = upload_reads(ctx, b, s2, q2, o2, n_pairs);
+  if (rc == 0) rc = rg_launch_filter_hits(s, a.seq, a.qual, a.offs, 0, n_pairs, a.n_bytes, minq, 1, a.hits);
+  if (rc == 0) rc = rg_launch_filter_hits(s, b.seq, b.qual, b.offs, 0, n_pairs, b.n_bytes, minq, 1, b.hits);
+  uint8_t* d_keep = nullptr;
+  if (rc == 0) RG_CUDA_OK(cudaMalloc(&d_keep, n_pairs));
+  if (rc == 0) rc = rg_launch_keep(ctx, a.hits, b.hits, n_pairs, thresh, d_keep);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(keep_host, d_keep, n_pairs, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      rg_set_error(cudaGetErrorString(e));
+      rc = RG_ERR_CUDA;
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_keep);
+  return rc;
+}
+
+int rg_filter_single(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint64_t n_reads, int minq,
+                     int32_t* hits_host) {
+  if (!s) return RG_ERR_ARG;
+  if (n_reads == 0) return 0;
+  rg_ctx* ctx = s->ctx;
+  DevReads a;
+  int rc = upload_reads(ctx, a, seq, qual, offs, n_reads);
+  if (rc == 0) rc = rg_launch_filter_hits(s, a.seq, a.qual, a.offs, 0, n_reads, a.n_bytes, minq, 0, a.hits);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(hits_host, a.hits, n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      rg_set_error(cudaGetErrorString(e));
+      rc = RG_ERR_CUDA;
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+}  // extern "C"

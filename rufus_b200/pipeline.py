@@ -1,0 +1,189 @@
+"""Host orchestration of one pass of the hot path over a trio (or any subject +
+controls): count every sample -> histogram -> subtract -> pull subject reads.
+
+Mirrors the stage order of runRufus.sh:766-797 (count), :916-929 (subtract),
+:946-985 (read pull). Two drivers share the same C-ABI calls:
+
+  * DevicePipeline: inputs already resident in HBM (torch tensors are used only to
+    own device memory and, for world > 1, for the NCCL all-to-all). This is what
+    bench.py times as `value`.
+  * host_step(): the public host-buffer API (rg_count_push / rg_subtract /
+    rg_filter_pairs) — bench.py's `e2e`.
+
+Multi-GPU: the k-mer space is partitioned by hash prefix; each rank
+extracts k-mers from its own slice of reads, buckets them by owner rank
+(rg_extract_partition_dev), ONE all-to-all routes the packed keys to their owners,
+each owner inserts into its shard table. Subtraction is shard-local (same hash =>
+same shard); the (small) mutant set is all-gathered so every rank filters its own
+slice of subject reads without a second exchange of reads.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import api
+
+
+def split_sizes_from_offsets(offsets) -> list[int]:
+    """bucket offsets (n_parts+1) -> per-destination send counts for the all-to-all"""
+    o = [int(x) for x in offsets]
+    return [o[i + 1] - o[i] for i in range(len(o) - 1)]
+
+
+def exchange_keys(keys, send_sizes, group=None):
+    """One ragged all-to-all of packed k-mers (torch tensor, int64 view of u64 keys).
+
+    keys: 1-D tensor laid out as contiguous per-destination buckets; send_sizes[r] keys
+    go to rank r. Returns the tensor of keys this rank owns. Works on any backend
+    (NCCL on GPUs, gloo on CPU for the host-logic tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    send = torch.tensor(send_sizes, dtype=torch.int64, device=keys.device)
+    recv = torch.empty(world, dtype=torch.int64, device=keys.device)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_sizes = [int(x) for x in recv.tolist()]
+    out = torch.empty(sum(recv_sizes), dtype=keys.dtype, device=keys.device)
+    dist.all_to_all_single(out, keys[: sum(send_sizes)], output_split_sizes=recv_sizes,
+                           input_split_sizes=list(send_sizes), group=group)
+    return out
+
+
+def gather_varlen(local, group=None):
+    """all-gather of a ragged 1-D tensor (the per-shard HashList pieces)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    ns = [torch.empty(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    sizes = [int(x.item()) for x in ns]
+    mx = max(sizes + [1])
+    pad = torch.zeros(mx, dtype=local.dtype, device=local.device)
+    pad[: local.numel()] = local
+    outs = [torch.empty(mx, dtype=local.dtype, device=local.device) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(outs, sizes)])
+
+
+class DevicePipeline:
+    """count -> histo -> subtract -> filter with every input resident in HBM."""
+
+    def __init__(self, ctx: api.Context, k: int, streams, subject_pairs, read_len: int, est_distinct: int,
+                 min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
+                 mode: int = api.MODE_TILED, rank: int = 0, world: int = 1, max_mutant: int = 1 << 22):
+        import torch
+
+        self.torch = torch
+        self.ctx, self.k, self.read_len = ctx, k, read_len
+        self.streams = streams                      # list of uint8 CUDA tensors [n_reads*read_len], subject first
+        self.s1, self.q1, self.s2, self.q2 = subject_pairs
+        self.n_pairs = self.s1.numel() // read_len
+        self.min_cov, self.max_cov, self.minq, self.thresh, self.lower = min_cov, max_cov, minq, thresh, lower
+        self.rank, self.world = rank, world
+        dev = self.s1.device
+        shard = (rank, world) if world > 1 else None
+        self.tables = [api.KmerTable(ctx, k, True, est_distinct, mode, shard=shard) for _ in streams]
+        self.mut_keys = torch.empty(max_mutant, dtype=torch.int64, device=dev)
+        self.mut_counts = torch.empty(max_mutant, dtype=torch.int32, device=dev)
+        self.hits1 = torch.empty(self.n_pairs, dtype=torch.int32, device=dev)
+        self.hits2 = torch.empty(self.n_pairs, dtype=torch.int32, device=dev)
+        self.keep = torch.empty(self.n_pairs, dtype=torch.uint8, device=dev)
+        if world > 1:
+            n_win = max(int(s.numel()) for s in streams)
+            self.part_keys = torch.empty(n_win, dtype=torch.int64, device=dev)
+            self.part_offs = torch.empty(world + 1, dtype=torch.int64, device=dev)
+        self.last = {}
+
+    def count_sample(self, i: int):
+        L = api.lib()
+        t = self.tables[i]
+        t.clear()
+        s = self.streams[i]
+        if self.world == 1:
+            t.push_dev(s, s.numel(), self.read_len)
+        else:
+            rc = L.rg_extract_partition_dev(self.ctx.h, self.k, 1, api._ptr(s), s.numel(), self.read_len, self.world,
+                                            api._ptr(self.part_keys), api._ptr(self.part_offs))
+            api._check(rc, "rg_extract_partition_dev")
+            sizes = split_sizes_from_offsets(self.part_offs.tolist())
+            mine = exchange_keys(self.part_keys, sizes)
+            t.push_keys_dev(mine, mine.numel())
+            self.last.setdefault("sent_keys", []).append(sum(sizes) - sizes[self.rank])
+        t.end(trim=False)
+
+    def step(self) -> dict:
+        torch = self.torch
+        L = api.lib()
+        self.last = {}
+        for i in range(len(self.tables)):
+            self.count_sample(i)
+        # histogram of the subject (jellyfish histo -f); all-reduced over shards
+        h = self.tables[0].histo(min_count=self.lower[0])
+        if self.world > 1:
+            import torch.distributed as dist
+            ht = torch.from_numpy(h.astype(np.int64)).to(self.s1.device)
+            dist.all_reduce(ht)
+            h = ht.cpu().numpy().astype(np.uint64)
+        # shard-local subtraction -> mutant k-mers (device)
+        others = self.tables[1:]
+        om = np.ascontiguousarray(self.lower[1:], np.uint64)
+        n = L.rg_subtract_dev(self.tables[0].h, self.lower[0], api._handles(others), api._ptr(om), len(others), 5,
+                              self.min_cov, self.max_cov, api._ptr(self.mut_keys), api._ptr(self.mut_counts),
+                              self.mut_keys.numel())
+        if n < 0:
+            raise api._err("rg_subtract_dev")
+        keys = self.mut_keys[:n]
+        if self.world > 1:
+            keys = gather_varlen(keys)
+        mset = api.MutantSet(self.ctx, L.rg_set_from_jf_keys_dev(self.ctx.h, api._ptr(keys), keys.numel(), self.k),
+                             self.k)
+        rc = L.rg_filter_pairs_fixed_dev(mset.h, api._ptr(self.s1), api._ptr(self.q1), api._ptr(self.s2),
+                                         api._ptr(self.q2), self.read_len, self.n_pairs, self.minq, self.thresh,
+                                         api._ptr(self.hits1), api._ptr(self.hits2), api._ptr(self.keep))
+        api._check(rc, "rg_filter_pairs_fixed_dev")
+        n_kept = int(self.keep.sum().item())     # device -> host read of the step's result
+        mset.free()
+        self.last.update({"n_mutant": int(keys.numel()), "n_kept": n_kept, "histo": h})
+        return self.last
+
+    def mutant_keys_host(self):
+        n = self.last["n_mutant"] if self.world == 1 else None
+        return self.mut_keys[:n].cpu().numpy().view(np.uint64) if n is not None else None
+
+    def free(self):
+        for t in self.tables:
+            t.free()
+
+
+def host_step(ctx: api.Context, k: int, host_streams, subject_pairs, read_len: int, est_distinct: int,
+              min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
+              mode: int = api.MODE_TILED, tables=None):
+    """The same pass through the public host-buffer API: every input starts in host
+    memory (pinned or not), results come back to host memory.
+
+    host_streams: list of uint8 numpy arrays (subject first), reads separated by a
+    non-ACGT byte. subject_pairs: (seq1, qual1, seq2, qual2) numpy [n_pairs, read_len]."""
+    own = tables is None
+    if own:
+        tables = [api.KmerTable(ctx, k, True, est_distinct, mode) for _ in host_streams]
+    for t, s in zip(tables, host_streams):
+        t.clear()
+        t.push_stream(s)
+        t.end(trim=False)
+    h = tables[0].histo(min_count=lower[0])
+    hk, hc = api.subtract(tables[0], tables[1:], subj_min=lower[0], other_min=list(lower[1:]), min_cov=min_cov,
+                          max_cov=max_cov, sort=False)
+    mset = api.MutantSet.from_jf_keys(ctx, hk, k)
+    s1, q1, s2, q2 = subject_pairs
+    offs = np.arange(s1.shape[0] + 1, dtype=np.uint64) * np.uint64(read_len)
+    keep = mset.filter_pairs(s1, q1, offs, s2, q2, offs, minq, thresh)
+    mset.free()
+    if own:
+        for t in tables:
+            t.free()
+    return {"histo": h, "hashlist": (hk, hc), "keep": keep}

@@ -76,12 +76,15 @@ def sample_pairs(haps, n_pairs: int, rng, read_len: int = 150, err: float = 0.00
     return tuple(out)
 
 
-def make_trio(seed: int, genome_len: int, n_pairs: int, read_len: int = 150, **kw):
-    """dict sample -> (seq1, qual1, seq2, qual2); plus the de-novo positions."""
+def make_trio(seed: int, genome_len: int, n_pairs: int, read_len: int = 150, slice_id: int | None = None, **kw):
+    """dict sample -> (seq1, qual1, seq2, qual2); plus the de-novo positions.
+
+    slice_id selects an independent batch of reads from the SAME individuals (one
+    slice per GPU rank in the multi-GPU runs); None keeps the original stream."""
     haps, dn = make_haplotypes(seed, genome_len, kw.pop("n_denovo", None))
     trio = {}
     for i, s in enumerate(SAMPLES):
-        rng = np.random.default_rng([seed, 1000 + i])
+        rng = np.random.default_rng([seed, 1000 + i] + ([] if slice_id is None else [slice_id]))
         trio[s] = sample_pairs(haps[s], n_pairs, rng, read_len, **kw)
     return trio, dn
 

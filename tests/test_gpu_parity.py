@@ -1,0 +1,180 @@
+"""GPU parity: every stage of the hot path through the C ABI vs (a) the golden
+outputs of the reference binaries and (b) the CPU oracle on the same inputs.
+Bit-exact: integer/byte work only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from cases import both_mates, load_case
+from conftest import ROOT
+from rufus_b200 import api, kmer, synth, fastq
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+CASES = ["testRun", "edge", "synth_k25", "synth_k31"]
+MODES = [api.MODE_DIRECT, api.MODE_TILED]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _count_all(ctx, reads, k, mode):
+    tabs = {}
+    for s, pair in reads.items():
+        r = both_mates(pair)
+        tabs[s] = api.KmerTable.count(ctx, r.seq, r.offs, k, True, mode=mode)
+    return tabs
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", CASES)
+def test_pipeline_matches_reference_goldens(ctx, case, mode):
+    g, reads = load_case(case)
+    k = g["k"]
+    names = list(reads)
+    tabs = _count_all(ctx, reads, k, mode)
+    mins = [g["L"]] + [g["ctlL"]] * (len(names) - 1)
+    for s, lo in zip(names, mins):
+        keys, counts = tabs[s].dump(min_count=lo)
+        gs = g["samples"][s]
+        assert keys.size == gs["n_distinct"]
+        r = both_mates(reads[s])
+        okeys, ocounts = oracle.count(r.seq, r.offs, k, True, lo)
+        assert np.array_equal(keys, okeys) and np.array_equal(counts, ocounts)
+        h = tabs[s].histo(min_count=lo)
+        assert h.size == 10002
+        assert {int(i): int(v) for i, v in enumerate(h) if v} == {int(a): b for a, b in gs["histo_nonzero"].items()}
+    mk, mc, _ = api.merge_unique([tabs[s] for s in names], mins)
+    assert sorted(kmer.dump_text(mk, mc, k, "\t")) == g["merge_sorted"]
+    subj = names[0]
+    hk, hc = api.subtract(tabs[subj], [tabs[s] for s in names[1:]], subj_min=mins[0], other_min=mins[1:],
+                          min_cov=g["min_cov"], max_cov=g["max_cov"])
+    hashlist = sorted(kmer.dump_text(hk, hc, k))
+    assert hashlist == g["hashlist_sorted"]
+    # query == jellyfish query on the subject .Jhash
+    q = tabs[subj].query(mk, min_count=mins[0])
+    sk, sc = tabs[subj].dump(min_count=mins[0])
+    lut = dict(zip(sk.tolist(), sc.tolist()))
+    assert q.tolist() == [lut.get(x, 0) for x in mk.tolist()]
+    # read pull, both ways of building the Mutations set
+    text = ("\n".join(hashlist) + "\n").encode()
+    m1, m2 = reads[subj]
+    for mset in (api.MutantSet.from_hashlist_text(ctx, text, k, paired=True), api.MutantSet.from_jf_keys(ctx, hk, k)):
+        keep = mset.filter_pairs(m1.seq, m1.qual, m1.offs, m2.seq, m2.qual, m2.offs, g["minq"], g["thresh"])
+        assert sorted(m1.names[i].decode() for i in np.flatnonzero(keep)) == g["pulled_mate1_names_sorted"]
+        hits = mset.filter_single(m1.seq, m1.qual, m1.offs, g["minq"])
+        got = sorted(f"{m1.names[i].decode()}:MH{hits[i]}" for i in np.flatnonzero(hits >= g["thresh"]))
+        assert got == g["single_names_sorted"]
+        mset.free()
+    for t in tabs.values():
+        t.free()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_medium_synthetic_vs_oracle(ctx, mode):
+    """60k pairs/sample (18 Mbases/sample), two pushes per sample, stream and offsets inputs."""
+    trio, _ = synth.make_trio(99, 600_000, 60_000)
+    k = 25
+    tabs, otabs = {}, {}
+    for s in synth.SAMPLES:
+        s1, q1, s2, q2 = trio[s]
+        t = api.KmerTable(ctx, k, True, est_distinct=6_000_000, mode=mode)
+        # mate 1 as a '\n'-separated stream (what the FASTQ sequence lines look like), mate 2 via offsets
+        st = np.concatenate([s1, np.full((s1.shape[0], 1), 10, np.uint8)], axis=1)
+        t.push_stream(st)
+        r2 = fastq.from_matrix(s2)
+        t.push_reads(r2.seq, r2.offs)
+        tabs[s] = t.end()
+        both = np.concatenate([s1, s2])
+        otabs[s] = oracle.count(both.reshape(-1), np.arange(both.shape[0] + 1, dtype=np.uint64) * 150, k, True, 1)
+        keys, counts = t.dump()
+        assert np.array_equal(keys, otabs[s][0]) and np.array_equal(counts, otabs[s][1])
+        st = t.stats()
+        assert st["distinct"] == keys.size and st["occurrences"] == int(counts.sum())
+    names = list(synth.SAMPLES)
+    flt = lambda kc, lo: (kc[0][kc[1] >= lo], kc[1][kc[1] >= lo])
+    ok, oc = oracle.hashlist(flt(otabs["Child"], 2), [flt(otabs[s], 2) for s in names[1:]], 5, 200)
+    hk, hc = api.subtract(tabs["Child"], [tabs[s] for s in names[1:]], min_cov=5, max_cov=200)
+    assert np.array_equal(hk, ok) and np.array_equal(hc, oc) and hk.size > 50
+    s1, q1, s2, q2 = trio["Child"]
+    offs = np.arange(s1.shape[0] + 1, dtype=np.uint64) * 150
+    mset = api.MutantSet.from_jf_keys(ctx, hk, k)
+    keep = mset.filter_pairs(s1, q1, offs, s2, q2, offs, 15, 1)
+    rset = oracle.rufus_set_from_kmers(kmer.keys_to_text(hk, k))
+    assert len(mset) == rset.size
+    okeep = oracle.filter_pairs(s1, q1, offs, s2, q2, offs, k, 15, 1, rset)
+    assert np.array_equal(keep, okeep) and keep.sum() > 20
+    for thr in (2, 5):
+        assert np.array_equal(mset.filter_pairs(s1, q1, offs, s2, q2, offs, 20, thr),
+                              oracle.filter_pairs(s1, q1, offs, s2, q2, offs, k, 20, thr, rset))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_table_growth_and_heavy_hitters(ctx, mode):
+    """est_distinct far too small -> spill + grow; poly-A reads -> one key with a huge count."""
+    rng = np.random.default_rng(3)
+    reads = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(40_000, 100))]
+    reads[:5000] = ord("A")
+    offs = np.arange(reads.shape[0] + 1, dtype=np.uint64) * 100
+    t = api.KmerTable(ctx, 21, True, est_distinct=1000, mode=mode)
+    t.push_reads(reads, offs)
+    t.end()
+    keys, counts = t.dump()
+    okeys, ocounts = oracle.count(reads.reshape(-1), offs, 21, True, 1)
+    assert np.array_equal(keys, okeys) and np.array_equal(counts, ocounts)
+    assert counts.max() >= 5000 * 80
+    t.free()
+
+
+@pytest.mark.parametrize("k,canonical", [(1, True), (5, False), (16, True), (31, False), (32, True)])
+def test_k_range_and_noncanonical(ctx, k, canonical):
+    rng = np.random.default_rng(k)
+    seq = np.frombuffer(b"ACGTNacgt", np.uint8)[rng.integers(0, 9, size=200_000)]
+    lens = rng.integers(0, 80, size=4000)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    seq = seq[: int(offs[-1])]
+    for mode in MODES:
+        t = api.KmerTable.count(ctx, seq, offs, k, canonical, mode=mode)
+        keys, counts = t.dump()
+        okeys, ocounts = oracle.count(seq, offs, k, canonical, 1)
+        assert np.array_equal(keys, okeys) and np.array_equal(counts, ocounts)
+        t.free()
+
+
+def test_empty_inputs(ctx):
+    t = api.KmerTable(ctx, 25, True, est_distinct=100)
+    t.push_reads(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    t.push_stream(np.zeros(0, np.uint8))
+    t.end()
+    assert t.dump()[0].size == 0 and int(t.histo().sum()) == 0
+    hk, hc = api.subtract(t, [t])
+    assert hk.size == 0
+    mset = api.MutantSet.from_jf_keys(ctx, hk, 25)
+    z = np.zeros(0, np.uint8)
+    o = np.zeros(1, np.uint64)
+    assert mset.filter_pairs(z, z, o, z, z, o).size == 0
+    # reads shorter than k and empty reads never hit
+    seq = np.frombuffer(b"ACGTACGTAC", np.uint8)
+    qual = np.full(10, ord("J"), np.uint8)
+    o = np.array([0, 0, 4, 4, 10], np.uint64)
+    assert mset.filter_single(seq, qual, o).tolist() == [0, 0, 0, 0]
+
+
+def test_from_pairs_roundtrip(ctx):
+    rng = np.random.default_rng(1)
+    keys = np.unique(rng.integers(0, 1 << 50, size=100_000, dtype=np.uint64))
+    counts = rng.integers(1, 5000, size=keys.size, dtype=np.uint32)
+    t = api.KmerTable.from_pairs(ctx, 25, keys, counts)
+    dk, dc = t.dump()
+    assert np.array_equal(dk, keys) and np.array_equal(dc, counts)
+    assert np.array_equal(t.query(keys[:1000]), counts[:1000])
+    assert t.query(np.array([(1 << 50) - 1 - int(keys[0])], np.uint64) + np.uint64(0)).size == 1
+    t.free()
