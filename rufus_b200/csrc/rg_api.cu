@@ -172,15 +172,17 @@ static uint32_t tiles_for(uint64_t est_distinct) {
   return (uint32_t)n;
 }
 
-// double the tile count and re-insert every (key,count)
-static int table_grow(rg_table* t) {
+// grow to new_tiles tiles and re-insert every (key,count)
+static int table_grow(rg_table* t, uint32_t new_tiles) {
   rg_ctx* ctx = t->ctx;
   uint64_t* old_keys = t->keys;
   uint32_t* old_counts = t->counts;
   const uint64_t old_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
   t->keys = nullptr;
   t->counts = nullptr;
-  int rc = table_alloc_tiles(t, t->n_tiles * 2);
+  if (t->mode == RG_MODE_TILED && new_tiles > (uint32_t)ctx->sm_count)
+    new_tiles = (new_tiles + ctx->sm_count - 1) / ctx->sm_count * ctx->sm_count;
+  int rc = table_alloc_tiles(t, new_tiles);
   if (rc) return rc;
   // bucket staging is sized per tile count: drop it, it is rebuilt on the next push
   if (t->part_cursor) { cudaFree(t->part_cursor); t->part_cursor = nullptr; }
@@ -220,7 +222,10 @@ static int table_resolve_spill(rg_table* t) {
     RG_CUDA_OK(cudaMemcpyAsync(tmp, t->spill, st[0] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, 3 * sizeof(uint64_t), ctx->stream));
     if (round > 0) {
-      rc = table_grow(t);
+      // worst case every spilled key is new and every current slot is taken: size for <= 50 % load
+      const uint64_t cur_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+      const uint32_t want = std::max<uint32_t>(t->n_tiles * 2, tiles_for(cur_slots + st[0]));
+      rc = table_grow(t, want);
       if (rc) { cudaFree(tmp); return rc; }
     }
     rc = rg_launch_insert_keys(t, tmp, st[0], nullptr);
@@ -750,6 +755,8 @@ static rg_set* set_alloc(rg_ctx* ctx, uint64_t n_vals, int k) {
     return nullptr;
   }
   s->slots = (uint32_t)slots;
+  s->bitmap_bits = 1u << 15;
+  while (s->bitmap_bits < RG_SET_BITMAP_BITS && (uint64_t)s->bitmap_bits < n_vals * 64) s->bitmap_bits <<= 1;
   if (cudaMalloc(&s->table, slots * 8) != cudaSuccess || cudaMalloc(&s->bitmap, RG_SET_BITMAP_BITS / 8) != cudaSuccess) {
     rg_set_error("rg_set: out of device memory");
     cudaFree(s->table);

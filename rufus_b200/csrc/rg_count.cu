@@ -256,6 +256,121 @@ partition_kernel(ExtractParams ep, uint32_t n_tiles_global, uint32_t tile_first,
   }
 }
 
+// CTA-aggregated variant (the one normally used): a CTA walks a SUPER-CHUNK of
+// SUPER x CHUNK windows twice. Pass 1 histograms the bucket ids in shared memory;
+// one global atomicAdd per (super-chunk, non-empty bucket) then reserves a
+// contiguous run in each bucket; pass 2 recomputes the keys (ALU is cheap, the
+// ASCII is L2-hot) and scatters them at run_base + shared-memory rank. Global
+// atomics drop from one per k-mer to ~n_tiles per 32 Ki k-mers.
+constexpr int SUPER = 8;
+
+__global__ void __launch_bounds__(COUNT_THREADS)
+partition_agg_kernel(ExtractParams ep, uint32_t n_tiles_global, uint32_t tile_first, uint32_t n_tiles,
+                     uint64_t* __restrict__ part_keys, uint32_t* __restrict__ cursor, uint32_t bucket_cap,
+                     uint64_t* status, uint64_t* spill, uint64_t spill_cap) {
+  __shared__ StageSmem sm;
+  extern __shared__ uint32_t dyn[];
+  uint32_t* hist = dyn;               // [n_tiles] pass 1: counts; pass 2: running rank
+  uint32_t* base = dyn + n_tiles;     // [n_tiles] start of this CTA's run inside the bucket
+  const uint64_t n_chunks = (ep.n_bytes + CHUNK - 1) / CHUNK;
+  const uint64_t n_super = (n_chunks + SUPER - 1) / SUPER;
+  for (uint64_t sc = blockIdx.x; sc < n_super; sc += gridDim.x) {
+    for (uint32_t i = threadIdx.x; i < n_tiles; i += blockDim.x) hist[i] = 0;
+    const uint64_t c_begin = sc * SUPER;
+    const uint64_t c_end = (c_begin + SUPER < n_chunks) ? c_begin + SUPER : n_chunks;
+    unsigned long long foreign = 0;
+    for (uint64_t c = c_begin; c < c_end; ++c) {
+      const uint64_t c0 = c * CHUNK;
+      __syncthreads();
+      stage_chunk(sm, ep, c0);
+      __syncthreads();
+      for (int p = threadIdx.x; p < CHUNK; p += blockDim.x) {
+        uint64_t key;
+        if (c0 + p + ep.k > ep.n_bytes) break;
+        if (!window_key(sm, p, ep.k, ep.canonical, key)) continue;
+        const uint32_t tile = rg_tile_of(rg_mix64(key), n_tiles_global) - tile_first;
+        if (tile >= n_tiles) { ++foreign; continue; }
+        atomicAdd(&hist[tile], 1u);
+      }
+    }
+    if (foreign) atomicAdd((unsigned long long*)&status[1], foreign);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+      const uint32_t cnt = hist[i];
+      base[i] = cnt ? atomicAdd(cursor + i, cnt) : 0u;
+      hist[i] = 0;
+    }
+    for (uint64_t c = c_begin; c < c_end; ++c) {
+      const uint64_t c0 = c * CHUNK;
+      __syncthreads();
+      stage_chunk(sm, ep, c0);
+      __syncthreads();
+      for (int p = threadIdx.x; p < CHUNK; p += blockDim.x) {
+        uint64_t key;
+        if (c0 + p + ep.k > ep.n_bytes) break;
+        if (!window_key(sm, p, ep.k, ep.canonical, key)) continue;
+        const uint32_t tile = rg_tile_of(rg_mix64(key), n_tiles_global) - tile_first;
+        if (tile >= n_tiles) continue;
+        const uint32_t at = base[tile] + atomicAdd(&hist[tile], 1u);
+        if (at < bucket_cap) {
+          part_keys[(uint64_t)tile * bucket_cap + at] = key;
+        } else {
+          const uint64_t sp = atomicAdd((unsigned long long*)&status[0], 1ull);
+          if (sp < spill_cap) spill[sp] = key;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int KEYS_SUPER = 32768;   // keys per CTA round of the key-list variant
+
+__global__ void __launch_bounds__(256)
+partition_keys_agg_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t n_tiles_global, uint32_t tile_first,
+                          uint32_t n_tiles, uint64_t* __restrict__ part_keys, uint32_t* __restrict__ cursor,
+                          uint32_t bucket_cap, uint64_t* status, uint64_t* spill, uint64_t spill_cap) {
+  extern __shared__ uint32_t dyn[];
+  uint32_t* hist = dyn;
+  uint32_t* base = dyn + n_tiles;
+  const uint64_t n_super = (n + KEYS_SUPER - 1) / KEYS_SUPER;
+  for (uint64_t sc = blockIdx.x; sc < n_super; sc += gridDim.x) {
+    for (uint32_t i = threadIdx.x; i < n_tiles; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const uint64_t lo = sc * KEYS_SUPER;
+    const uint64_t hi = lo + KEYS_SUPER < n ? lo + KEYS_SUPER : n;
+    unsigned long long foreign = 0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const uint32_t tile = rg_tile_of(rg_mix64(__ldg(keys + i)), n_tiles_global) - tile_first;
+      if (tile >= n_tiles) { ++foreign; continue; }
+      atomicAdd(&hist[tile], 1u);
+    }
+    if (foreign) atomicAdd((unsigned long long*)&status[1], foreign);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+      const uint32_t cnt = hist[i];
+      base[i] = cnt ? atomicAdd(cursor + i, cnt) : 0u;
+      hist[i] = 0;
+    }
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const uint64_t key = __ldg(keys + i);
+      const uint32_t tile = rg_tile_of(rg_mix64(key), n_tiles_global) - tile_first;
+      if (tile >= n_tiles) continue;
+      const uint32_t at = base[tile] + atomicAdd(&hist[tile], 1u);
+      if (at < bucket_cap) {
+        part_keys[(uint64_t)tile * bucket_cap + at] = key;
+      } else {
+        const uint64_t sp = atomicAdd((unsigned long long*)&status[0], 1ull);
+        if (sp < spill_cap) spill[sp] = key;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr uint32_t AGG_MAX_TILES = 16384;   // 8 B of shared memory per tile
+
 // same bucketing for an already-extracted key list (the receive side of the all-to-all)
 __global__ void __launch_bounds__(256)
 partition_keys_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t n_tiles_global, uint32_t tile_first,
@@ -284,7 +399,22 @@ int rg_launch_partition_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n) 
   unsigned grid = rg_grid(ctx, 8);
   const uint64_t need = (n + 255) / 256;
   if (need < grid) grid = (unsigned)need;
-  {
+  if (t->n_tiles <= AGG_MAX_TILES) {
+    const size_t smem = (size_t)t->n_tiles * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+      RG_CUDA_OK(cudaFuncSetAttribute(partition_keys_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(AGG_MAX_TILES * 8)));
+      attr_set = true;
+    }
+    const uint64_t n_super = (n + KEYS_SUPER - 1) / KEYS_SUPER;
+    unsigned g2 = rg_grid(ctx, smem > 48 * 1024 ? 1 : 4);
+    if (n_super < g2) g2 = (unsigned)n_super;
+    rg_launch_scope _ls(ctx, "partition_keys_kernel");
+    partition_keys_agg_kernel<<<g2, 256, smem, ctx->stream>>>(dev_keys, n, t->n_tiles_global, t->tile_first,
+                                                              t->n_tiles, t->part_keys, t->part_cursor, t->bucket_cap,
+                                                              t->d_status, t->spill, t->spill_cap);
+  } else {
     rg_launch_scope _ls(ctx, "partition_keys_kernel");
     partition_keys_kernel<<<grid, 256, 0, ctx->stream>>>(dev_keys, n, t->n_tiles_global, t->tile_first, t->n_tiles,
                                                          t->part_keys, t->part_cursor, t->bucket_cap, t->d_status,
@@ -300,7 +430,22 @@ int rg_launch_partition(rg_table* t, const ExtractParams& ep) {
   const uint64_t n_chunks = (ep.n_bytes + CHUNK - 1) / CHUNK;
   unsigned grid = rg_grid(ctx, 8);
   if (n_chunks < grid) grid = (unsigned)n_chunks;
-  {
+  if (t->n_tiles <= AGG_MAX_TILES) {
+    const size_t smem = (size_t)t->n_tiles * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+      RG_CUDA_OK(cudaFuncSetAttribute(partition_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(AGG_MAX_TILES * 8)));
+      attr_set = true;
+    }
+    const uint64_t n_super = (n_chunks + SUPER - 1) / SUPER;
+    unsigned g2 = rg_grid(ctx, smem > 96 * 1024 ? 1 : (smem > 40 * 1024 ? 2 : 4));
+    if (n_super < g2) g2 = (unsigned)n_super;
+    rg_launch_scope _ls(ctx, "partition_kernel");
+    partition_agg_kernel<<<g2, COUNT_THREADS, smem, ctx->stream>>>(ep, t->n_tiles_global, t->tile_first, t->n_tiles,
+                                                                   t->part_keys, t->part_cursor, t->bucket_cap,
+                                                                   t->d_status, t->spill, t->spill_cap);
+  } else {
     rg_launch_scope _ls(ctx, "partition_kernel");
     partition_kernel<<<grid, COUNT_THREADS, 0, ctx->stream>>>(ep, t->n_tiles_global, t->tile_first, t->n_tiles,
                                                               t->part_keys, t->part_cursor, t->bucket_cap, t->d_status,

@@ -24,12 +24,12 @@ __host__ __device__ __forceinline__ uint32_t rg_set_hash(uint64_t v) { return (u
 
 // ---- set construction -----------------------------------------------------
 __global__ void set_build_kernel(const uint64_t* __restrict__ vals, uint64_t n, uint64_t* table, uint32_t slots,
-                                 uint32_t* bitmap, unsigned long long* n_distinct) {
+                                 uint32_t* bitmap, uint32_t bitmap_bits, unsigned long long* n_distinct) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t v = vals[i];
     if (v == RG_EMPTY) continue;   // handled by has_all_ones on the host
     const uint32_t h = rg_set_hash(v);
-    atomicOr(bitmap + ((h & (RG_SET_BITMAP_BITS - 1)) >> 5), 1u << (h & 31));
+    atomicOr(bitmap + ((h & (bitmap_bits - 1)) >> 5), 1u << (h & 31));
     uint32_t slot = h & (slots - 1);
     for (;;) {
       const unsigned long long cur = atomicCAS((unsigned long long*)(table + slot), (unsigned long long)RG_EMPTY,
@@ -52,7 +52,7 @@ int rg_launch_set_build(rg_set* s, const uint64_t* d_vals, uint64_t n) {
   if (grid > rg_grid(ctx, 8)) grid = rg_grid(ctx, 8);
   {
     rg_launch_scope _ls(ctx, "set_build_kernel");
-    set_build_kernel<<<grid, 256, 0, ctx->stream>>>(d_vals, n, s->table, s->slots, s->bitmap,
+    set_build_kernel<<<grid, 256, 0, ctx->stream>>>(d_vals, n, s->table, s->slots, s->bitmap, s->bitmap_bits,
                                                     reinterpret_cast<unsigned long long*>(ctx->d_scratch));
   }
   RG_CUDA_OK(cudaGetLastError());
@@ -93,7 +93,6 @@ int rg_launch_jf_to_rufus(rg_ctx* ctx, const uint64_t* d_jf, uint64_t n, int k, 
 struct FilterSmem {
   uint32_t codes[FCODE_WORDS + 2];   // little-endian: base i of a word at bits (2i, 2i+1), rufus codes
   uint32_t bad[FBIT_WORDS + 2];      // little-endian flag bits
-  uint32_t bitmap[RG_SET_BITMAP_BITS / 32];
 };
 
 __device__ __forceinline__ void fconvert16(const uint4 s, const uint4 q, int minq, uint32_t& codes, uint32_t& bad) {
@@ -128,13 +127,13 @@ __global__ void __launch_bounds__(FILTER_THREADS)
 filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, const uint64_t* __restrict__ offs,
                    uint32_t read_len, uint64_t n_reads, uint64_t n_bytes, int k, int minq, int skip_last,
                    const uint64_t* __restrict__ table, uint32_t slots, const uint32_t* __restrict__ g_bitmap,
-                   int has_all_ones, int32_t* __restrict__ hits) {
-  extern __shared__ __align__(16) unsigned char fsm_raw[];
-  FilterSmem& sm = *reinterpret_cast<FilterSmem*>(fsm_raw);
+                   uint32_t bitmap_bits, int has_all_ones, int32_t* __restrict__ hits) {
+  extern __shared__ __align__(16) uint32_t s_bitmap[];   // bitmap_bits-bit prefilter of the set
+  __shared__ FilterSmem sm;
   {
     const uint4* src = reinterpret_cast<const uint4*>(g_bitmap);
-    uint4* dst = reinterpret_cast<uint4*>(sm.bitmap);
-    for (uint32_t i = threadIdx.x; i < RG_SET_BITMAP_BITS / 128; i += blockDim.x) dst[i] = __ldg(src + i);
+    uint4* dst = reinterpret_cast<uint4*>(s_bitmap);
+    for (uint32_t i = threadIdx.x; i < bitmap_bits / 128; i += blockDim.x) dst[i] = __ldg(src + i);
   }
   uint16_t* bad16 = reinterpret_cast<uint16_t*>(sm.bad);
   const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
@@ -173,8 +172,8 @@ filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, 
         hit = has_all_ones != 0;
       } else {
         const uint32_t h = rg_set_hash(v);
-        const uint32_t bit = h & (RG_SET_BITMAP_BITS - 1);
-        if (!((sm.bitmap[bit >> 5] >> (bit & 31)) & 1u)) continue;
+        const uint32_t bit = h & (bitmap_bits - 1);
+        if (!((s_bitmap[bit >> 5] >> (bit & 31)) & 1u)) continue;
         hit = false;
         uint32_t slot = h & (slots - 1);
         for (;;) {
@@ -215,20 +214,21 @@ int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const ui
   rg_ctx* ctx = s->ctx;
   RG_CUDA_OK(cudaMemsetAsync(hits, 0, n_reads * sizeof(int32_t), ctx->stream));
   if (n_bytes == 0 || n_reads == 0) return 0;
-  const size_t smem = sizeof(FilterSmem);
+  const size_t smem = s->bitmap_bits / 8;
   static bool attr_set = false;
   if (!attr_set) {
-    RG_CUDA_OK(cudaFuncSetAttribute(filter_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RG_CUDA_OK(cudaFuncSetAttribute(filter_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(RG_SET_BITMAP_BITS / 8)));
     attr_set = true;
   }
   const uint64_t n_chunks = (n_bytes + FCHUNK - 1) / FCHUNK;
-  unsigned grid = rg_grid(ctx, 3);
+  unsigned grid = rg_grid(ctx, smem >= 65536 ? 3 : (smem >= 32768 ? 6 : 8));
   if (n_chunks < grid) grid = (unsigned)n_chunks;
   {
     rg_launch_scope _ls(ctx, "filter_hits_kernel");
     filter_hits_kernel<<<grid, FILTER_THREADS, smem, ctx->stream>>>(seq, qual, offs, read_len, n_reads, n_bytes, s->k,
                                                                     minq, skip_last, s->table, s->slots, s->bitmap,
-                                                                    s->has_all_ones, hits);
+                                                                    s->bitmap_bits, s->has_all_ones, hits);
   }
   RG_CUDA_OK(cudaGetLastError());
   return 0;

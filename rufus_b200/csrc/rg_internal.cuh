@@ -82,7 +82,8 @@ struct rg_set {
   uint64_t n = 0;           // distinct rufus keys
   uint32_t slots = 0;       // power of two
   uint64_t* table = nullptr;  // open addressing, EMPTY = ~0
-  uint32_t* bitmap = nullptr;  // RG_SET_BITMAP_BITS-bit prefilter
+  uint32_t* bitmap = nullptr;  // bitmap_bits-bit prefilter (allocated at RG_SET_BITMAP_BITS)
+  uint32_t bitmap_bits = 1u << 15;  // power of two in [2^15, RG_SET_BITMAP_BITS], ~64 bits per member
   int has_all_ones = 0;     // the value ~0 itself is a member (k = 32, all T)
 };
 #define RG_SET_BITMAP_BITS (1u << 19)
