@@ -225,8 +225,8 @@ def main():
         streams.append(torch.from_numpy(np.concatenate([s1, s2]).reshape(-1)).to(dev))
     subj = tuple(torch.from_numpy(a.reshape(-1)).to(dev) for a in trio["Child"])
     bases_per_step = sum(int(s.numel()) for s in streams)
-    # distinct k-mers per shard: genomic/world + ~7.5 error k-mers per read
-    est = int((2.2 * args.genome) / world + 16 * args.pairs)
+    # distinct k-mers per shard: genomic (two haplotypes, ~3 % private) / world + ~6.2 error k-mers per read
+    est = int((1.03 * args.genome) / world + 6.2 * 2 * args.pairs)
     pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, 150 * world, MINQ, THRESH,
                                    mode=mode, rank=rank, world=world)
 
@@ -322,8 +322,10 @@ def main():
         res = None
         e2e_steps = max(3, args.steps // 2)
         for i in range(2):
+            tm = {}
             res = pipeline.host_step(ctx, K, host_streams, pairs_host, READ_LEN, est, MIN_COV, 150, MINQ, THRESH,
-                                     mode=mode, tables=tables)
+                                     mode=mode, tables=tables, timings=tm)
+            log("e2e warm-up pass, host-side phase times (ms):", {k: round(v, 2) for k, v in tm.items()})
         barrier()
         e0.record()
         for i in range(e2e_steps):

@@ -165,10 +165,10 @@ static int table_alloc_tiles(rg_table* t, uint32_t n_tiles) {
 }
 
 static uint32_t tiles_for(uint64_t est_distinct) {
-  // aim for <= 50 % load
-  uint64_t n = (est_distinct * 2 + RG_TILE_SLOTS - 1) >> RG_TILE_BITS;
+  // aim for <= 60 % load
+  uint64_t n = (est_distinct * 5 / 3 + RG_TILE_SLOTS - 1) >> RG_TILE_BITS;
   if (n < 1) n = 1;
-  if (n > (1u << 24)) n = 1u << 24;
+  if (n > (1u << 18)) n = 1u << 18;   // 2^18 tiles = 4 Gi slots: the slot bits come out of a 32-bit hash
   return (uint32_t)n;
 }
 
@@ -255,8 +255,8 @@ static int prepare_buckets(rg_table* t, uint64_t n_keys) {
   rg_ctx* ctx = t->ctx;
   // bucket capacity: mean keys per tile + 25 % + slack; overflow goes to the spill list
   const uint64_t mean = n_keys / t->n_tiles + 1;
-  uint64_t cap = mean + mean / 4 + 1024;
-  cap = (cap + 1) & ~1ull;  // keep slabs 16-byte aligned
+  uint64_t cap = mean + mean / 4 + 1024 + rg_partition_pad_keys(t->n_tiles, n_keys);
+  cap = (cap + 3) & ~3ull;  // slabs start on a 32-byte sector boundary
   if (!t->part_cursor) RG_CUDA_OK(cudaMalloc(&t->part_cursor, (uint64_t)t->n_tiles * sizeof(uint32_t)));
   if (t->part_cap < cap * t->n_tiles) {
     if (t->part_keys) {
@@ -480,7 +480,7 @@ int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occ, uint64_t*
 int rg_table_k(rg_table* t) { return t ? t->k : 0; }
 int rg_table_canonical(rg_table* t) { return t ? t->canonical : 0; }
 
-uint32_t rg_key_partition(uint64_t jf_key, uint32_t n_parts) { return rg_tile_of(rg_mix64(jf_key), n_parts); }
+uint32_t rg_key_partition(uint64_t jf_key, uint32_t n_parts) { return rg_tile_of_key(jf_key, n_parts); }
 
 int rg_extract_partition_dev(rg_ctx* ctx, int k, int canonical, const char* dev_stream, uint64_t n_bytes,
                              uint32_t read_stride, uint32_t n_parts, uint64_t* keys_out_dev,

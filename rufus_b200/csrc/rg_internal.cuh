@@ -15,10 +15,10 @@
 // RG_TILE_SLOTS slots, stored SoA: keys[] (u64, EMPTY = ~0) and counts[] (u32).
 // One tile = 128 KiB of keys + 64 KiB of counts = 192 KiB: exactly what one CTA
 // stages in shared memory (227 KiB/SM on B200) in the tiled insert.
-//   h      = mix64(key)
-//   tile   = mulhi32(h >> 32, n_tiles_global)      ("hash prefix": also the shard id
-//                                                    of the multi-GPU partition)
-//   slot0  = h & (RG_TILE_SLOTS-1)
+//   h      = hash32(key)                  (xor-fold + one 64-bit Fibonacci multiply, high word)
+//   p      = h * n_tiles_global           (64-bit product)
+//   tile   = p >> 32                      ("hash prefix": also the shard id of the multi-GPU partition)
+//   slot0  = low32(p) >> (32 - RG_TILE_BITS)   (the position of h inside its tile's hash range)
 // ---------------------------------------------------------------------------
 #define RG_TILE_BITS 14
 #define RG_TILE_SLOTS (1u << RG_TILE_BITS)
@@ -119,8 +119,23 @@ __host__ __device__ __forceinline__ uint64_t rg_mix64(uint64_t h) {
   return h;
 }
 
-__host__ __device__ __forceinline__ uint32_t rg_tile_of(uint64_t h, uint32_t n_tiles_global) {
-  return (uint32_t)(((h >> 32) * (uint64_t)n_tiles_global) >> 32);
+// table hash: cheap enough for the per-k-mer inner loops (~7 integer instructions)
+__host__ __device__ __forceinline__ uint32_t rg_hash32(uint64_t key) {
+  uint64_t x = key ^ (key >> 29);
+  x *= 0x9E3779B97F4A7C15ull;
+  return (uint32_t)(x >> 32);
+}
+
+// tile (global numbering) and home slot of a key
+__host__ __device__ __forceinline__ void rg_locate(uint64_t key, uint32_t n_tiles_global, uint32_t& tile,
+                                                   uint32_t& slot) {
+  const uint64_t p = (uint64_t)rg_hash32(key) * n_tiles_global;
+  tile = (uint32_t)(p >> 32);
+  slot = (uint32_t)p >> (32 - RG_TILE_BITS);
+}
+
+__host__ __device__ __forceinline__ uint32_t rg_tile_of_key(uint64_t key, uint32_t n_tiles_global) {
+  return (uint32_t)(((uint64_t)rg_hash32(key) * n_tiles_global) >> 32);
 }
 
 // reverse complement of a jf key (first base in the MSBs of 2k bits)
@@ -159,11 +174,11 @@ static inline TableView rg_view(const rg_table* t) {
 
 // add `add` to key's counter in a global-memory table. Returns 0 ok, 1 tile full, 2 foreign shard.
 __device__ __forceinline__ int rg_table_add(const TableView& tv, uint64_t key, uint32_t add) {
-  const uint64_t h = rg_mix64(key);
-  const uint32_t tile = rg_tile_of(h, tv.n_tiles_global) - tv.tile_first;
+  uint32_t tile, slot;
+  rg_locate(key, tv.n_tiles_global, tile, slot);
+  tile -= tv.tile_first;
   if (tile >= tv.n_tiles) return 2;
   const uint64_t base = (uint64_t)tile << RG_TILE_BITS;
-  uint32_t slot = (uint32_t)h & (RG_TILE_SLOTS - 1);
   for (uint32_t probe = 0; probe < RG_TILE_SLOTS; ++probe) {
     unsigned long long* kp = (unsigned long long*)(tv.keys + base + slot);
     unsigned long long cur = *(volatile unsigned long long*)kp;
@@ -179,11 +194,11 @@ __device__ __forceinline__ int rg_table_add(const TableView& tv, uint64_t key, u
 
 // count of key (0 if absent)
 __device__ __forceinline__ uint32_t rg_table_get(const TableView& tv, uint64_t key) {
-  const uint64_t h = rg_mix64(key);
-  const uint32_t tile = rg_tile_of(h, tv.n_tiles_global) - tv.tile_first;
+  uint32_t tile, slot;
+  rg_locate(key, tv.n_tiles_global, tile, slot);
+  tile -= tv.tile_first;
   if (tile >= tv.n_tiles) return 0;
   const uint64_t base = (uint64_t)tile << RG_TILE_BITS;
-  uint32_t slot = (uint32_t)h & (RG_TILE_SLOTS - 1);
   for (uint32_t probe = 0; probe < RG_TILE_SLOTS; ++probe) {
     const uint64_t cur = __ldg(tv.keys + base + slot);
     if (cur == key) return __ldg(tv.counts + base + slot);
@@ -208,7 +223,8 @@ struct ExtractParams {
 int rg_launch_count_direct(rg_table* t, const ExtractParams& ep);
 int rg_launch_partition(rg_table* t, const ExtractParams& ep);   // into t->part_keys buckets
 int rg_launch_partition_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n);
-int rg_launch_tile_insert(rg_table* t);                           // consume buckets
+int rg_launch_tile_insert(rg_table* t);
+uint64_t rg_partition_pad_keys(uint32_t n_tiles, uint64_t n_units);                           // consume buckets
 int rg_launch_insert_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n, const uint32_t* dev_counts);
 int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads, uint32_t* brk);
 int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, uint32_t n_parts, uint64_t* keys_out,

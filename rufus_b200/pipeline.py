@@ -162,26 +162,40 @@ class DevicePipeline:
 
 def host_step(ctx: api.Context, k: int, host_streams, subject_pairs, read_len: int, est_distinct: int,
               min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
-              mode: int = api.MODE_TILED, tables=None):
+              mode: int = api.MODE_TILED, tables=None, timings: dict | None = None):
     """The same pass through the public host-buffer API: every input starts in host
     memory (pinned or not), results come back to host memory.
 
     host_streams: list of uint8 numpy arrays (subject first), reads separated by a
     non-ACGT byte. subject_pairs: (seq1, qual1, seq2, qual2) numpy [n_pairs, read_len]."""
+    import time
+
+    def lap(name, t0):
+        if timings is not None:
+            ctx.sync()
+            timings[name] = timings.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return time.perf_counter()
+
     own = tables is None
     if own:
         tables = [api.KmerTable(ctx, k, True, est_distinct, mode) for _ in host_streams]
+    t0 = time.perf_counter()
     for t, s in zip(tables, host_streams):
         t.clear()
         t.push_stream(s)
         t.end(trim=False)
+    t0 = lap("count_ms", t0)
     h = tables[0].histo(min_count=lower[0])
+    t0 = lap("histo_ms", t0)
     hk, hc = api.subtract(tables[0], tables[1:], subj_min=lower[0], other_min=list(lower[1:]), min_cov=min_cov,
                           max_cov=max_cov, sort=False)
+    t0 = lap("subtract_ms", t0)
     mset = api.MutantSet.from_jf_keys(ctx, hk, k)
     s1, q1, s2, q2 = subject_pairs
     offs = np.arange(s1.shape[0] + 1, dtype=np.uint64) * np.uint64(read_len)
+    t0 = lap("set_ms", t0)
     keep = mset.filter_pairs(s1, q1, offs, s2, q2, offs, minq, thresh)
+    t0 = lap("filter_ms", t0)
     mset.free()
     if own:
         for t in tables:
