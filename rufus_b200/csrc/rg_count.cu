@@ -134,6 +134,14 @@ int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads,
 // DRAM round trip per k-mer.
 // ---------------------------------------------------------------------------
 constexpr int TILE_THREADS = 1024;
+constexpr uint32_t TILE_RING_KEYS = 128;   // per-warp staging ring of the bucket stream (1 KiB x 32 warps)
+constexpr size_t TILE_SMEM = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (TILE_THREADS / 32) * TILE_RING_KEYS * 8;
+
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -211,46 +219,77 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
     __syncthreads();
   }
 
-  // stream the bucket: 8 keys (four 16-byte loads) in flight per thread before the first insert
-  const uint4* src = reinterpret_cast<const uint4*>(part_keys + (uint64_t)tile * bucket_cap);
-  const uint32_t n2 = (n + 1) >> 1;                    // bucket slabs are 32-byte aligned and padded with RG_EMPTY
-  constexpr int UNROLL = 4;
-  for (uint32_t i0 = 0; i0 < n2; i0 += UNROLL * blockDim.x) {
-    uint4 v[UNROLL];
+  // Stream the bucket. Warp w consumes the w-th 1/32 of the bucket through a private 128-key ring
+  // in shared memory that is kept full with cp.async (4 quarters of 32 keys, 3 in flight ahead of
+  // the reader). Lanes REFILL themselves from the ring: each iteration the lanes whose key has
+  // found its slot claim the next keys of the warp's stream (ballot + popc), so the probe loop
+  // runs ~(mean probes) iterations per key instead of (max over the 32 lanes), and it stays
+  // convergent: every lane executes every iteration until the whole warp is done.
+  {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64) +
+                     warp * TILE_RING_KEYS;
+    const uint64_t* src = part_keys + (uint64_t)tile * bucket_cap;
+    const uint32_t chunk = (n + 31) >> 5;
+    const uint32_t begin = min(n, warp * chunk), end = min(n, begin + chunk);
+    uint32_t issued = begin;          // cp.async issued for keys [begin, issued)
+    auto issue_quarter = [&]() {
+      const uint32_t i = issued + lane;
+      if (i < end) cp_async_8(ring + ((i - begin) & (TILE_RING_KEYS - 1)), src + i);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      issued += 32;
+    };
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const uint32_t idx = i0 + u * blockDim.x + threadIdx.x;
-      v[u] = idx < n2 ? __ldg(src + idx) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const uint32_t idx = i0 + u * blockDim.x + threadIdx.x;
-      uint64_t two[2] = {((uint64_t)v[u].y << 32) | v[u].x, ((uint64_t)v[u].w << 32) | v[u].z};
-      if (2 * idx + 1 >= n) two[1] = RG_EMPTY;         // odd tail
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint64_t key = two[h];
-        if (key == RG_EMPTY) continue;                 // pad slot of a partition run
-        uint32_t tile_unused, slot;
-        rg_locate(key, n_tiles_global, tile_unused, slot);
-        bool done = false;
-        for (uint32_t probe = 0; probe < RG_TILE_SLOTS; ++probe) {
-          unsigned long long cur = *(volatile unsigned long long*)(skeys + slot);
-          if (cur == RG_EMPTY)
-            cur = atomicCAS((unsigned long long*)(skeys + slot), (unsigned long long)RG_EMPTY, (unsigned long long)key);
-          if (cur == RG_EMPTY || cur == key) {
-            atomicAdd(scounts + slot, 1u);
-            done = true;
-            break;
-          }
-          slot = (slot + 1) & (RG_TILE_SLOTS - 1);
-        }
-        if (!done) {
-          const uint64_t sp = atomicAdd((unsigned long long*)&status[0], 1ull);
-          if (sp < spill_cap) spill[sp] = key;
+    for (int q = 0; q < 4; ++q) issue_quarter();
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    uint32_t head = begin;            // next unclaimed key of the warp's stream
+    uint32_t slot = 0, probes = 0;
+    uint64_t key = RG_EMPTY;
+    bool have = false;
+    for (;;) {
+      // ---- claim: lanes without a key take the next ones of the stream
+      const uint32_t want = __ballot_sync(0xFFFFFFFFu, !have);
+      const uint32_t my = head + __popc(want & lt_mask);
+      if (!have && my < end) {
+        key = ring[(my - begin) & (TILE_RING_KEYS - 1)];
+        if (key != RG_EMPTY) {        // (pad slots of the partition runs are skipped)
+          uint32_t tile_unused;
+          rg_locate(key, n_tiles_global, tile_unused, slot);
+          probes = 0;
+          have = true;
         }
       }
+      const uint32_t old_head = head;
+      head = min(end, head + (uint32_t)__popc(want));
+      // ---- the reader left a quarter of the ring: refill it with the quarter 4 ahead
+      if (((head - begin) >> 5) != ((old_head - begin) >> 5)) {
+        __syncwarp();                 // every lane has read its claim before the slot is overwritten
+        issue_quarter();
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();                 // the two quarters the next claims can touch are complete for all lanes
+      }
+      // ---- one probe for every lane that holds a key
+      if (have) {
+        unsigned long long seen = *(volatile unsigned long long*)(skeys + slot);
+        if (seen == RG_EMPTY)
+          seen = atomicCAS((unsigned long long*)(skeys + slot), (unsigned long long)RG_EMPTY, (unsigned long long)key);
+        if (seen == RG_EMPTY || seen == key) {
+          atomicAdd(scounts + slot, 1u);
+          have = false;
+        } else {
+          slot = (slot + 1) & (RG_TILE_SLOTS - 1);
+          if (++probes == RG_TILE_SLOTS) {             // tile full
+            const uint64_t sp = atomicAdd((unsigned long long*)&status[0], 1ull);
+            if (sp < spill_cap) spill[sp] = key;
+            have = false;
+          }
+        }
+      }
+      if (head >= end && !__any_sync(0xFFFFFFFFu, have)) break;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   // generic-proxy writes -> visible to the async proxy, then bulk store the tile
@@ -270,7 +309,7 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
 
 int rg_launch_tile_insert(rg_table* t) {
   rg_ctx* ctx = t->ctx;
-  const size_t smem = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64;
+  const size_t smem = TILE_SMEM;
   static bool attr_set = false;
   if (!attr_set) {
     RG_CUDA_OK(cudaFuncSetAttribute(tile_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

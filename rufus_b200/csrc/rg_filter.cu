@@ -14,13 +14,24 @@
 // reads) and the read-boundary / last-base rule applied.
 #include "rg_internal.cuh"
 
-constexpr int FCHUNK = 4096;
-constexpr int FSTAGE = FCHUNK + 64;
-constexpr int FCODE_WORDS = FSTAGE / 16;
-constexpr int FBIT_WORDS = FSTAGE / 32;
-constexpr int FILTER_THREADS = 256;
+#include "rg_extract.cuh"
 
-__host__ __device__ __forceinline__ uint32_t rg_set_hash(uint64_t v) { return (uint32_t)(rg_mix64(v) >> 20); }
+constexpr int FILTER_THREADS = 512;
+constexpr int FILTER_R = 16;                         // windows per thread: one 16-base word, all shifts static
+constexpr int FCHUNK = FILTER_THREADS * FILTER_R;    // window starts per CTA chunk
+constexpr int FCODE_WORDS = FCHUNK / 16 + 3;         // + 48 bases of tail
+constexpr int FBIT_WORDS = FCHUNK / 32 + 2;
+
+// one multiply: the high word picks the prefilter bit, the middle bits the set slot
+__host__ __device__ __forceinline__ uint64_t rg_set_mix(uint64_t v) {
+  return (v ^ (v >> 29)) * 0x9E3779B97F4A7C15ull;
+}
+__host__ __device__ __forceinline__ uint32_t rg_set_bit(uint64_t mix, uint32_t bitmap_bits) {
+  return (uint32_t)(mix >> 32) & (bitmap_bits - 1);
+}
+__host__ __device__ __forceinline__ uint32_t rg_set_slot(uint64_t mix, uint32_t slots) {
+  return (uint32_t)(mix >> 17) & (slots - 1);
+}
 
 // ---- set construction -----------------------------------------------------
 __global__ void set_build_kernel(const uint64_t* __restrict__ vals, uint64_t n, uint64_t* table, uint32_t slots,
@@ -28,9 +39,10 @@ __global__ void set_build_kernel(const uint64_t* __restrict__ vals, uint64_t n, 
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t v = vals[i];
     if (v == RG_EMPTY) continue;   // handled by has_all_ones on the host
-    const uint32_t h = rg_set_hash(v);
-    atomicOr(bitmap + ((h & (bitmap_bits - 1)) >> 5), 1u << (h & 31));
-    uint32_t slot = h & (slots - 1);
+    const uint64_t mix = rg_set_mix(v);
+    const uint32_t bit = rg_set_bit(mix, bitmap_bits);
+    atomicOr(bitmap + (bit >> 5), 1u << (bit & 31));
+    uint32_t slot = rg_set_slot(mix, slots);
     for (;;) {
       const unsigned long long cur = atomicCAS((unsigned long long*)(table + slot), (unsigned long long)RG_EMPTY,
                                                (unsigned long long)v);
@@ -90,92 +102,134 @@ int rg_launch_jf_to_rufus(rg_ctx* ctx, const uint64_t* d_jf, uint64_t n, int k, 
 }
 
 // ---- the filter -------------------------------------------------------------
-struct FilterSmem {
-  uint32_t codes[FCODE_WORDS + 2];   // little-endian: base i of a word at bits (2i, 2i+1), rufus codes
-  uint32_t bad[FBIT_WORDS + 2];      // little-endian flag bits
+struct FilterStage {
+  uint32_t codes[FCODE_WORDS + 1];   // little-endian: base i of a word at bits (2i, 2i+1), rufus codes
+  uint32_t bad[FBIT_WORDS + 2];      // little-endian flag bits: low quality, 'N', or past the end of the stream
 };
 
-__device__ __forceinline__ void fconvert16(const uint4 s, const uint4 q, int minq, uint32_t& codes, uint32_t& bad) {
+// 16 sequence + 16 quality bytes -> 16 rufus codes (Util::HashToLong: C -> bit 2i+1, G -> bit 2i,
+// T -> both, anything else 0) and 16 streak-reset flags (qual-33 < MinQ as signed char, or 'N').
+// thr4 = (MinQ + 33) replicated in the four bytes; all_bad / none_bad cover thresholds outside a char.
+__device__ __forceinline__ void fconvert16(const uint4 s, const uint4 q, uint32_t thr4, bool all_bad, uint32_t& codes,
+                                           uint32_t& bad) {
   const uint32_t sw[4] = {s.x, s.y, s.z, s.w};
   const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
   codes = 0;
   bad = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t c = (sw[i] >> (8 * j)) & 0xFFu;
-      const int qv = (int)(signed char)((qw[i] >> (8 * j)) & 0xFFu) - 33;
-      // Util::HashToLong: C -> bit(2i+1), G -> bit(2i), T -> both, anything else 0
-      const uint32_t code = (c == 'C') ? 2u : (c == 'G') ? 1u : (c == 'T') ? 3u : 0u;
-      const int idx = i * 4 + j;
-      codes |= code << (2 * idx);
-      bad |= (uint32_t)((qv < minq) || (c == 'N')) << idx;
-    }
+    const uint32_t c4 = (__vcmpeq4(sw[i], 0x43434343u) & 0x02020202u) | (__vcmpeq4(sw[i], 0x47474747u) & 0x01010101u) |
+                        (__vcmpeq4(sw[i], 0x54545454u) & 0x03030303u);
+    codes |= ((c4 | (c4 >> 6) | (c4 >> 12) | (c4 >> 18)) & 0xFFu) << (8 * i);
+    const uint32_t b4 = (__vcmplts4(qw[i], thr4) | __vcmpeq4(sw[i], 0x4E4E4E4Eu)) & 0x01010101u;
+    bad |= ((b4 | (b4 >> 7) | (b4 >> 14) | (b4 >> 21)) & 0xFu) << (4 * i);
   }
+  if (all_bad) bad = 0xFFFFu;
 }
 
 __device__ __forceinline__ uint4 load16_guarded(const char* base, uint64_t p, uint64_t n, unsigned char fill) {
   if (p + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(base + p));
+  const uint32_t f4 = fill * 0x01010101u;
+  if (p >= n) return make_uint4(f4, f4, f4, f4);
   unsigned char tmp[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) tmp[j] = (p + j < n) ? (unsigned char)base[p + j] : fill;
   return *reinterpret_cast<uint4*>(tmp);
 }
 
+struct FilterPrefetch {
+  uint4 s, q, ts, tq;
+};
+
+__device__ __forceinline__ void filter_prefetch(FilterPrefetch& pf, const char* seq, const char* qual, uint64_t n_bytes,
+                                                uint64_t c0) {
+  // past-the-end bases read as 'N': the streak resets there, like at the end of the reference's read
+  pf.s = load16_guarded(seq, c0 + (uint64_t)threadIdx.x * 16, n_bytes, 'N');
+  pf.q = load16_guarded(qual, c0 + (uint64_t)threadIdx.x * 16, n_bytes, 0);
+  if (threadIdx.x < 3) {
+    pf.ts = load16_guarded(seq, c0 + (uint64_t)(FILTER_THREADS + threadIdx.x) * 16, n_bytes, 'N');
+    pf.tq = load16_guarded(qual, c0 + (uint64_t)(FILTER_THREADS + threadIdx.x) * 16, n_bytes, 0);
+  }
+}
+
+__device__ __forceinline__ void filter_stage_store(FilterStage& sm, const FilterPrefetch& pf, uint32_t thr4,
+                                                   bool all_bad) {
+  uint16_t* bad16 = reinterpret_cast<uint16_t*>(sm.bad);
+  uint32_t c, b;
+  fconvert16(pf.s, pf.q, thr4, all_bad, c, b);
+  sm.codes[threadIdx.x] = c;
+  bad16[threadIdx.x] = (uint16_t)b;
+  if (threadIdx.x < 3) {
+    fconvert16(pf.ts, pf.tq, thr4, all_bad, c, b);
+    sm.codes[FILTER_THREADS + threadIdx.x] = c;
+    bad16[FILTER_THREADS + threadIdx.x] = (uint16_t)b;
+  }
+  if (threadIdx.x == 3) {
+    sm.codes[FCODE_WORDS] = 0;
+    bad16[FILTER_THREADS + 3] = 0xFFFFu;
+    sm.bad[FBIT_WORDS] = 0xFFFFFFFFu;
+    sm.bad[FBIT_WORDS + 1] = 0xFFFFFFFFu;
+  }
+}
+
+// Position-parallel: thread t owns the 16 windows starting at bases 16t..16t+15 of the chunk. A
+// window is tested iff its K flag bits are clear; its rufus key is two static funnel shifts of the
+// staged code words; membership = shared-memory bitmap prefilter (one multiply), then the
+// L2-resident set. Only on a hit is the owning read located and the read-boundary rule applied.
 __global__ void __launch_bounds__(FILTER_THREADS)
 filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, const uint64_t* __restrict__ offs,
                    uint32_t read_len, uint64_t n_reads, uint64_t n_bytes, int k, int minq, int skip_last,
                    const uint64_t* __restrict__ table, uint32_t slots, const uint32_t* __restrict__ g_bitmap,
                    uint32_t bitmap_bits, int has_all_ones, int32_t* __restrict__ hits) {
   extern __shared__ __align__(16) uint32_t s_bitmap[];   // bitmap_bits-bit prefilter of the set
-  __shared__ FilterSmem sm;
+  __shared__ FilterStage sm;
   {
     const uint4* src = reinterpret_cast<const uint4*>(g_bitmap);
     uint4* dst = reinterpret_cast<uint4*>(s_bitmap);
     for (uint32_t i = threadIdx.x; i < bitmap_bits / 128; i += blockDim.x) dst[i] = __ldg(src + i);
   }
-  uint16_t* bad16 = reinterpret_cast<uint16_t*>(sm.bad);
+  // RUFUS.Filter.cpp:207: `qual[i]-33 < MinQ` on a (signed) char
+  const int thr = minq + 33;
+  const bool all_bad = thr > 127;
+  const uint32_t thr4 = (uint32_t)(uint8_t)(int8_t)(thr < -128 ? -128 : (thr > 127 ? 127 : thr)) * 0x01010101u;
   const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
   const uint64_t n_chunks = (n_bytes + FCHUNK - 1) / FCHUNK;
+  FilterPrefetch pf;
+  if (blockIdx.x < n_chunks) filter_prefetch(pf, seq, qual, n_bytes, (uint64_t)blockIdx.x * FCHUNK);
   for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const uint64_t c0 = c * FCHUNK;
+    __syncthreads();                         // previous chunk's windows are done with the stage
+    filter_stage_store(sm, pf, thr4, all_bad);
+    if (c + gridDim.x < n_chunks) filter_prefetch(pf, seq, qual, n_bytes, (c + gridDim.x) * FCHUNK);
     __syncthreads();
-    for (int i = threadIdx.x; i < FCODE_WORDS; i += blockDim.x) {
-      const uint64_t p = c0 + (uint64_t)i * 16;
-      uint32_t cw = 0, bw = 0xFFFFu;
-      if (p < n_bytes) {
-        const uint4 s4 = load16_guarded(seq, p, n_bytes, 'N');
-        const uint4 q4 = load16_guarded(qual, p, n_bytes, 0);
-        fconvert16(s4, q4, minq, cw, bw);
-      }
-      sm.codes[i] = cw;
-      bad16[i] = (uint16_t)bw;
+    const int t = threadIdx.x;
+    const uint32_t valid = (uint32_t)and_run(~bits_at(sm.bad, t * FILTER_R), k) & 0xFFFFu;
+    if (valid == 0) continue;
+    const uint32_t V0 = sm.codes[t], V1 = sm.codes[t + 1], V2 = sm.codes[t + 2];
+    // pass 1 (branch-free): which windows pass the prefilter
+    uint32_t maybe = 0;
+#pragma unroll
+    for (int w = 0; w < FILTER_R; ++w) {
+      const uint32_t lo = w ? __funnelshift_r(V0, V1, 2 * w) : V0;
+      const uint32_t hi = w ? __funnelshift_r(V1, V2, 2 * w) : V1;
+      const uint64_t v = (((uint64_t)hi << 32) | lo) & kmask;
+      const uint32_t bit = rg_set_bit(rg_set_mix(v), bitmap_bits);
+      maybe |= ((s_bitmap[bit >> 5] >> (bit & 31)) & 1u) << w;
     }
-    if (threadIdx.x < 2) {
-      sm.codes[FCODE_WORDS + threadIdx.x] = 0;
-      sm.bad[FBIT_WORDS + threadIdx.x] = 0xFFFFFFFFu;
-    }
-    __syncthreads();
-    for (int p = threadIdx.x; p < FCHUNK; p += blockDim.x) {
-      const uint64_t gp = c0 + p;
-      if (gp + k > n_bytes) break;
-      const int bj = p >> 5, bs = p & 31;
-      const uint64_t badw = (((uint64_t)sm.bad[bj + 1] << 32) | sm.bad[bj]) >> bs;
-      if (badw & ((k == 64) ? ~0ull : ((1ull << k) - 1))) continue;
-      const int j = p >> 4, s = (p & 15) * 2;
-      uint64_t x = ((uint64_t)sm.codes[j + 1] << 32) | sm.codes[j];
-      if (s) x = (x >> s) | ((uint64_t)sm.codes[j + 2] << (64 - s));
+    maybe &= valid;
+    // pass 2 (rare): exact lookup, then the read that owns the window
+    while (maybe) {
+      const int w = __ffs(maybe) - 1;
+      maybe &= maybe - 1;
+      uint64_t x = ((uint64_t)V1 << 32) | V0;
+      if (w) x = (x >> (2 * w)) | ((uint64_t)V2 << (64 - 2 * w));
       const uint64_t v = x & kmask;
       bool hit;
       if (v == RG_EMPTY) {
         hit = has_all_ones != 0;
       } else {
-        const uint32_t h = rg_set_hash(v);
-        const uint32_t bit = h & (bitmap_bits - 1);
-        if (!((s_bitmap[bit >> 5] >> (bit & 31)) & 1u)) continue;
         hit = false;
-        uint32_t slot = h & (slots - 1);
+        uint32_t slot = rg_set_slot(rg_set_mix(v), slots);
         for (;;) {
           const uint64_t cur = __ldg(table + slot);
           if (cur == v) { hit = true; break; }
@@ -184,8 +238,8 @@ filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, 
         }
       }
       if (!hit) continue;
-      // locate the read that owns base gp and apply the boundary rules
-      uint64_t r, r0, r1;
+      const uint64_t gp = c0 + (uint64_t)t * FILTER_R + w;
+      uint64_t r, r1;
       if (offs != nullptr) {
         uint64_t lo = 0, hi = n_reads;   // largest r with offs[r] <= gp
         while (hi - lo > 1) {
@@ -193,16 +247,13 @@ filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, 
           if (__ldg(offs + mid) <= gp) lo = mid; else hi = mid;
         }
         r = lo;
-        r0 = __ldg(offs + r);
         r1 = __ldg(offs + r + 1);
         // empty reads share their offset with the next read: skip forward to the owner
-        while (r1 <= gp && r + 1 < n_reads) { ++r; r0 = r1; r1 = __ldg(offs + r + 1); }
+        while (r1 <= gp && r + 1 < n_reads) { ++r; r1 = __ldg(offs + r + 1); }
       } else {
         r = gp / read_len;
-        r0 = r * read_len;
-        r1 = r0 + read_len;
+        r1 = (r + 1) * read_len;
       }
-      (void)r0;
       const uint64_t end_excl = skip_last ? (r1 > 0 ? r1 - 1 : 0) : r1;   // window must end before this
       if (gp + k <= end_excl) atomicAdd(hits + r, 1);
     }
@@ -222,7 +273,7 @@ int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const ui
     attr_set = true;
   }
   const uint64_t n_chunks = (n_bytes + FCHUNK - 1) / FCHUNK;
-  unsigned grid = rg_grid(ctx, smem >= 65536 ? 3 : (smem >= 32768 ? 6 : 8));
+  unsigned grid = rg_grid(ctx, smem >= 65536 ? 3 : 4);
   if (n_chunks < grid) grid = (unsigned)n_chunks;
   {
     rg_launch_scope _ls(ctx, "filter_hits_kernel");

@@ -17,12 +17,30 @@
 #include "rg_extract.cuh"
 
 constexpr int PART_THREADS = 1024;
-constexpr uint32_t PART_MAX_TILES = 8192;
-constexpr size_t PART_SMEM_LIMIT = 232448;         // 227 KiB opt-in limit per CTA (static + dynamic)
+constexpr int PART_R = 16;                          // windows per thread: one 16-base word, so every shift below is static
+constexpr uint32_t PART_K = PART_THREADS * PART_R;  // windows (keys) counting-sorted at once
+constexpr size_t PART_SMEM_LIMIT = 232448;          // 227 KiB opt-in limit per CTA (static + dynamic)
 
-template <int R>
-constexpr size_t part_static_smem() { return sizeof(StageT<PART_THREADS, R>) + 33 * sizeof(uint32_t) + 128; }
-static size_t part_dynamic_smem(int r, uint32_t n_tiles) { return (size_t)r * PART_THREADS * 10 + (size_t)n_tiles * 12; }
+// Staging of one super-chunk (PART_K window starts + 48 bases of tail) as four bit streams:
+//   fwd : 16 bases per word, BIG-endian (base i of the word at bits 31-2i..30-2i), A0 C1 G2 T3:
+//         a left funnel shift of three consecutive words by 2w puts window w's first base in the MSBs,
+//         i.e. the Jellyfish forward key (mer_dna.hpp:330-354) after one right shift by 64-2k
+//   rcw : 16 bases per word, LITTLE-endian (base i at bits 2i..2i+1), complemented codes: a right
+//         funnel shift by 2w and a 2k-bit mask give the reverse-complement key directly
+//   bad : 1 bit per base, set for every byte outside ACGTacgt (window restart, mer_iterator.hpp:72-79)
+//   brk : 1 bit per base, set where a new read starts (offset / fixed-stride inputs)
+struct PartStage {
+  static constexpr int CODE_WORDS = PART_K / 16 + 3;
+  static constexpr int BIT_WORDS = PART_K / 32 + 2;
+  uint32_t fwd[CODE_WORDS + 1];
+  uint32_t rcw[CODE_WORDS + 1];
+  uint32_t bad[BIT_WORDS + 2];
+  uint32_t brk[BIT_WORDS + 2];
+};
+
+constexpr size_t part_static_smem() { return sizeof(PartStage) + 33 * sizeof(uint32_t) + 256; }
+// ukeys (8 B) + sorted (tile,index) entries (4 B) per key; count->gdelta and loff per tile
+static size_t part_dynamic_smem(uint32_t n_tiles) { return (size_t)PART_K * 12 + (size_t)n_tiles * 8; }
 
 struct PartGeom {
   uint32_t n_tiles_global, tile_first, n_tiles;
@@ -60,115 +78,257 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
   return warp_sums[warp] + incl - v;
 }
 
+// 16 ASCII bytes -> big-endian forward codes, little-endian complemented codes, 16 bad flags
+__device__ __forceinline__ void convert16_both(const uint4 v, uint32_t& fwd_be, uint32_t& rc_le, uint32_t& bad) {
+  uint32_t le;
+  convert16_le(v, le, bad);
+  rc_le = ~le;
+  uint32_t r = __brev(le);                                    // reverses bits: 2-bit groups end up bit-swapped
+  fwd_be = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+
+__device__ __forceinline__ uint4 load16_stream(const ExtractParams& ep, uint64_t p) {
+  uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+  if (p + 16 <= ep.n_bytes) {
+    v = __ldg(reinterpret_cast<const uint4*>(ep.stream + p));
+  } else if (p < ep.n_bytes) {
+    unsigned char tmp[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tmp[j] = (p + j < ep.n_bytes) ? (unsigned char)ep.stream[p + j] : (unsigned char)'\n';
+    v = *reinterpret_cast<uint4*>(tmp);
+  }
+  return v;
+}
+
+// read-start flags of the 32 bases starting at stream position p (p multiple of 32);
+// r_p = p % read_stride (tracked incrementally by the caller: no 64-bit division per word)
+__device__ __forceinline__ uint32_t brk_word(const ExtractParams& ep, uint64_t p, uint32_t r_p) {
+  uint32_t w = 0;
+  if (ep.brk != nullptr) {
+    if (p < ep.n_bytes) w = __ldg(ep.brk + (p >> 5));
+  } else if (ep.read_stride != 0) {
+    const uint32_t first = r_p == 0 ? 0 : ep.read_stride - r_p;  // offset of the first read start >= p
+    for (uint32_t j = first; j < 32; j += ep.read_stride) w |= 1u << j;
+  }
+  return w;
+}
+
+// What one thread prefetches for the next super-chunk: its 16 bases, (threads 0..2) one tail word,
+// and (threads < BIT_WORDS) one word of read-start flags.
+struct PartPrefetch {
+  uint4 body, tail;
+  uint32_t brk;
+};
+
+// r0 = s0 % read_stride (read_stride < 2^31, checked on the host)
+__device__ __forceinline__ void part_prefetch(PartPrefetch& pf, const ExtractParams& ep, uint64_t s0, uint32_t r0) {
+  pf.body = load16_stream(ep, s0 + (uint64_t)threadIdx.x * 16);
+  if (threadIdx.x < 3) pf.tail = load16_stream(ep, s0 + (uint64_t)(PART_THREADS + threadIdx.x) * 16);
+  if (threadIdx.x < PartStage::BIT_WORDS) {
+    uint32_t r = 0;
+    if (ep.read_stride != 0) r = (r0 + threadIdx.x * 32u) % ep.read_stride;
+    pf.brk = brk_word(ep, s0 + (uint64_t)threadIdx.x * 32, r);
+  }
+}
+
+__device__ __forceinline__ void part_stage_store(PartStage& sm, const PartPrefetch& pf) {
+  uint16_t* bad16 = reinterpret_cast<uint16_t*>(sm.bad);
+  uint32_t f, r, b;
+  convert16_both(pf.body, f, r, b);
+  sm.fwd[threadIdx.x] = f;
+  sm.rcw[threadIdx.x] = r;
+  bad16[threadIdx.x] = (uint16_t)b;
+  if (threadIdx.x < 3) {
+    convert16_both(pf.tail, f, r, b);
+    sm.fwd[PART_THREADS + threadIdx.x] = f;
+    sm.rcw[PART_THREADS + threadIdx.x] = r;
+    bad16[PART_THREADS + threadIdx.x] = (uint16_t)b;
+  }
+  if (threadIdx.x < PartStage::BIT_WORDS) sm.brk[threadIdx.x] = pf.brk;
+  if (threadIdx.x == 3) {
+    sm.fwd[PartStage::CODE_WORDS] = 0;
+    sm.rcw[PartStage::CODE_WORDS] = 0;
+    bad16[PART_THREADS + 3] = 0xFFFFu;
+    sm.bad[PartStage::BIT_WORDS] = 0xFFFFFFFFu;
+    sm.bad[PartStage::BIT_WORDS + 1] = 0xFFFFFFFFu;
+    sm.brk[PartStage::BIT_WORDS] = 0;
+    sm.brk[PartStage::BIT_WORDS + 1] = 0;
+  }
+}
+
+// The 16 windows starting at bases 16t .. 16t+15 of the staged super-chunk: emit(w, key, ok) with
+// ok == false when window w holds no k-mer (key is then garbage). ~12 integer instructions per window.
+template <typename Emit>
+__device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, int canonical, Emit&& emit) {
+  const int p0 = t * PART_R;
+  const uint64_t good = ~bits_at(sm.bad, p0);
+  const uint64_t nobrk = ~bits_at(sm.brk, p0 + 1);          // bit j: no read starts at base p0+j+1
+  uint64_t valid = and_run(good, k);
+  if (k > 1) valid &= and_run(nobrk, k - 1);
+  const uint32_t W0 = sm.fwd[t], W1 = sm.fwd[t + 1], W2 = sm.fwd[t + 2];
+  const uint32_t V0 = sm.rcw[t], V1 = sm.rcw[t + 1], V2 = sm.rcw[t + 2];
+  const uint64_t mask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+  const int down = 64 - 2 * k;
+  const uint32_t valid16 = (uint32_t)valid;
+#pragma unroll
+  for (int w = 0; w < PART_R; ++w) {
+    const uint32_t fhi = w ? __funnelshift_l(W1, W0, 2 * w) : W0;
+    const uint32_t flo = w ? __funnelshift_l(W2, W1, 2 * w) : W1;
+    const uint32_t rlo = w ? __funnelshift_r(V0, V1, 2 * w) : V0;
+    const uint32_t rhi = w ? __funnelshift_r(V1, V2, 2 * w) : V1;
+    const uint64_t fwd = (((uint64_t)fhi << 32) | flo) >> down;
+    const uint64_t rc = (((uint64_t)rhi << 32) | rlo) & mask;
+    const uint64_t key = (!canonical || fwd < rc) ? fwd : rc;
+    emit(w, key, (valid16 & (1u << w)) != 0);
+  }
+}
+
 // FROM_KEYS = false: windows of the ASCII stream; true: an already extracted key list.
-// R = windows (keys) per thread per super-chunk; K = PART_THREADS * R keys are sorted at once.
-// ukeys is TRANSPOSED (key w of thread t at w*PART_THREADS + t) so that a warp's accesses are
-// conflict-free.
-template <bool FROM_KEYS, int R>
+// PART_K keys are counting-sorted by tile in shared memory per super-chunk:
+//   1. keys -> ukeys[] (transposed: key w of thread t at w*1024+t, conflict-free) and ONE shared
+//      atomic per key on the tile histogram whose return value is the key's rank inside its run;
+//      (tile, rank) stays in a register
+//   2. block scan -> local offsets; one global atomicAdd per non-empty tile reserves a run rounded
+//      up to 4 keys (a full 32-byte sector); its latency hides behind step 3
+//   3. entry (tile, index of the key in ukeys) is scattered to its sorted position
+//   4. copy-out in sorted order: consecutive threads write consecutive keys of a run, pad slots
+//      get RG_EMPTY (the tile insert skips them), so every global write is a fully covered sector.
+// The ASCII of the next super-chunk is prefetched into registers during steps 1-2.
+// SHARDED: the table holds one hash-prefix shard (multi-GPU), so keys of other shards are counted as foreign.
+template <bool FROM_KEYS, bool SHARDED>
 __global__ void __launch_bounds__(PART_THREADS, 1)
 partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, uint64_t n_in, PartGeom g) {
   extern __shared__ __align__(16) unsigned char dyn[];
-  using Stage = StageT<PART_THREADS, R>;
-  __shared__ Stage sm;
+  __shared__ PartStage sm;
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t scan_total;
-  constexpr uint32_t K = PART_THREADS * R;
-  uint64_t* ukeys = reinterpret_cast<uint64_t*>(dyn);                 // [K]
-  uint16_t* spos = reinterpret_cast<uint16_t*>(dyn + (size_t)K * 8);  // [K] key indices in bucket order
-  uint32_t* hist = reinterpret_cast<uint32_t*>(dyn + (size_t)K * 10); // [n_tiles] count, then remaining rank
-  uint32_t* loff = hist + g.n_tiles;                                  // [n_tiles] local offset of the run
-  uint32_t* gbase = loff + g.n_tiles;                                 // [n_tiles] offset of the run in its bucket
+  __shared__ uint32_t any_overflow;
+  uint64_t* ukeys = reinterpret_cast<uint64_t*>(dyn);                        // [PART_K]
+  uint32_t* sorted = reinterpret_cast<uint32_t*>(dyn + (size_t)PART_K * 8);  // [PART_K] (tile << 16) | key index
+  uint32_t* hist = sorted + PART_K;       // [n_tiles] run length, then (step 2) offset of the run in part_keys - loff
+  uint32_t* loff = hist + g.n_tiles;      // [n_tiles] local offset of the run
   const uint32_t per_thread = (g.n_tiles + PART_THREADS - 1) / PART_THREADS;
 
   const uint64_t n_units = FROM_KEYS ? n_in : ep.n_bytes;
-  const uint64_t n_super = (n_units + K - 1) / K;
+  const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
+  PartPrefetch pf;
+  uint32_t r_next = 0, r_step = 0;   // (start of the next super-chunk to prefetch) % read_stride, and its increment
+  if (!FROM_KEYS && ep.read_stride != 0) {
+    r_next = (uint32_t)(((uint64_t)blockIdx.x * PART_K) % ep.read_stride);
+    r_step = (uint32_t)(((uint64_t)gridDim.x * PART_K) % ep.read_stride);
+  }
+  auto advance_r = [&]() {
+    r_next += r_step;
+    if (r_next >= ep.read_stride) r_next -= ep.read_stride;
+  };
+  if (!FROM_KEYS && blockIdx.x < n_super) {
+    part_prefetch(pf, ep, (uint64_t)blockIdx.x * PART_K, r_next);
+    advance_r();
+    part_stage_store(sm, pf);
+  }
+  if (threadIdx.x == 0) any_overflow = 0;
   for (uint64_t sc = blockIdx.x; sc < n_super; sc += gridDim.x) {
-    const uint64_t s0 = sc * K;
-    for (uint32_t i = threadIdx.x; i < g.n_tiles; i += blockDim.x) hist[i] = 0;
-    if (!FROM_KEYS) stage_super(sm, ep, s0);
+    const uint64_t s0 = sc * PART_K;
+    for (uint32_t i = threadIdx.x; i < g.n_tiles; i += PART_THREADS) hist[i] = 0;
+    const bool more = sc + gridDim.x < n_super;
+    if (!FROM_KEYS && more) {
+      part_prefetch(pf, ep, (sc + gridDim.x) * PART_K, r_next);
+      advance_r();
+    }
     __syncthreads();
-    // ---- 1. keys -> ukeys, histogram of bucket ids
+    // ---- 1. keys -> ukeys, rank inside the tile's run
+    uint32_t meta[PART_R];
     uint32_t foreign = 0;
-    auto take = [&](int w, uint64_t key) {
-      if (key != RG_EMPTY) {
-        const uint32_t tile = rg_tile_of_key(key, g.n_tiles_global) - g.tile_first;
-        if (tile >= g.n_tiles) {
-          ++foreign;
-          key = RG_EMPTY;
-        } else {
-          atomicAdd(&hist[tile], 1u);
-        }
-      }
+    // branch-free: the hash is computed for every window, only the shared atomic is predicated
+    auto take = [&](int w, uint64_t key, bool ok) {
+      const uint32_t tile = rg_tile_of_key(key, g.n_tiles_global) - g.tile_first;
+      const bool mine = !SHARDED || tile < g.n_tiles;
+      if (SHARDED) foreign += (ok && !mine) ? 1u : 0u;
+      uint32_t m = 0xFFFFFFFFu;
+      if (ok && mine) m = (tile << 16) | atomicAdd(&hist[tile], 1u);
+      meta[w] = m;
       ukeys[w * PART_THREADS + threadIdx.x] = key;
     };
     if (FROM_KEYS) {
+      uint64_t kk[PART_R];
 #pragma unroll
-      for (int w = 0; w < R; ++w) {
+      for (int w = 0; w < PART_R; ++w) {
         const uint64_t i = s0 + (uint64_t)w * PART_THREADS + threadIdx.x;
-        take(w, i < n_in ? __ldg(in_keys + i) : RG_EMPTY);
+        kk[w] = i < n_in ? __ldg(in_keys + i) : RG_EMPTY;
       }
+#pragma unroll
+      for (int w = 0; w < PART_R; ++w) take(w, kk[w], kk[w] != RG_EMPTY);
     } else {
-      roll_windows(sm, threadIdx.x, ep.k, ep.canonical, take);
+      part_windows(sm, threadIdx.x, ep.k, ep.canonical, take);
     }
     if (foreign) atomicAdd((unsigned long long*)&g.status[1], (unsigned long long)foreign);
     __syncthreads();
-    // ---- 2. local offsets (exclusive scan of the counts) + global run reservation (padded to 4 keys)
-    {
-      const uint32_t t0 = threadIdx.x * per_thread;
-      uint32_t sum = 0;
-      for (uint32_t j = 0; j < per_thread; ++j)
-        if (t0 + j < g.n_tiles) sum += hist[t0 + j];
-      uint32_t run = block_exclusive_scan(sum, warp_sums, &scan_total);
-      for (uint32_t j = 0; j < per_thread; ++j) {
-        const uint32_t t = t0 + j;
-        if (t < g.n_tiles) {
-          const uint32_t cnt = hist[t];
-          loff[t] = run;
-          run += cnt;
-          uint32_t gb = 0;
-          if (cnt) {
-            const uint32_t padded = (cnt + 3u) & ~3u;
-            gb = atomicAdd(g.cursor + t, padded);
-            uint64_t* dst = g.part_keys + (uint64_t)t * g.bucket_cap;
-            if (gb + padded <= g.bucket_cap) {
-              for (uint32_t q = cnt; q < padded; ++q) dst[gb + q] = RG_EMPTY;      // pad slots of the run
-            } else {
-              // bucket overflow (heavy hitters): this run goes to the spill list (step 4); what it
-              // reserved below the capacity is neutralised with RG_EMPTY
-              for (uint32_t q = gb; q < g.bucket_cap; ++q) dst[q] = RG_EMPTY;
-              gb = 0xFFFFFFFFu;
-            }
+    // ---- 2. local offsets (exclusive scan of the run lengths) + global run reservation (padded to 4 keys)
+    const uint32_t t0 = threadIdx.x * per_thread;
+    uint32_t sum = 0;
+    for (uint32_t j = 0; j < per_thread; ++j)
+      if (t0 + j < g.n_tiles) sum += hist[t0 + j];
+    uint32_t run = block_exclusive_scan(sum, warp_sums, &scan_total);
+    for (uint32_t j = 0; j < per_thread; ++j) {
+      const uint32_t t = t0 + j;
+      if (t < g.n_tiles) {
+        const uint32_t cnt = hist[t];
+        loff[t] = run;
+        uint32_t gd = 0;
+        if (cnt) {
+          const uint32_t padded = (cnt + 3u) & ~3u;
+          const uint32_t gb = atomicAdd(g.cursor + t, padded);
+          uint64_t* dst = g.part_keys + (uint64_t)t * g.bucket_cap;
+          if (gb + padded <= g.bucket_cap) {
+            for (uint32_t q = cnt; q < padded; ++q) dst[gb + q] = RG_EMPTY;      // pad slots of the run
+            gd = t * g.bucket_cap + gb - run;                                    // sorted index -> part_keys index
+          } else {
+            // bucket overflow (heavy hitters): this run goes to the spill list (step 4); what it
+            // reserved below the capacity is neutralised with RG_EMPTY
+            for (uint32_t q = gb; q < g.bucket_cap; ++q) dst[q] = RG_EMPTY;
+            loff[t] = run | 0x80000000u;
+            any_overflow = 1;
           }
-          gbase[t] = gb;
         }
+        hist[t] = gd;
+        run += cnt;
       }
     }
+    // the next super-chunk's bases are in registers by now; the stage buffers are free since step 1 ended
+    if (!FROM_KEYS && more) part_stage_store(sm, pf);
     __syncthreads();
-    // ---- 3. bucket-order placement of the key indices (hist counts down to the rank)
+    // ---- 3. (tile, key index) entries in tile order
+    const bool ovf = any_overflow != 0;
 #pragma unroll
-    for (int w = 0; w < R; ++w) {
-      const uint32_t q = w * PART_THREADS + threadIdx.x;
-      const uint64_t key = ukeys[q];
-      if (key == RG_EMPTY) continue;
-      const uint32_t tile = rg_tile_of_key(key, g.n_tiles_global) - g.tile_first;
-      const uint32_t r = atomicSub(&hist[tile], 1u) - 1u;      // cnt-1 .. 0
-      spos[loff[tile] + r] = (uint16_t)q;
+    for (int w = 0; w < PART_R; ++w) {
+      const uint32_t m = meta[w];
+      if (m == 0xFFFFFFFFu) continue;
+      const uint32_t tile = m >> 16;
+      const uint32_t pos = (loff[tile] & 0x7FFFFFFFu) + (m & 0xFFFFu);
+      sorted[pos] = (m & 0xFFFF0000u) | (uint32_t)(w * PART_THREADS + threadIdx.x);
     }
     __syncthreads();
-    // ---- 4. copy-out in bucket order: consecutive threads write consecutive keys of a run
-    {
-      const uint32_t total = scan_total;
-      for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-        const uint64_t key = ukeys[spos[i]];
-        const uint32_t tile = rg_tile_of_key(key, g.n_tiles_global) - g.tile_first;
-        const uint32_t gb = gbase[tile];
-        if (gb != 0xFFFFFFFFu) {
-          g.part_keys[(uint64_t)tile * g.bucket_cap + gb + (i - loff[tile])] = key;
+    // ---- 4. copy-out in sorted order
+    const uint32_t total = scan_total;
+    if (!ovf) {
+#pragma unroll 4
+      for (uint32_t i = threadIdx.x; i < total; i += PART_THREADS) {
+        const uint32_t e = sorted[i];
+        g.part_keys[hist[e >> 16] + i] = ukeys[e & 0xFFFFu];
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < total; i += PART_THREADS) {
+        const uint32_t e = sorted[i];
+        const uint64_t key = ukeys[e & 0xFFFFu];
+        if (!(loff[e >> 16] & 0x80000000u)) {
+          g.part_keys[hist[e >> 16] + i] = key;
         } else {
           const uint64_t sp = atomicAdd((unsigned long long*)&g.status[0], 1ull);
           if (sp < g.spill_cap) g.spill[sp] = key;
         }
       }
+      __syncthreads();
+      if (threadIdx.x == 0) any_overflow = 0;
     }
     __syncthreads();
   }
@@ -211,37 +371,30 @@ partition_scatter_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys,
   }
 }
 
-// keys per thread per super-chunk (R) that fits shared memory for this tile count; 0 = scatter fallback
-static int part_r_for(uint32_t n_tiles) {
-  if (n_tiles > PART_MAX_TILES) return 0;
-  if (part_dynamic_smem(20, n_tiles) + part_static_smem<20>() <= PART_SMEM_LIMIT) return 20;
-  if (part_dynamic_smem(16, n_tiles) + part_static_smem<16>() <= PART_SMEM_LIMIT) return 16;
-  if (part_dynamic_smem(12, n_tiles) + part_static_smem<12>() <= PART_SMEM_LIMIT) return 12;
-  if (part_dynamic_smem(8, n_tiles) + part_static_smem<8>() <= PART_SMEM_LIMIT) return 8;
-  return 0;
+// does the sorted kernel's per-tile state fit shared memory for this tile count? (else: scatter fallback)
+static bool part_sorted_fits(uint32_t n_tiles) {
+  return n_tiles < 65536 && part_dynamic_smem(n_tiles) + part_static_smem() <= PART_SMEM_LIMIT;
 }
 
 // upper bound on the pad keys one bucket can receive in a push of n_units windows/keys:
 // up to 3 per (super-chunk, bucket) run
 uint64_t rg_partition_pad_keys(uint32_t n_tiles, uint64_t n_units) {
-  const int r = part_r_for(n_tiles);
-  if (r == 0) return 0;
-  const uint64_t K = (uint64_t)r * PART_THREADS;
-  return 3 * ((n_units + K - 1) / K);
+  if (!part_sorted_fits(n_tiles)) return 0;
+  return 3 * ((n_units + PART_K - 1) / PART_K);
 }
 
-template <bool FROM_KEYS, int R>
+template <bool FROM_KEYS>
 static int launch_sorted(rg_ctx* ctx, const char* name, const ExtractParams& ep, const uint64_t* keys, uint64_t n_keys,
                          const PartGeom& g, uint64_t n_units) {
-  const size_t smem = part_dynamic_smem(R, g.n_tiles);
-  RG_CUDA_OK(cudaFuncSetAttribute(partition_sorted_kernel<FROM_KEYS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-  const uint64_t K = (uint64_t)R * PART_THREADS;
-  const uint64_t n_super = (n_units + K - 1) / K;
+  const size_t smem = part_dynamic_smem(g.n_tiles);
+  const bool sharded = g.n_tiles_global != g.n_tiles;
+  auto kern = sharded ? partition_sorted_kernel<FROM_KEYS, true> : partition_sorted_kernel<FROM_KEYS, false>;
+  RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
   unsigned grid = rg_grid(ctx, 1);
   if (n_super < grid) grid = (unsigned)n_super;
   rg_launch_scope _ls(ctx, name);
-  partition_sorted_kernel<FROM_KEYS, R><<<grid, PART_THREADS, smem, ctx->stream>>>(ep, keys, n_keys, g);
+  kern<<<grid, PART_THREADS, smem, ctx->stream>>>(ep, keys, n_keys, g);
   return 0;
 }
 
@@ -262,15 +415,11 @@ static int launch_partition(rg_table* t, const ExtractParams& ep, const uint64_t
   if (n_units == 0) return 0;
   const char* name = FROM_KEYS ? "partition_keys_kernel" : "partition_kernel";
   int rc = 0;
-  switch (part_r_for(t->n_tiles)) {
-    case 20: rc = launch_sorted<FROM_KEYS, 20>(ctx, name, ep, keys, n_keys, g, n_units); break;
-    case 16: rc = launch_sorted<FROM_KEYS, 16>(ctx, name, ep, keys, n_keys, g, n_units); break;
-    case 12: rc = launch_sorted<FROM_KEYS, 12>(ctx, name, ep, keys, n_keys, g, n_units); break;
-    case 8: rc = launch_sorted<FROM_KEYS, 8>(ctx, name, ep, keys, n_keys, g, n_units); break;
-    default: {
-      rg_launch_scope _ls(ctx, name);
-      partition_scatter_kernel<FROM_KEYS><<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(ep, keys, n_keys, g);
-    }
+  if (part_sorted_fits(t->n_tiles) && (uint64_t)t->n_tiles * t->bucket_cap < (1ull << 32)) {
+    rc = launch_sorted<FROM_KEYS>(ctx, name, ep, keys, n_keys, g, n_units);
+  } else {
+    rg_launch_scope _ls(ctx, name);
+    partition_scatter_kernel<FROM_KEYS><<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(ep, keys, n_keys, g);
   }
   if (rc) return rc;
   RG_CUDA_OK(cudaGetLastError());
