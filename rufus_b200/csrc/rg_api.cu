@@ -40,6 +40,11 @@ rg_ctx* rg_init(int device) {
   ctx->stream = ctx->own_stream;
   RG_CUDA_OKP(cudaMallocHost(&ctx->h_scratch, 256 * sizeof(uint64_t)));
   RG_CUDA_OKP(cudaMalloc(&ctx->d_scratch, 256 * sizeof(uint64_t)));
+  RG_CUDA_OKP(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    RG_CUDA_OKP(cudaEventCreateWithFlags(&ctx->slot_copied[i], cudaEventDisableTiming));
+    RG_CUDA_OKP(cudaEventCreateWithFlags(&ctx->slot_free[i], cudaEventDisableTiming));
+  }
   return ctx;
 }
 
@@ -47,8 +52,17 @@ void rg_shutdown(rg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
   cudaFreeHost(ctx->h_scratch);
   cudaFree(ctx->d_scratch);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->slot[i]);
+    cudaEventDestroy(ctx->slot_copied[i]);
+    cudaEventDestroy(ctx->slot_free[i]);
+  }
+  for (int i = 0; i < 6; ++i) cudaFree(ctx->pool[i]);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -148,6 +162,52 @@ static int read_scalars(rg_ctx* ctx, const uint64_t* d, int n, uint64_t* out) {
   RG_CUDA_OK(cudaMemcpyAsync(ctx->h_scratch, d, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < n; ++i) out[i] = ctx->h_scratch[i];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// host -> device pipeline: two staging slots. slot_acquire() makes the copy stream wait until the
+// kernels that last read the slot are done; slot_publish() makes `stream` wait for the slot's copy;
+// slot_release() marks the point on `stream` after which the slot may be overwritten.
+// ---------------------------------------------------------------------------
+static const uint64_t RG_SLOT_BYTES = 32ull << 20;
+
+static int slots_ensure(rg_ctx* ctx) {
+  if (ctx->slot_bytes) return 0;
+  for (int i = 0; i < 2; ++i) {
+    RG_CUDA_OK(cudaMalloc(&ctx->slot[i], RG_SLOT_BYTES + 256));
+    RG_CUDA_OK(cudaEventRecord(ctx->slot_free[i], ctx->stream));
+  }
+  ctx->slot_bytes = RG_SLOT_BYTES;
+  return 0;
+}
+static int slot_acquire(rg_ctx* ctx, uint32_t* which) {
+  const uint32_t i = ctx->slot_next++ & 1u;
+  RG_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->slot_free[i], 0));
+  *which = i;
+  return 0;
+}
+static int slot_publish(rg_ctx* ctx, uint32_t i) {
+  RG_CUDA_OK(cudaEventRecord(ctx->slot_copied[i], ctx->copy_stream));
+  RG_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->slot_copied[i], 0));
+  return 0;
+}
+static int slot_release(rg_ctx* ctx, uint32_t i) {
+  RG_CUDA_OK(cudaEventRecord(ctx->slot_free[i], ctx->stream));
+  return 0;
+}
+// grow-only device scratch, index 0..5
+static int pool_ensure(rg_ctx* ctx, int i, uint64_t bytes) {
+  if (ctx->pool_bytes[i] >= bytes) return 0;
+  if (ctx->pool[i]) {
+    RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->pool[i]);
+    ctx->pool[i] = nullptr;
+    ctx->pool_bytes[i] = 0;
+  }
+  const uint64_t want = (bytes + (bytes >> 2) + 4096) & ~255ull;
+  RG_CUDA_OK(cudaMalloc(&ctx->pool[i], want));
+  ctx->pool_bytes[i] = want;
   return 0;
 }
 
@@ -300,7 +360,29 @@ static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, 
     if (rc) return rc;
   }
   t->tiles_dirty = true;
-  return table_resolve_spill(t);
+  t->unchecked = true;      // status words are read back by table_finish (rg_count_end or the first reader)
+  return 0;
+}
+
+// every reader of a table goes through this: resolve what the enqueued pushes left behind
+static int table_finish(rg_table* t) {
+  if (!t->unchecked) return 0;
+  const int rc = table_resolve_spill(t);
+  if (rc == 0) t->unchecked = false;
+  return rc;
+}
+
+// enqueue partition launches for one staged piece of a host stream (tiled mode) or the fused
+// count (direct mode); the tile insert of the tiled mode is launched once per push by the caller
+static int push_piece(rg_table* t, const char* dev, uint64_t n_bytes) {
+  ExtractParams ep;
+  ep.stream = dev;
+  ep.n_bytes = n_bytes;
+  ep.brk = nullptr;
+  ep.read_stride = 0;
+  ep.k = t->k;
+  ep.canonical = t->canonical;
+  return t->mode == RG_MODE_TILED ? rg_launch_partition(t, ep) : rg_launch_count_direct(t, ep);
 }
 
 extern "C" {
@@ -356,13 +438,45 @@ int rg_count_push_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uin
   return push_dev_impl(t, dev_stream, n_bytes, read_stride, nullptr);
 }
 
+// Asynchronous for pinned host memory: the pieces are copied on the context's copy stream into two
+// staging slots while the partition kernel of the previous piece runs, so the H2D copy and the
+// kernels overlap; the caller's buffer must stay valid until rg_count_end / rg_sync. A piece
+// carries the k-1 bytes before it, so that the windows spanning a piece boundary are counted
+// (exactly once: a window is only taken where it fits entirely).
 int rg_count_push(rg_table* t, const char* host_stream, uint64_t n_bytes) {
   if (!t) return RG_ERR_ARG;
   if (n_bytes == 0) return 0;
-  int rc = ensure_stage(t, n_bytes);
+  rg_ctx* ctx = t->ctx;
+  int rc = slots_ensure(ctx);
   if (rc) return rc;
-  RG_CUDA_OK(cudaMemcpyAsync(t->stage, host_stream, n_bytes, cudaMemcpyHostToDevice, t->ctx->stream));
-  return push_dev_impl(t, reinterpret_cast<const char*>(t->stage), n_bytes, 0, nullptr);
+  if (t->mode == RG_MODE_TILED) {
+    rc = prepare_buckets(t, n_bytes);
+    if (rc) return rc;
+  }
+  const uint64_t halo = (uint64_t)t->k - 1;
+  const uint64_t piece = ctx->slot_bytes - 64;          // payload bytes per slot (halo fits in the slack)
+  for (uint64_t off = 0; off < n_bytes; off += piece) {
+    const uint64_t len = std::min(piece, n_bytes - off);
+    const uint64_t pre = off ? halo : 0;
+    uint32_t i;
+    rc = slot_acquire(ctx, &i);
+    if (rc) return rc;
+    RG_CUDA_OK(cudaMemcpyAsync(ctx->slot[i], host_stream + off - pre, len + pre, cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+    rc = slot_publish(ctx, i);
+    if (rc) return rc;
+    rc = push_piece(t, ctx->slot[i], len + pre);
+    if (rc) return rc;
+    rc = slot_release(ctx, i);
+    if (rc) return rc;
+  }
+  if (t->mode == RG_MODE_TILED) {
+    rc = rg_launch_tile_insert(t);
+    if (rc) return rc;
+  }
+  t->tiles_dirty = true;
+  t->unchecked = true;
+  return 0;
 }
 
 int rg_count_push_reads(rg_table* t, const char* host_seq, const uint64_t* host_offs, uint64_t n_reads) {
@@ -414,14 +528,14 @@ int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_key
   }
   if (rc) return rc;
   t->tiles_dirty = true;
-  return table_resolve_spill(t);
+  t->unchecked = true;
+  return 0;
 }
 
 int rg_count_end(rg_table* t) {
   if (!t) return RG_ERR_ARG;
-  int rc = table_resolve_spill(t);
-  if (rc) return rc;
-  return 0;
+  t->unchecked = true;
+  return table_finish(t);
 }
 
 int rg_table_trim(rg_table* t) {
@@ -466,7 +580,9 @@ void rg_table_free(rg_table* t) {
 
 int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occ, uint64_t* n_slots) {
   if (!t) return RG_ERR_ARG;
-  int rc = rg_launch_stats(t, t->ctx->d_scratch);
+  int rc = table_finish(t);
+  if (rc) return rc;
+  rc = rg_launch_stats(t, t->ctx->d_scratch);
   if (rc) return rc;
   uint64_t v[2];
   rc = read_scalars(t->ctx, t->ctx->d_scratch, 2, v);
@@ -509,7 +625,8 @@ int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint6
   const uint64_t nb = rg_histo_rows(low, high);
   uint64_t* d_out = nullptr;
   RG_CUDA_OK(cudaMalloc(&d_out, nb * 8));
-  int rc = rg_launch_histo(t, min_count, histo_base(low), nb, d_out);
+  int rc = table_finish(t);
+  if (rc == 0) rc = rg_launch_histo(t, min_count, histo_base(low), nb, d_out);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(out_host, d_out, nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -538,7 +655,8 @@ int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* k
   uint32_t* d_counts = nullptr;
   RG_CUDA_OK(cudaMalloc(&d_keys, (cap ? cap : 1) * 8));
   RG_CUDA_OK(cudaMalloc(&d_counts, (cap ? cap : 1) * 4));
-  int64_t rc = rg_launch_dump(t, min_count ? min_count : 1, max_count, d_keys, d_counts, cap, ctx->d_scratch);
+  int64_t rc = table_finish(t);
+  if (rc == 0) rc = rg_launch_dump(t, min_count ? min_count : 1, max_count, d_keys, d_counts, cap, ctx->d_scratch);
   uint64_t n = 0;
   if (rc == 0) rc = read_scalars(ctx, ctx->d_scratch, 1, &n);
   if (rc == 0) {
@@ -592,8 +710,9 @@ int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_co
   uint32_t* dc = nullptr;
   RG_CUDA_OK(cudaMalloc(&dk, n * 8));
   RG_CUDA_OK(cudaMalloc(&dc, n * 4));
-  int rc = RG_ERR_CUDA;
-  if (cudaMemcpyAsync(dk, keys_host, n * 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess) {
+  int rc = table_finish(t);
+  if (rc == 0) rc = RG_ERR_CUDA;
+  if (rc == RG_ERR_CUDA && cudaMemcpyAsync(dk, keys_host, n * 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess) {
     rc = rg_launch_query(t, dk, n, min_count, dc);
     if (rc == 0 && (cudaMemcpyAsync(counts_host, dc, n * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
                     cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
@@ -618,6 +737,8 @@ static int fill_others(OtherTables& ot, rg_table* const* others, const uint64_t*
       rg_set_error("subtract: tables must share k");
       return RG_ERR_ARG;
     }
+    const int frc = table_finish(others[i]);
+    if (frc) return frc;
     ot.tv[i] = rg_view(others[i]);
     uint64_t m = other_min ? other_min[i] : 1;
     ot.min_count[i] = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(m, 1), 0xFFFFFFFFull);
@@ -631,7 +752,9 @@ int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* othe
   if (!subj) return RG_ERR_ARG;
   rg_ctx* ctx = subj->ctx;
   OtherTables ot;
-  int rc = fill_others(ot, others, other_min, n_others, subj->k);
+  int rc = table_finish(subj);
+  if (rc) return rc;
+  rc = fill_others(ot, others, other_min, n_others, subj->k);
   if (rc) return rc;
   // candidates: c >= subj_min (in the subject .Jhash), c >= floor (merge_files.cc:149), min_cov <= c <= max_cov
   uint64_t lo = std::max<uint64_t>(std::max<uint64_t>(subj_min, floor), 1);
@@ -909,7 +1032,7 @@ int rg_filter_hits_dev(rg_set* s, const char* seq_dev, const char* qual_dev, con
     rg_set_error("rg_filter_hits_dev: null set or unaligned (16 B) buffers");
     return RG_ERR_ARG;
   }
-  return rg_launch_filter_hits(s, seq_dev, qual_dev, offs_dev, 0, n_reads, n_bytes, minq, skip_last, hits_dev);
+  return rg_launch_filter_hits(s, seq_dev, qual_dev, offs_dev, 0, n_reads, n_bytes, 0, true, minq, skip_last, hits_dev);
 }
 
 int rg_filter_hits_fixed_dev(rg_set* s, const char* seq_dev, const char* qual_dev, uint32_t read_len,
@@ -918,8 +1041,8 @@ int rg_filter_hits_fixed_dev(rg_set* s, const char* seq_dev, const char* qual_de
     rg_set_error("rg_filter_hits_fixed_dev: bad arguments");
     return RG_ERR_ARG;
   }
-  return rg_launch_filter_hits(s, seq_dev, qual_dev, nullptr, read_len, n_reads, (uint64_t)read_len * n_reads, minq,
-                               skip_last, hits_dev);
+  return rg_launch_filter_hits(s, seq_dev, qual_dev, nullptr, read_len, n_reads, (uint64_t)read_len * n_reads, 0, true,
+                               minq, skip_last, hits_dev);
 }
 
 int rg_filter_pairs_fixed_dev(rg_set* s, const char* s1, const char* q1, const char* s2, const char* q2,
@@ -931,35 +1054,53 @@ int rg_filter_pairs_fixed_dev(rg_set* s, const char* s1, const char* q1, const c
   return rc;
 }
 
-struct DevReads {
-  char* seq = nullptr;
-  char* qual = nullptr;
-  uint64_t* offs = nullptr;
-  int32_t* hits = nullptr;
-  uint64_t n_bytes = 0;
-  ~DevReads() {
-    cudaFree(seq);
-    cudaFree(qual);
-    cudaFree(offs);
-    cudaFree(hits);
+// Host-buffer read pull: the offsets go up once, the sequence + quality bytes are streamed through
+// the two staging slots in pieces that end on read boundaries (copy of piece i+1 overlaps the
+// filter kernel of piece i); device scratch comes from the context's grow-only pool.
+static int filter_host_mate(rg_set* s, const char* seq, const char* qual, const uint64_t* offs_host,
+                            const uint64_t* offs_dev, uint64_t n_reads, int minq, int skip_last, int32_t* hits_dev) {
+  rg_ctx* ctx = s->ctx;
+  RG_CUDA_OK(cudaMemsetAsync(hits_dev, 0, n_reads * sizeof(int32_t), ctx->stream));
+  const uint64_t half = (ctx->slot_bytes / 2) & ~255ull;     // sequence in the first half of a slot, quality in the second
+  uint64_t r0 = 0;
+  while (r0 < n_reads) {
+    // largest r1 with offs[r1] - offs[r0] <= half (at least one read; a longer read is rejected)
+    uint64_t lo = r0 + 1, hi = n_reads;
+    if (offs_host[lo] - offs_host[r0] > half) {
+      rg_set_error("filter: a read is longer than the staging slot");
+      return RG_ERR_ARG;
+    }
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi + 1) >> 1;
+      if (offs_host[mid] - offs_host[r0] <= half) lo = mid; else hi = mid - 1;
+    }
+    const uint64_t r1 = lo, b0 = offs_host[r0], len = offs_host[r1] - b0;
+    if (len) {
+      uint32_t i;
+      int rc = slot_acquire(ctx, &i);
+      if (rc) return rc;
+      RG_CUDA_OK(cudaMemcpyAsync(ctx->slot[i], seq + b0, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+      RG_CUDA_OK(cudaMemcpyAsync(ctx->slot[i] + half, qual + b0, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+      rc = slot_publish(ctx, i);
+      if (rc == 0)
+        rc = rg_launch_filter_hits(s, ctx->slot[i], ctx->slot[i] + half, offs_dev, 0, n_reads, len, b0, false, minq,
+                                   skip_last, hits_dev);
+      if (rc == 0) rc = slot_release(ctx, i);
+      if (rc) return rc;
+    }
+    r0 = r1;
   }
-};
+  return 0;
+}
 
-static int upload_reads(rg_ctx* ctx, DevReads& d, const char* seq, const char* qual, const uint64_t* offs,
-                        uint64_t n_reads) {
-  const uint64_t base = offs[0];
-  d.n_bytes = offs[n_reads] - base;
-  if (base != 0) {
+static int upload_offsets(rg_ctx* ctx, int pool_idx, const uint64_t* offs, uint64_t n_reads) {
+  if (offs[0] != 0) {
     rg_set_error("filter: offsets must start at 0");
     return RG_ERR_ARG;
   }
-  RG_CUDA_OK(cudaMalloc(&d.seq, d.n_bytes + 16));
-  RG_CUDA_OK(cudaMalloc(&d.qual, d.n_bytes + 16));
-  RG_CUDA_OK(cudaMalloc(&d.offs, (n_reads + 1) * 8));
-  RG_CUDA_OK(cudaMalloc(&d.hits, (n_reads + 1) * 4));
-  RG_CUDA_OK(cudaMemcpyAsync(d.seq, seq, d.n_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  RG_CUDA_OK(cudaMemcpyAsync(d.qual, qual, d.n_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  RG_CUDA_OK(cudaMemcpyAsync(d.offs, offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = pool_ensure(ctx, pool_idx, (n_reads + 1) * 8);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaMemcpyAsync(ctx->pool[pool_idx], offs, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
 
@@ -968,25 +1109,23 @@ int rg_filter_pairs(rg_set* s, const char* s1, const char* q1, const uint64_t* o
   if (!s) return RG_ERR_ARG;
   if (n_pairs == 0) return 0;
   rg_ctx* ctx = s->ctx;
-  DevReads a, b;
-  int rc = upload_reads(ctx, a, s1, q1, o1, n_pairs);
-  if (rc == 0) rc = upload_reads(ctx, b, s2, q2, o2, n_pairs);
-  if (rc == 0) rc = rg_launch_filter_hits(s, a.seq, a.qual, a.offs, 0, n_pairs, a.n_bytes, minq, 1, a.hits);
-  if (rc == 0) rc = rg_launch_filter_hits(s, b.seq, b.qual, b.offs, 0, n_pairs, b.n_bytes, minq, 1, b.hits);
-  uint8_t* d_keep = nullptr;
-  if (rc == 0) RG_CUDA_OK(cudaMalloc(&d_keep, n_pairs));
-  if (rc == 0) rc = rg_launch_keep(ctx, a.hits, b.hits, n_pairs, thresh, d_keep);
-  if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(keep_host, d_keep, n_pairs, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-      rg_set_error(cudaGetErrorString(e));
-      rc = RG_ERR_CUDA;
-    }
-  }
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_keep);
-  return rc;
+  int rc = slots_ensure(ctx);
+  if (rc == 0) rc = upload_offsets(ctx, 0, o1, n_pairs);
+  if (rc == 0) rc = upload_offsets(ctx, 1, o2, n_pairs);
+  if (rc == 0) rc = pool_ensure(ctx, 2, n_pairs * 4);
+  if (rc == 0) rc = pool_ensure(ctx, 3, n_pairs * 4);
+  if (rc == 0) rc = pool_ensure(ctx, 4, n_pairs);
+  if (rc) return rc;
+  int32_t* h1 = static_cast<int32_t*>(ctx->pool[2]);
+  int32_t* h2 = static_cast<int32_t*>(ctx->pool[3]);
+  uint8_t* d_keep = static_cast<uint8_t*>(ctx->pool[4]);
+  rc = filter_host_mate(s, s1, q1, o1, static_cast<const uint64_t*>(ctx->pool[0]), n_pairs, minq, 1, h1);
+  if (rc == 0) rc = filter_host_mate(s, s2, q2, o2, static_cast<const uint64_t*>(ctx->pool[1]), n_pairs, minq, 1, h2);
+  if (rc == 0) rc = rg_launch_keep(ctx, h1, h2, n_pairs, thresh, d_keep);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaMemcpyAsync(keep_host, d_keep, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 int rg_filter_single(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint64_t n_reads, int minq,
@@ -994,19 +1133,16 @@ int rg_filter_single(rg_set* s, const char* seq, const char* qual, const uint64_
   if (!s) return RG_ERR_ARG;
   if (n_reads == 0) return 0;
   rg_ctx* ctx = s->ctx;
-  DevReads a;
-  int rc = upload_reads(ctx, a, seq, qual, offs, n_reads);
-  if (rc == 0) rc = rg_launch_filter_hits(s, a.seq, a.qual, a.offs, 0, n_reads, a.n_bytes, minq, 0, a.hits);
-  if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(hits_host, a.hits, n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-      rg_set_error(cudaGetErrorString(e));
-      rc = RG_ERR_CUDA;
-    }
-  }
-  cudaStreamSynchronize(ctx->stream);
-  return rc;
+  int rc = slots_ensure(ctx);
+  if (rc == 0) rc = upload_offsets(ctx, 0, offs, n_reads);
+  if (rc == 0) rc = pool_ensure(ctx, 2, n_reads * 4);
+  if (rc) return rc;
+  int32_t* h = static_cast<int32_t*>(ctx->pool[2]);
+  rc = filter_host_mate(s, seq, qual, offs, static_cast<const uint64_t*>(ctx->pool[0]), n_reads, minq, 0, h);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaMemcpyAsync(hits_host, h, n_reads * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 }  // extern "C"

@@ -230,64 +230,63 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64) +
                      warp * TILE_RING_KEYS;
-    const uint64_t* src = part_keys + (uint64_t)tile * bucket_cap;
     const uint32_t chunk = (n + 31) >> 5;
-    const uint32_t begin = min(n, warp * chunk), end = min(n, begin + chunk);
-    uint32_t issued = begin;          // cp.async issued for keys [begin, issued)
+    const uint32_t begin = min(n, warp * chunk);
+    const uint32_t n_rel = min(n, begin + chunk) - begin;       // keys of this warp's stream
+    const uint64_t* gsrc = part_keys + (uint64_t)tile * bucket_cap + begin + lane;   // this lane's next key to stage
+    uint32_t issued = 0;              // cp.async issued for stream positions [0, issued)
     auto issue_quarter = [&]() {
-      const uint32_t i = issued + lane;
-      if (i < end) cp_async_8(ring + ((i - begin) & (TILE_RING_KEYS - 1)), src + i);
+      if (issued + lane < n_rel) cp_async_8(ring + (issued & (TILE_RING_KEYS - 32)) + lane, gsrc);
       asm volatile("cp.async.commit_group;" ::: "memory");
+      gsrc += 32;
       issued += 32;
     };
 #pragma unroll
     for (int q = 0; q < 4; ++q) issue_quarter();
     asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncwarp();
-    uint32_t head = begin;            // next unclaimed key of the warp's stream
+    uint32_t head = 0;                // next unclaimed position of the warp's stream
     uint32_t slot = 0, probes = 0;
     uint64_t key = RG_EMPTY;
     bool have = false;
     for (;;) {
       // ---- claim: lanes without a key take the next ones of the stream
       const uint32_t want = __ballot_sync(0xFFFFFFFFu, !have);
+      if (head >= n_rel && want == 0xFFFFFFFFu) break;          // warp-uniform
       const uint32_t my = head + __popc(want & lt_mask);
-      if (!have && my < end) {
-        key = ring[(my - begin) & (TILE_RING_KEYS - 1)];
-        if (key != RG_EMPTY) {        // (pad slots of the partition runs are skipped)
-          uint32_t tile_unused;
-          rg_locate(key, n_tiles_global, tile_unused, slot);
-          probes = 0;
-          have = true;
-        }
+      if (!have && my < n_rel) {
+        key = ring[my & (TILE_RING_KEYS - 1)];
+        uint32_t tile_unused;
+        rg_locate(key, n_tiles_global, tile_unused, slot);
+        probes = 0;
+        have = key != RG_EMPTY;       // (pad slots of the partition runs are skipped)
       }
-      const uint32_t old_head = head;
-      head = min(end, head + (uint32_t)__popc(want));
+      const uint32_t new_head = min(n_rel, head + (uint32_t)__popc(want));
       // ---- the reader left a quarter of the ring: refill it with the quarter 4 ahead
-      if (((head - begin) >> 5) != ((old_head - begin) >> 5)) {
+      if ((new_head ^ head) >> 5) {
         __syncwarp();                 // every lane has read its claim before the slot is overwritten
         issue_quarter();
         asm volatile("cp.async.wait_group 2;" ::: "memory");
         __syncwarp();                 // the two quarters the next claims can touch are complete for all lanes
       }
+      head = new_head;
       // ---- one probe for every lane that holds a key
       if (have) {
         unsigned long long seen = *(volatile unsigned long long*)(skeys + slot);
         if (seen == RG_EMPTY)
           seen = atomicCAS((unsigned long long*)(skeys + slot), (unsigned long long)RG_EMPTY, (unsigned long long)key);
-        if (seen == RG_EMPTY || seen == key) {
-          atomicAdd(scounts + slot, 1u);
+        const bool hit = (seen == RG_EMPTY) | (seen == key);
+        if (hit) atomicAdd(scounts + slot, 1u);
+        have = !hit;
+        slot = (slot + (hit ? 0u : 1u)) & (RG_TILE_SLOTS - 1);
+        probes += hit ? 0u : 1u;
+        if (probes == RG_TILE_SLOTS) {                 // tile full
+          const uint64_t sp = atomicAdd((unsigned long long*)&status[0], 1ull);
+          if (sp < spill_cap) spill[sp] = key;
           have = false;
-        } else {
-          slot = (slot + 1) & (RG_TILE_SLOTS - 1);
-          if (++probes == RG_TILE_SLOTS) {             // tile full
-            const uint64_t sp = atomicAdd((unsigned long long*)&status[0], 1ull);
-            if (sp < spill_cap) spill[sp] = key;
-            have = false;
-          }
+          probes = 0;
         }
       }
-      if (head >= end && !__any_sync(0xFFFFFFFFu, have)) break;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }

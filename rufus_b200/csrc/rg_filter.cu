@@ -178,8 +178,8 @@ __device__ __forceinline__ void filter_stage_store(FilterStage& sm, const Filter
 // L2-resident set. Only on a hit is the owning read located and the read-boundary rule applied.
 __global__ void __launch_bounds__(FILTER_THREADS)
 filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, const uint64_t* __restrict__ offs,
-                   uint32_t read_len, uint64_t n_reads, uint64_t n_bytes, int k, int minq, int skip_last,
-                   const uint64_t* __restrict__ table, uint32_t slots, const uint32_t* __restrict__ g_bitmap,
+                   uint32_t read_len, uint64_t n_reads, uint64_t n_bytes, uint64_t pos_base, int k, int minq,
+                   int skip_last, const uint64_t* __restrict__ table, uint32_t slots, const uint32_t* __restrict__ g_bitmap,
                    uint32_t bitmap_bits, int has_all_ones, int32_t* __restrict__ hits) {
   extern __shared__ __align__(16) uint32_t s_bitmap[];   // bitmap_bits-bit prefilter of the set
   __shared__ FilterStage sm;
@@ -238,7 +238,7 @@ filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, 
         }
       }
       if (!hit) continue;
-      const uint64_t gp = c0 + (uint64_t)t * FILTER_R + w;
+      const uint64_t gp = pos_base + c0 + (uint64_t)t * FILTER_R + w;   // absolute stream position
       uint64_t r, r1;
       if (offs != nullptr) {
         uint64_t lo = 0, hi = n_reads;   // largest r with offs[r] <= gp
@@ -261,9 +261,10 @@ filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, 
 }
 
 int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint32_t read_len,
-                          uint64_t n_reads, uint64_t n_bytes, int minq, int skip_last, int32_t* hits) {
+                          uint64_t n_reads, uint64_t n_bytes, uint64_t pos_base, bool zero_hits, int minq, int skip_last,
+                          int32_t* hits) {
   rg_ctx* ctx = s->ctx;
-  RG_CUDA_OK(cudaMemsetAsync(hits, 0, n_reads * sizeof(int32_t), ctx->stream));
+  if (zero_hits) RG_CUDA_OK(cudaMemsetAsync(hits, 0, n_reads * sizeof(int32_t), ctx->stream));
   if (n_bytes == 0 || n_reads == 0) return 0;
   const size_t smem = s->bitmap_bits / 8;
   static bool attr_set = false;
@@ -277,8 +278,9 @@ int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const ui
   if (n_chunks < grid) grid = (unsigned)n_chunks;
   {
     rg_launch_scope _ls(ctx, "filter_hits_kernel");
-    filter_hits_kernel<<<grid, FILTER_THREADS, smem, ctx->stream>>>(seq, qual, offs, read_len, n_reads, n_bytes, s->k,
-                                                                    minq, skip_last, s->table, s->slots, s->bitmap,
+    filter_hits_kernel<<<grid, FILTER_THREADS, smem, ctx->stream>>>(seq, qual, offs, read_len, n_reads, n_bytes,
+                                                                    pos_base, s->k, minq, skip_last, s->table, s->slots,
+                                                                    s->bitmap,
                                                                     s->bitmap_bits, s->has_all_ones, hits);
   }
   RG_CUDA_OK(cudaGetLastError());

@@ -15,7 +15,7 @@
 // RG_TILE_SLOTS slots, stored SoA: keys[] (u64, EMPTY = ~0) and counts[] (u32).
 // One tile = 128 KiB of keys + 64 KiB of counts = 192 KiB: exactly what one CTA
 // stages in shared memory (227 KiB/SM on B200) in the tiled insert.
-//   h      = hash32(key)                  (xor-fold + one 64-bit Fibonacci multiply, high word)
+//   h      = hash32(key)                  (lo * C1 + hi * C2 mod 2^32)
 //   p      = h * n_tiles_global           (64-bit product)
 //   tile   = p >> 32                      ("hash prefix": also the shard id of the multi-GPU partition)
 //   slot0  = low32(p) >> (32 - RG_TILE_BITS)   (the position of h inside its tile's hash range)
@@ -44,6 +44,17 @@ struct rg_ctx {
   // small pinned scratch for scalar read-backs
   uint64_t* h_scratch = nullptr;  // pinned, 64 u64
   uint64_t* d_scratch = nullptr;  // device, 64 u64
+  // host -> device pipeline of the host-buffer entry points: two staging slots filled on a copy
+  // stream while the kernels of the previous slot run on `stream`
+  cudaStream_t copy_stream = nullptr;
+  char* slot[2] = {nullptr, nullptr};
+  uint64_t slot_bytes = 0;
+  cudaEvent_t slot_copied[2] = {nullptr, nullptr};   // recorded on copy_stream after the slot's H2D
+  cudaEvent_t slot_free[2] = {nullptr, nullptr};     // recorded on stream after the last kernel that reads the slot
+  uint32_t slot_next = 0;
+  // grow-only device scratch for the read filter's host entry points (offsets, hit counters, keep mask)
+  void* pool[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t pool_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
 
 struct rg_table {
@@ -63,6 +74,7 @@ struct rg_table {
   uint64_t* spill = nullptr;    // keys that found their tile full
   uint64_t spill_cap = 0;
   bool tiles_dirty = false;     // table holds data (tiled insert must load tiles, not zero them)
+  bool unchecked = false;       // pushes were enqueued whose status words (spill / foreign) are not read back yet
   // tiled-mode staging
   uint64_t* part_keys = nullptr;     // bucketed keys
   uint64_t part_cap = 0;             // total key capacity
@@ -119,11 +131,11 @@ __host__ __device__ __forceinline__ uint64_t rg_mix64(uint64_t h) {
   return h;
 }
 
-// table hash: cheap enough for the per-k-mer inner loops (~7 integer instructions)
+// table hash: two 32-bit multiply-adds (both on the FMA pipe, nothing on the integer ALU pipe that the
+// extraction saturates). Checked against the previous xor-shift-multiply hash on real k-mer sets: same
+// tile-load variance (Poisson) and the same mean probe length (profiles/README.md).
 __host__ __device__ __forceinline__ uint32_t rg_hash32(uint64_t key) {
-  uint64_t x = key ^ (key >> 29);
-  x *= 0x9E3779B97F4A7C15ull;
-  return (uint32_t)(x >> 32);
+  return (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
 }
 
 // tile (global numbering) and home slot of a key
@@ -246,8 +258,10 @@ int rg_launch_rehash(rg_table* dst, const uint64_t* old_keys, const uint32_t* ol
 
 int rg_launch_set_build(rg_set* s, const uint64_t* d_vals, uint64_t n);
 int rg_launch_jf_to_rufus(rg_ctx* ctx, const uint64_t* d_jf, uint64_t n, int k, uint64_t* d_out2n);
+// pos_base: stream position of seq[0] (offs / read_len are absolute); zero_hits: clear hits[0..n_reads) first
 int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint32_t read_len,
-                          uint64_t n_reads, uint64_t n_bytes, int minq, int skip_last, int32_t* hits);
+                          uint64_t n_reads, uint64_t n_bytes, uint64_t pos_base, bool zero_hits, int minq, int skip_last,
+                          int32_t* hits);
 int rg_launch_keep(rg_ctx* ctx, const int32_t* h1, const int32_t* h2, uint64_t n, int thresh, uint8_t* keep);
 
 // RAII: times one kernel launch when profiling is on, and counts the launch

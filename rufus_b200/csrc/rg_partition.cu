@@ -16,10 +16,15 @@
 //      insert skips them), so every global write is a fully covered sector.
 #include "rg_extract.cuh"
 
-constexpr int PART_THREADS = 1024;
+#ifndef PART_CTAS
+#define PART_CTAS 1                                 // CTAs per SM (2 half-size CTAs measured slower: 1.31 vs 0.84 ms, profiles/README.md)
+#endif
+constexpr int PART_THREADS = 1024 / PART_CTAS;
 constexpr int PART_R = 16;                          // windows per thread: one 16-base word, so every shift below is static
 constexpr uint32_t PART_K = PART_THREADS * PART_R;  // windows (keys) counting-sorted at once
-constexpr size_t PART_SMEM_LIMIT = 232448;          // 227 KiB opt-in limit per CTA (static + dynamic)
+constexpr int PART_TILES_PER_THREAD = 3;             // the sorted kernel handles up to 3 * 1024 tiles (shared memory caps it earlier)
+// 227 KiB opt-in limit per CTA (static + dynamic); 228 KiB per SM with 1 KiB reserved per resident CTA
+constexpr size_t PART_SMEM_LIMIT = PART_CTAS == 1 ? 232448 : (233472 / PART_CTAS - 1024);
 
 // Staging of one super-chunk (PART_K window starts + 48 bases of tail) as four bit streams:
 //   fwd : 16 bases per word, BIG-endian (base i of the word at bits 31-2i..30-2i), A0 C1 G2 T3:
@@ -39,8 +44,10 @@ struct PartStage {
 };
 
 constexpr size_t part_static_smem() { return sizeof(PartStage) + 33 * sizeof(uint32_t) + 256; }
-// ukeys (8 B) + sorted (tile,index) entries (4 B) per key; count->gdelta and loff per tile
-static size_t part_dynamic_smem(uint32_t n_tiles) { return (size_t)PART_K * 12 + (size_t)n_tiles * 8; }
+// ukeys (8 B) + sorted (tile,index) entries (4 B) per key; count->gdelta and loff per tile; overflow bitmap
+static size_t part_dynamic_smem(uint32_t n_tiles) {
+  return (size_t)PART_K * 12 + (size_t)n_tiles * 8 + (size_t)((n_tiles + 31) / 32) * 4;
+}
 
 struct PartGeom {
   uint32_t n_tiles_global, tile_first, n_tiles;
@@ -78,12 +85,26 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
   return warp_sums[warp] + incl - v;
 }
 
-// 16 ASCII bytes -> big-endian forward codes, little-endian complemented codes, 16 bad flags
+// 16 ASCII bytes -> big-endian forward codes, little-endian complemented codes, 16 bad flags.
+// The per-byte fields are gathered with one multiply each (no carries: every partial product lands
+// on its own bits), which keeps this off the integer ALU pipe.
 __device__ __forceinline__ void convert16_both(const uint4 v, uint32_t& fwd_be, uint32_t& rc_le, uint32_t& bad) {
-  uint32_t le;
-  convert16_le(v, le, bad);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t le = 0;
+  bad = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t x = (w[i] >> 1) & 0x03030303u;             // A0 C1 G3 T2 per byte
+    const uint32_t c4 = x ^ ((x >> 1) & 0x01010101u);         // A0 C1 G2 T3
+    le |= ((c4 * 0x01041040u) >> 24) << (8 * i);              // char j (byte j) -> bits 2j..2j+1
+    const uint32_t u = w[i] & 0xDFDFDFDFu;                    // upper-case
+    const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
+                        __vcmpeq4(u, 0x54545454u);            // 0xFF per valid byte
+    const uint32_t nb = ~ok & 0x01010101u;                    // bit 0 of byte j set if char j is bad
+    bad |= ((nb * 0x10204080u) >> 28) << (4 * i);             // bit j = char j
+  }
   rc_le = ~le;
-  uint32_t r = __brev(le);                                    // reverses bits: 2-bit groups end up bit-swapped
+  const uint32_t r = __brev(le);                              // reverses bits: 2-bit groups end up bit-swapped
   fwd_be = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
 }
 
@@ -122,8 +143,14 @@ struct PartPrefetch {
 
 // r0 = s0 % read_stride (read_stride < 2^31, checked on the host)
 __device__ __forceinline__ void part_prefetch(PartPrefetch& pf, const ExtractParams& ep, uint64_t s0, uint32_t r0) {
-  pf.body = load16_stream(ep, s0 + (uint64_t)threadIdx.x * 16);
-  if (threadIdx.x < 3) pf.tail = load16_stream(ep, s0 + (uint64_t)(PART_THREADS + threadIdx.x) * 16);
+  if (s0 + PART_K + 64 <= ep.n_bytes) {           // CTA-uniform: no per-load bounds checks
+    const uint4* src = reinterpret_cast<const uint4*>(ep.stream + s0);
+    pf.body = __ldg(src + threadIdx.x);
+    if (threadIdx.x < 3) pf.tail = __ldg(src + PART_THREADS + threadIdx.x);
+  } else {
+    pf.body = load16_stream(ep, s0 + (uint64_t)threadIdx.x * 16);
+    if (threadIdx.x < 3) pf.tail = load16_stream(ep, s0 + (uint64_t)(PART_THREADS + threadIdx.x) * 16);
+  }
   if (threadIdx.x < PartStage::BIT_WORDS) {
     uint32_t r = 0;
     if (ep.read_stride != 0) r = (r0 + threadIdx.x * 32u) % ep.read_stride;
@@ -157,7 +184,10 @@ __device__ __forceinline__ void part_stage_store(PartStage& sm, const PartPrefet
 }
 
 // The 16 windows starting at bases 16t .. 16t+15 of the staged super-chunk: emit(w, key, ok) with
-// ok == false when window w holds no k-mer (key is then garbage). ~12 integer instructions per window.
+// ok == false when window w holds no k-mer (key is then garbage).
+// k > 16: the three forward words are shifted right by 64-2k ONCE per thread, so each window costs
+// two funnel shifts + one mask per strand (the low word needs no mask), a 64-bit compare and a
+// select: 10 integer-ALU instructions. k <= 16 takes the generic path.
 template <typename Emit>
 __device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, int canonical, Emit&& emit) {
   const int p0 = t * PART_R;
@@ -167,19 +197,39 @@ __device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, 
   if (k > 1) valid &= and_run(nobrk, k - 1);
   const uint32_t W0 = sm.fwd[t], W1 = sm.fwd[t + 1], W2 = sm.fwd[t + 2];
   const uint32_t V0 = sm.rcw[t], V1 = sm.rcw[t + 1], V2 = sm.rcw[t + 2];
-  const uint64_t mask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-  const int down = 64 - 2 * k;
   const uint32_t valid16 = (uint32_t)valid;
+  if (k > 16) {
+    const int down = 64 - 2 * k;                            // 0..30
+    const uint32_t himask = (k == 32) ? 0xFFFFFFFFu : ((1u << (2 * k - 32)) - 1u);
+    // X = (W0:W1:W2:0) >> down, as four words
+    const uint32_t X0 = W0 >> down, X1 = __funnelshift_r(W1, W0, down), X2 = __funnelshift_r(W2, W1, down),
+                   X3 = __funnelshift_r(0u, W2, down);
 #pragma unroll
-  for (int w = 0; w < PART_R; ++w) {
-    const uint32_t fhi = w ? __funnelshift_l(W1, W0, 2 * w) : W0;
-    const uint32_t flo = w ? __funnelshift_l(W2, W1, 2 * w) : W1;
-    const uint32_t rlo = w ? __funnelshift_r(V0, V1, 2 * w) : V0;
-    const uint32_t rhi = w ? __funnelshift_r(V1, V2, 2 * w) : V1;
-    const uint64_t fwd = (((uint64_t)fhi << 32) | flo) >> down;
-    const uint64_t rc = (((uint64_t)rhi << 32) | rlo) & mask;
-    const uint64_t key = (!canonical || fwd < rc) ? fwd : rc;
-    emit(w, key, (valid16 & (1u << w)) != 0);
+    for (int w = 0; w < PART_R; ++w) {
+      const uint32_t fhi = (w ? __funnelshift_l(X1, X0, 2 * w) : X0) & himask;
+      const uint32_t flo = w ? __funnelshift_l(X2, X1, 2 * w) : X1;
+      const uint32_t rlo = w ? __funnelshift_r(V0, V1, 2 * w) : V0;
+      const uint32_t rhi = (w ? __funnelshift_r(V1, V2, 2 * w) : V1) & himask;
+      (void)X3;
+      const uint64_t fwd = ((uint64_t)fhi << 32) | flo;
+      const uint64_t rc = ((uint64_t)rhi << 32) | rlo;
+      const uint64_t key = (!canonical || fwd < rc) ? fwd : rc;
+      emit(w, key, (valid16 & (1u << w)) != 0);
+    }
+  } else {
+    const uint64_t mask = (1ull << (2 * k)) - 1;
+    const int down = 64 - 2 * k;
+#pragma unroll
+    for (int w = 0; w < PART_R; ++w) {
+      const uint32_t fhi = w ? __funnelshift_l(W1, W0, 2 * w) : W0;
+      const uint32_t flo = w ? __funnelshift_l(W2, W1, 2 * w) : W1;
+      const uint32_t rlo = w ? __funnelshift_r(V0, V1, 2 * w) : V0;
+      const uint32_t rhi = w ? __funnelshift_r(V1, V2, 2 * w) : V1;
+      const uint64_t fwd = (((uint64_t)fhi << 32) | flo) >> down;
+      const uint64_t rc = (((uint64_t)rhi << 32) | rlo) & mask;
+      const uint64_t key = (!canonical || fwd < rc) ? fwd : rc;
+      emit(w, key, (valid16 & (1u << w)) != 0);
+    }
   }
 }
 
@@ -196,7 +246,7 @@ __device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, 
 // The ASCII of the next super-chunk is prefetched into registers during steps 1-2.
 // SHARDED: the table holds one hash-prefix shard (multi-GPU), so keys of other shards are counted as foreign.
 template <bool FROM_KEYS, bool SHARDED>
-__global__ void __launch_bounds__(PART_THREADS, 1)
+__global__ void __launch_bounds__(PART_THREADS, PART_CTAS)
 partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, uint64_t n_in, PartGeom g) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ PartStage sm;
@@ -207,7 +257,9 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
   uint32_t* sorted = reinterpret_cast<uint32_t*>(dyn + (size_t)PART_K * 8);  // [PART_K] (tile << 16) | key index
   uint32_t* hist = sorted + PART_K;       // [n_tiles] run length, then (step 2) offset of the run in part_keys - loff
   uint32_t* loff = hist + g.n_tiles;      // [n_tiles] local offset of the run
+  uint32_t* ovf_bits = loff + g.n_tiles;  // [(n_tiles+31)/32] tiles whose bucket overflowed in this super-chunk
   const uint32_t per_thread = (g.n_tiles + PART_THREADS - 1) / PART_THREADS;
+  const uint32_t ovf_words = (g.n_tiles + 31) >> 5;
 
   const uint64_t n_units = FROM_KEYS ? n_in : ep.n_bytes;
   const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
@@ -227,6 +279,7 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     part_stage_store(sm, pf);
   }
   if (threadIdx.x == 0) any_overflow = 0;
+  for (uint32_t i = threadIdx.x; i < ovf_words; i += PART_THREADS) ovf_bits[i] = 0;
   for (uint64_t sc = blockIdx.x; sc < n_super; sc += gridDim.x) {
     const uint64_t s0 = sc * PART_K;
     for (uint32_t i = threadIdx.x; i < g.n_tiles; i += PART_THREADS) hist[i] = 0;
@@ -237,15 +290,19 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     }
     __syncthreads();
     // ---- 1. keys -> ukeys, rank inside the tile's run
-    uint32_t meta[PART_R];
+    uint32_t meta[PART_R];           // (tile << 16) | rank, or ~0 for a window without a k-mer
     uint32_t foreign = 0;
     // branch-free: the hash is computed for every window, only the shared atomic is predicated
     auto take = [&](int w, uint64_t key, bool ok) {
-      const uint32_t tile = rg_tile_of_key(key, g.n_tiles_global) - g.tile_first;
-      const bool mine = !SHARDED || tile < g.n_tiles;
-      if (SHARDED) foreign += (ok && !mine) ? 1u : 0u;
+      uint32_t tile = rg_tile_of_key(key, g.n_tiles_global);
+      if (SHARDED) {
+        tile -= g.tile_first;
+        const bool mine = tile < g.n_tiles;
+        foreign += (ok && !mine) ? 1u : 0u;
+        ok = ok && mine;
+      }
       uint32_t m = 0xFFFFFFFFu;
-      if (ok && mine) m = (tile << 16) | atomicAdd(&hist[tile], 1u);
+      if (ok) m = tile * 65536u + atomicAdd(&hist[tile], 1u);
       meta[w] = m;
       ukeys[w * PART_THREADS + threadIdx.x] = key;
     };
@@ -261,53 +318,65 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     } else {
       part_windows(sm, threadIdx.x, ep.k, ep.canonical, take);
     }
-    if (foreign) atomicAdd((unsigned long long*)&g.status[1], (unsigned long long)foreign);
+    if (SHARDED && foreign) atomicAdd((unsigned long long*)&g.status[1], (unsigned long long)foreign);
     __syncthreads();
-    // ---- 2. local offsets (exclusive scan of the run lengths) + global run reservation (padded to 4 keys)
+    // ---- 2. local offsets (exclusive scan of the run lengths); the global run reservations (one
+    // atomicAdd per non-empty tile, run padded to 4 keys) are only ISSUED here: their results are
+    // consumed after step 3, which hides the round trip to L2
     const uint32_t t0 = threadIdx.x * per_thread;
+    uint32_t cnt[PART_TILES_PER_THREAD], gb[PART_TILES_PER_THREAD];
     uint32_t sum = 0;
-    for (uint32_t j = 0; j < per_thread; ++j)
-      if (t0 + j < g.n_tiles) sum += hist[t0 + j];
+#pragma unroll
+    for (int j = 0; j < PART_TILES_PER_THREAD; ++j) {
+      cnt[j] = ((uint32_t)j < per_thread && t0 + j < g.n_tiles) ? hist[t0 + j] : 0u;
+      sum += cnt[j];
+    }
     uint32_t run = block_exclusive_scan(sum, warp_sums, &scan_total);
-    for (uint32_t j = 0; j < per_thread; ++j) {
-      const uint32_t t = t0 + j;
-      if (t < g.n_tiles) {
-        const uint32_t cnt = hist[t];
-        loff[t] = run;
-        uint32_t gd = 0;
-        if (cnt) {
-          const uint32_t padded = (cnt + 3u) & ~3u;
-          const uint32_t gb = atomicAdd(g.cursor + t, padded);
-          uint64_t* dst = g.part_keys + (uint64_t)t * g.bucket_cap;
-          if (gb + padded <= g.bucket_cap) {
-            for (uint32_t q = cnt; q < padded; ++q) dst[gb + q] = RG_EMPTY;      // pad slots of the run
-            gd = t * g.bucket_cap + gb - run;                                    // sorted index -> part_keys index
-          } else {
-            // bucket overflow (heavy hitters): this run goes to the spill list (step 4); what it
-            // reserved below the capacity is neutralised with RG_EMPTY
-            for (uint32_t q = gb; q < g.bucket_cap; ++q) dst[q] = RG_EMPTY;
-            loff[t] = run | 0x80000000u;
-            any_overflow = 1;
-          }
-        }
-        hist[t] = gd;
-        run += cnt;
+    const uint32_t run0 = run;
+#pragma unroll
+    for (int j = 0; j < PART_TILES_PER_THREAD; ++j) {
+      gb[j] = 0;
+      if (cnt[j]) {
+        loff[t0 + j] = run;
+        gb[j] = atomicAdd(g.cursor + t0 + j, (cnt[j] + 3u) & ~3u);
+        run += cnt[j];
       }
     }
     // the next super-chunk's bases are in registers by now; the stage buffers are free since step 1 ended
     if (!FROM_KEYS && more) part_stage_store(sm, pf);
     __syncthreads();
     // ---- 3. (tile, key index) entries in tile order
-    const bool ovf = any_overflow != 0;
 #pragma unroll
     for (int w = 0; w < PART_R; ++w) {
       const uint32_t m = meta[w];
-      if (m == 0xFFFFFFFFu) continue;
       const uint32_t tile = m >> 16;
-      const uint32_t pos = (loff[tile] & 0x7FFFFFFFu) + (m & 0xFFFFu);
-      sorted[pos] = (m & 0xFFFF0000u) | (uint32_t)(w * PART_THREADS + threadIdx.x);
+      if (m != 0xFFFFFFFFu) sorted[loff[tile] + (m & 0xFFFFu)] = tile * 65536u + (w * PART_THREADS + threadIdx.x);
+    }
+    // ---- 3b. the reservations have landed: pad slots, sorted index -> part_keys index (into hist[])
+    run = run0;
+#pragma unroll
+    for (int j = 0; j < PART_TILES_PER_THREAD; ++j) {
+      if (cnt[j]) {
+        const uint32_t t = t0 + j;
+        const uint32_t padded = (cnt[j] + 3u) & ~3u;
+        const uint32_t at = t * g.bucket_cap + gb[j];                // index of the run in part_keys
+        if (gb[j] + padded <= g.bucket_cap) {
+          if (cnt[j] + 0 < padded) g.part_keys[at + padded - 1] = RG_EMPTY;   // at most 3 pad slots
+          if (cnt[j] + 1 < padded) g.part_keys[at + padded - 2] = RG_EMPTY;
+          if (cnt[j] + 2 < padded) g.part_keys[at + padded - 3] = RG_EMPTY;
+          hist[t] = at - run;
+        } else {
+          // bucket overflow (heavy hitters): this run goes to the spill list (step 4); what it
+          // reserved below the capacity is neutralised with RG_EMPTY
+          for (uint32_t q = gb[j]; q < g.bucket_cap; ++q) g.part_keys[(uint64_t)t * g.bucket_cap + q] = RG_EMPTY;
+          atomicOr(&ovf_bits[t >> 5], 1u << (t & 31));
+          any_overflow = 1;
+        }
+        run += cnt[j];
+      }
     }
     __syncthreads();
+    const bool ovf = any_overflow != 0;
     // ---- 4. copy-out in sorted order
     const uint32_t total = scan_total;
     if (!ovf) {
@@ -319,9 +388,10 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     } else {
       for (uint32_t i = threadIdx.x; i < total; i += PART_THREADS) {
         const uint32_t e = sorted[i];
+        const uint32_t tile = e >> 16;
         const uint64_t key = ukeys[e & 0xFFFFu];
-        if (!(loff[e >> 16] & 0x80000000u)) {
-          g.part_keys[hist[e >> 16] + i] = key;
+        if (!((ovf_bits[tile >> 5] >> (tile & 31)) & 1u)) {
+          g.part_keys[hist[tile] + i] = key;
         } else {
           const uint64_t sp = atomicAdd((unsigned long long*)&g.status[0], 1ull);
           if (sp < g.spill_cap) g.spill[sp] = key;
@@ -329,6 +399,7 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
       }
       __syncthreads();
       if (threadIdx.x == 0) any_overflow = 0;
+      for (uint32_t i = threadIdx.x; i < ovf_words; i += PART_THREADS) ovf_bits[i] = 0;
     }
     __syncthreads();
   }
@@ -373,7 +444,7 @@ partition_scatter_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys,
 
 // does the sorted kernel's per-tile state fit shared memory for this tile count? (else: scatter fallback)
 static bool part_sorted_fits(uint32_t n_tiles) {
-  return n_tiles < 65536 && part_dynamic_smem(n_tiles) + part_static_smem() <= PART_SMEM_LIMIT;
+  return n_tiles <= PART_TILES_PER_THREAD * PART_THREADS && part_dynamic_smem(n_tiles) + part_static_smem() <= PART_SMEM_LIMIT;
 }
 
 // upper bound on the pad keys one bucket can receive in a push of n_units windows/keys:
@@ -390,8 +461,9 @@ static int launch_sorted(rg_ctx* ctx, const char* name, const ExtractParams& ep,
   const bool sharded = g.n_tiles_global != g.n_tiles;
   auto kern = sharded ? partition_sorted_kernel<FROM_KEYS, true> : partition_sorted_kernel<FROM_KEYS, false>;
   RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
-  unsigned grid = rg_grid(ctx, 1);
+  unsigned grid = rg_grid(ctx, PART_CTAS);
   if (n_super < grid) grid = (unsigned)n_super;
   rg_launch_scope _ls(ctx, name);
   kern<<<grid, PART_THREADS, smem, ctx->stream>>>(ep, keys, n_keys, g);

@@ -114,14 +114,15 @@ class DevicePipeline:
             mine = exchange_keys(self.part_keys, sizes)
             t.push_keys_dev(mine, mine.numel())
             self.last.setdefault("sent_keys", []).append(sum(sizes) - sizes[self.rank])
-        t.end(trim=False)
 
     def step(self) -> dict:
         torch = self.torch
         L = api.lib()
         self.last = {}
         for i in range(len(self.tables)):
-            self.count_sample(i)
+            self.count_sample(i)          # enqueued only: no host synchronisation between the samples
+        for t in self.tables:
+            t.end(trim=False)             # one read-back of the status words per table (spill / foreign keys)
         # histogram of the subject (jellyfish histo -f); all-reduced over shards
         h = self.tables[0].histo(min_count=self.lower[0])
         if self.world > 1:
@@ -182,7 +183,8 @@ def host_step(ctx: api.Context, k: int, host_streams, subject_pairs, read_len: i
     t0 = time.perf_counter()
     for t, s in zip(tables, host_streams):
         t.clear()
-        t.push_stream(s)
+        t.push_stream(s)                  # asynchronous: H2D pieces overlap the kernels of the previous pieces
+    for t in tables:
         t.end(trim=False)
     t0 = lap("count_ms", t0)
     h = tables[0].histo(min_count=lower[0])
