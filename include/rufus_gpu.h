@@ -68,6 +68,10 @@ int rg_profile_names(rg_ctx* ctx, char* buf, uint64_t cap);
 /* plain device-memory helpers for callers that keep inputs resident in HBM */
 void* rg_dev_alloc(rg_ctx* ctx, uint64_t bytes);
 void rg_dev_free(rg_ctx* ctx, void* dptr);
+/* pinned host memory: host buffers allocated here make the H2D copies of the host entry points
+ * asynchronous (they overlap the kernels); any other host memory works too, only slower */
+void* rg_host_alloc(uint64_t bytes);
+void rg_host_free(void* p);
 int rg_h2d(rg_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
 int rg_d2h(rg_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
 
@@ -85,6 +89,9 @@ int rg_count_push_reads(rg_table* t, const char* host_seq, const uint64_t* host_
 /* DEVICE-resident stream (16-byte aligned). read_stride > 0: a read starts every
  * read_stride bytes (fixed-length reads without separators); 0: separators only. */
 int rg_count_push_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride);
+/* Make room for up to extra_distinct more distinct keys (grows and re-hashes the table if the
+ * load would pass ~60 %): for streaming callers that learn the input size as they read it. */
+int rg_table_reserve(rg_table* t, uint64_t extra_distinct);
 /* Finish counting: flush staged keys, resolve spills. */
 int rg_count_end(rg_table* t);
 void rg_table_free(rg_table* t);
@@ -130,6 +137,36 @@ rg_table* rg_table_from_pairs(rg_ctx* ctx, int k, int canonical, const uint64_t*
 /* `jellyfish query` (query_main.cc:44-51; binary_dumper.hpp:156-197): count of each jf key,
  * 0 when absent or below min_count. Host in/out. */
 int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_count, uint32_t* counts_host);
+
+/* ---- K5 on disk: the `.Jhash` file -------------------
+ * Byte-compatible with Jellyfish 2.2.5 binary/sorted files: header of
+ * generic_file_header.hpp:96-119 + file_header.hpp:34-41, records of
+ * binary_dumper.hpp:44-48 in the (pos, key) order of sorted_dumper.hpp:80-111, hash
+ * matrix regenerated exactly as large_hash_array.hpp:948 does (unseeded glibc random()).
+ * Files written here load in real `jellyfish dump/histo/query/merge`, and real files
+ * (e.g. `-e` excludes) load here. */
+typedef struct rg_jf_info {
+  int k, canonical;
+  uint64_t size;            /* header "size" (power of two) */
+  uint32_t counter_len;     /* bytes per count */
+  uint64_t n_records;
+  uint32_t matrix_r;
+  uint64_t max_reprobe_offset;
+  uint64_t columns[64];     /* matrix1.columns, 2k used */
+} rg_jf_info;
+/* matrix of a `jellyfish count -s size -m k` table: 2k columns, r = ceil(log2(size)) rows */
+int rg_jf_matrix(uint64_t size, int k, uint64_t* columns_out, uint32_t* r_out, uint64_t* size_out);
+/* position of a key in that table (matrix * key & (size-1)); ~0 on bad arguments */
+uint64_t rg_jf_pos(uint64_t jf_key, uint64_t size, int k);
+/* reorder HOST (key,count) pairs into the file order of such a table, on the device. Returns n. */
+int64_t rg_jf_sort(rg_ctx* ctx, uint64_t* keys_host, uint32_t* counts_host, uint64_t n, uint64_t size, int k);
+/* `jellyfish count -o path -L min_count [-U max_count] -s size --out-counter-len counter_len`:
+ * write the table as a .Jhash; cmdline goes into the header. Returns records written. 0 = default
+ * for max_count (none) and counter_len (4). */
+int64_t rg_table_write_jhash(rg_table* t, const char* path, uint64_t min_count, uint64_t max_count, uint64_t size,
+                             uint32_t counter_len, const char* const* cmdline, int n_cmdline);
+/* load a .Jhash (ours or real Jellyfish's) into a device table; info (optional) gets the header values */
+rg_table* rg_table_read_jhash(rg_ctx* ctx, const char* path, rg_jf_info* info);
 
 /* ---- S1: subtraction ----------------------------------------------------
  * modified `jellyfish merge` (src/modifiedJellyfish/jellyfish/merge_files.cc:86-154):

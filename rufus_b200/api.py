@@ -53,6 +53,8 @@ def lib():
         "rg_launch_count": (u64, [vp]),
         "rg_dev_alloc": (vp, [vp, u64]),
         "rg_dev_free": (None, [vp, vp]),
+        "rg_host_alloc": (vp, [u64]),
+        "rg_host_free": (None, [vp]),
         "rg_h2d": (i32, [vp, vp, vp, u64]),
         "rg_d2h": (i32, [vp, vp, vp, u64]),
         "rg_count_begin": (vp, [vp, i32, i32, u64, i32]),
@@ -60,6 +62,7 @@ def lib():
         "rg_count_push_reads": (i32, [vp, vp, vp, u64]),
         "rg_count_push_dev": (i32, [vp, vp, u64, u32]),
         "rg_count_end": (i32, [vp]),
+        "rg_table_reserve": (i32, [vp, u64]),
         "rg_table_free": (None, [vp]),
         "rg_table_clear": (i32, [vp]),
         "rg_table_trim": (i32, [vp]),
@@ -79,6 +82,11 @@ def lib():
         "rg_dump": (i64, [vp, u64, u64, vp, vp, u64, C.POINTER(u64)]),
         "rg_table_from_pairs": (vp, [vp, i32, i32, vp, vp, u64]),
         "rg_query": (i32, [vp, vp, u64, u64, vp]),
+        "rg_jf_matrix": (i32, [u64, i32, vp, C.POINTER(u32), C.POINTER(u64)]),
+        "rg_jf_pos": (u64, [u64, u64, i32]),
+        "rg_jf_sort": (i64, [vp, vp, vp, u64, u64, i32]),
+        "rg_table_write_jhash": (i64, [vp, C.c_char_p, u64, u64, u64, u32, vp, i32]),
+        "rg_table_read_jhash": (vp, [vp, C.c_char_p, vp]),
         "rg_merge_unique": (i64, [vp, vp, i32, u64, vp, vp, vp, u64, C.POINTER(u64)]),
         "rg_subtract": (i64, [vp, u64, vp, vp, i32, u64, i64, i64, vp, vp, u64, C.POINTER(u64)]),
         "rg_subtract_dev": (i64, [vp, u64, vp, vp, i32, u64, i64, i64, vp, vp, u64]),
@@ -104,7 +112,19 @@ def lib():
     return L
 
 
-ABI_SYMBOLS = None  # filled lazily by abi_symbols()
+class JfInfo(C.Structure):
+    """rg_jf_info: header values of a .Jhash file"""
+    _fields_ = [("k", C.c_int), ("canonical", C.c_int), ("size", C.c_uint64), ("counter_len", C.c_uint32),
+                ("n_records", C.c_uint64), ("matrix_r", C.c_uint32), ("max_reprobe_offset", C.c_uint64),
+                ("columns", C.c_uint64 * 64)]
+
+
+def jf_matrix(size: int, k: int):
+    """(columns[2k], r, size rounded to a power of two) of a `jellyfish count -s size -m k` table"""
+    cols = (C.c_uint64 * 64)()
+    r, sz = C.c_uint32(), C.c_uint64()
+    _check(lib().rg_jf_matrix(size, k, cols, C.byref(r), C.byref(sz)), "rg_jf_matrix")
+    return [int(x) for x in cols[: 2 * k]], int(r.value), int(sz.value)
 
 
 def _err(what: str):
@@ -263,6 +283,25 @@ class KmerTable:
             o = np.argsort(keys, kind="stable")
             keys, counts = keys[o], counts[o]
         return keys.copy(), counts.copy()
+
+    def write_jhash(self, path: str, min_count: int = 1, max_count: int = 0, size: int = 1 << 33,
+                    counter_len: int = 4, cmdline=()) -> int:
+        """the .Jhash a `jellyfish count -L min_count -s size -o path` would leave (byte-compatible)"""
+        argv = (C.c_char_p * max(len(cmdline), 1))(*[a.encode() for a in cmdline])
+        n = lib().rg_table_write_jhash(self.h, path.encode(), min_count, max_count, size, counter_len, argv,
+                                       len(cmdline))
+        if n < 0:
+            raise _err("rg_table_write_jhash")
+        return int(n)
+
+    @classmethod
+    def read_jhash(cls, ctx, path: str):
+        """load a .Jhash written by us or by real Jellyfish; returns (table, JfInfo)"""
+        info = JfInfo()
+        h = lib().rg_table_read_jhash(ctx.h, path.encode(), C.byref(info))
+        if not h:
+            raise _err("rg_table_read_jhash")
+        return cls(ctx, info.k, bool(info.canonical), _handle=h), info
 
     def query(self, keys, min_count: int = 1) -> np.ndarray:
         keys = np.ascontiguousarray(keys, np.uint64)

@@ -143,6 +143,17 @@ void rg_dev_free(rg_ctx* ctx, void* p) {
     cudaFree(p);
   }
 }
+void* rg_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) {
+    rg_set_error("rg_host_alloc: cudaMallocHost failed");
+    return nullptr;
+  }
+  return p;
+}
+void rg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
 int rg_h2d(rg_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
   RG_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
@@ -365,7 +376,7 @@ static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, 
 }
 
 // every reader of a table goes through this: resolve what the enqueued pushes left behind
-static int table_finish(rg_table* t) {
+int rg_table_finish(rg_table* t) {
   if (!t->unchecked) return 0;
   const int rc = table_resolve_spill(t);
   if (rc == 0) t->unchecked = false;
@@ -535,7 +546,21 @@ int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_key
 int rg_count_end(rg_table* t) {
   if (!t) return RG_ERR_ARG;
   t->unchecked = true;
-  return table_finish(t);
+  return rg_table_finish(t);
+}
+
+// make room for up to extra_distinct new keys before a push (streaming callers do not know the
+// number of distinct k-mers up front): grows (re-hashes) when the load would exceed ~60 %
+int rg_table_reserve(rg_table* t, uint64_t extra_distinct) {
+  if (!t) return RG_ERR_ARG;
+  int rc = rg_table_finish(t);
+  if (rc) return rc;
+  uint64_t distinct = 0;
+  rc = rg_table_stats(t, &distinct, nullptr, nullptr);
+  if (rc) return rc;
+  const uint32_t want = tiles_for(distinct + extra_distinct);
+  if (want <= t->n_tiles) return 0;
+  return table_grow(t, std::max<uint32_t>(want, t->n_tiles + t->n_tiles / 2));
 }
 
 int rg_table_trim(rg_table* t) {
@@ -580,7 +605,7 @@ void rg_table_free(rg_table* t) {
 
 int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occ, uint64_t* n_slots) {
   if (!t) return RG_ERR_ARG;
-  int rc = table_finish(t);
+  int rc = rg_table_finish(t);
   if (rc) return rc;
   rc = rg_launch_stats(t, t->ctx->d_scratch);
   if (rc) return rc;
@@ -625,7 +650,7 @@ int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint6
   const uint64_t nb = rg_histo_rows(low, high);
   uint64_t* d_out = nullptr;
   RG_CUDA_OK(cudaMalloc(&d_out, nb * 8));
-  int rc = table_finish(t);
+  int rc = rg_table_finish(t);
   if (rc == 0) rc = rg_launch_histo(t, min_count, histo_base(low), nb, d_out);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(out_host, d_out, nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
@@ -655,7 +680,7 @@ int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* k
   uint32_t* d_counts = nullptr;
   RG_CUDA_OK(cudaMalloc(&d_keys, (cap ? cap : 1) * 8));
   RG_CUDA_OK(cudaMalloc(&d_counts, (cap ? cap : 1) * 4));
-  int64_t rc = table_finish(t);
+  int64_t rc = rg_table_finish(t);
   if (rc == 0) rc = rg_launch_dump(t, min_count ? min_count : 1, max_count, d_keys, d_counts, cap, ctx->d_scratch);
   uint64_t n = 0;
   if (rc == 0) rc = read_scalars(ctx, ctx->d_scratch, 1, &n);
@@ -710,7 +735,7 @@ int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_co
   uint32_t* dc = nullptr;
   RG_CUDA_OK(cudaMalloc(&dk, n * 8));
   RG_CUDA_OK(cudaMalloc(&dc, n * 4));
-  int rc = table_finish(t);
+  int rc = rg_table_finish(t);
   if (rc == 0) rc = RG_ERR_CUDA;
   if (rc == RG_ERR_CUDA && cudaMemcpyAsync(dk, keys_host, n * 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess) {
     rc = rg_launch_query(t, dk, n, min_count, dc);
@@ -737,7 +762,7 @@ static int fill_others(OtherTables& ot, rg_table* const* others, const uint64_t*
       rg_set_error("subtract: tables must share k");
       return RG_ERR_ARG;
     }
-    const int frc = table_finish(others[i]);
+    const int frc = rg_table_finish(others[i]);
     if (frc) return frc;
     ot.tv[i] = rg_view(others[i]);
     uint64_t m = other_min ? other_min[i] : 1;
@@ -752,7 +777,7 @@ int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* othe
   if (!subj) return RG_ERR_ARG;
   rg_ctx* ctx = subj->ctx;
   OtherTables ot;
-  int rc = table_finish(subj);
+  int rc = rg_table_finish(subj);
   if (rc) return rc;
   rc = fill_others(ot, others, other_min, n_others, subj->k);
   if (rc) return rc;

@@ -232,6 +232,9 @@ struct ExtractParams {
   int canonical;
 };
 
+// read back the status words of the enqueued pushes and resolve spills (every reader calls it first)
+int rg_table_finish(rg_table* t);
+
 int rg_launch_count_direct(rg_table* t, const ExtractParams& ep);
 int rg_launch_partition(rg_table* t, const ExtractParams& ep);   // into t->part_keys buckets
 int rg_launch_partition_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n);

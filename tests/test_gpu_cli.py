@@ -1,0 +1,130 @@
+"""GPU parity of the drop-in executables (tools/bin: jellyfish, RUFUS.Filter, RUFUS.Filter.single):
+the reference's own stage commands (tests/golden/make_golden.py replays them with the
+reference binaries) are run with OUR binaries on the same inputs and compared with the committed
+goldens; where the reference binaries travelled with the repo (oracle/_ref), the files we write are
+also fed to the REAL jellyfish (and vice versa) to pin the .Jhash byte format."""
+import gzip
+import hashlib
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from cases import golden
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "tools", "bin")
+JF = os.path.join(BIN, "jellyfish")
+REFJF = os.path.join(ROOT, "oracle", "_ref", "jellyfish")
+SAMPLES = {"testRun": ("Child", "Mother", "Father"), "edge": ("Subj", "CtlA", "CtlB")}
+
+
+def sh(cmd, cwd, **kw):
+    return subprocess.run(cmd, shell=True, check=True, cwd=cwd, capture_output=True, executable="/bin/bash", **kw)
+
+
+def md5(b):
+    return hashlib.md5(b).hexdigest()
+
+
+def records(path):
+    raw = open(path, "rb").read()
+    return raw[9 + int(raw[:9]):]
+
+
+@pytest.fixture(scope="module", params=["testRun", "edge"])
+def run(request, tmp_path_factory):
+    if not os.path.exists(JF):
+        pytest.fail("tools/bin/jellyfish is missing: run `make tools`")
+    case = request.param
+    g = golden(case)
+    work = str(tmp_path_factory.mktemp(case))
+    fq = {}
+    for s in SAMPLES[case]:
+        for m in (1, 2):
+            dst = os.path.join(work, f"{s}.mate{m}.fastq")
+            src = os.path.join(GOLDEN, case, f"{s}.mate{m}.fastq")
+            if os.path.exists(src + ".gz"):
+                open(dst, "wb").write(gzip.open(src + ".gz").read())
+            else:
+                shutil.copy(src, dst)
+        fq[s] = (f"{s}.mate1.fastq", f"{s}.mate2.fastq")
+    k = g["k"]
+    for i, s in enumerate(SAMPLES[case]):
+        lo = g["L"] if i == 0 else g["ctlL"]
+        sh(f"{JF} count --disk -m {k} -L {lo} -s 16M -t 4 -o {s}.Jhash -C {fq[s][0]} {fq[s][1]}", work)
+        sh(f"{JF} histo -f -o {s}.histo {s}.Jhash", work)
+    return case, g, work, fq
+
+
+def test_count_histo_dump_match_goldens(run):
+    case, g, work, fq = run
+    for s in SAMPLES[case]:
+        gs = g["samples"][s]
+        assert md5(open(os.path.join(work, s + ".histo"), "rb").read()) == gs["histo_md5"]
+        dump = sh(f"{JF} dump -c {s}.Jhash | LC_ALL=C sort", work).stdout
+        assert dump.count(b"\n") == gs["n_distinct"]
+        assert md5(dump) == gs["dump_sorted_md5"]
+        assert dump == gzip.open(os.path.join(GOLDEN, case, s + ".dump.sorted.gz")).read()
+
+
+def test_merge_query_hashlist_match_goldens(run):
+    case, g, work, fq = run
+    names = SAMPLES[case]
+    merged = sh(f"{JF} merge " + " ".join(s + ".Jhash" for s in names) + " > merge.out; cat merge.out", work).stdout
+    assert sorted(merged.decode().splitlines()) == g["merge_sorted"]
+    q = sh(f"{JF} query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) {names[0]}.Jhash", work).stdout.decode()
+    hl = [l for l in q.splitlines() if g["min_cov"] <= int(l.split()[1]) <= g["max_cov"]]
+    assert sorted(hl) == g["hashlist_sorted"]
+    open(os.path.join(work, "HashList"), "w").write("\n".join(hl) + "\n")
+
+
+def test_read_pull_matches_goldens(run):
+    case, g, work, fq = run
+    if not os.path.exists(os.path.join(work, "HashList")):
+        open(os.path.join(work, "HashList"), "w").write("\n".join(g["hashlist_sorted"]) + "\n")
+    m1, m2 = fq[SAMPLES[case][0]]
+    sh(f"{BIN}/RUFUS.Filter HashList {m1} {m2} out {g['k']} {g['minq']} {g['thresh']} 4", work)
+    o1 = open(os.path.join(work, "out.Mutations.Mate1.fastq")).read().splitlines()
+    o2 = open(os.path.join(work, "out.Mutations.Mate2.fastq")).read().splitlines()
+    assert sorted(o1[0::4]) == g["pulled_mate1_names_sorted"]
+    assert sorted(o2[0::4]) == g["pulled_mate2_names_sorted"]
+    # the records are the input records, verbatim
+    src = open(os.path.join(work, m1)).read().splitlines()
+    have = {tuple(src[i:i + 4]) for i in range(0, len(src), 4)}
+    assert all(tuple(o1[i:i + 4]) in have for i in range(0, len(o1), 4))
+    sh(f"{BIN}/RUFUS.Filter.single HashList {m1} se {g['k']} {g['minq']} {g['thresh']} 4", work)
+    se = open(os.path.join(work, "se.Mutations.fastq")).read().splitlines()
+    assert sorted(se[0::4]) == g["single_names_sorted"]
+    # mate files may be FIFOs (runRufus.sh:971-981): lock-step reading must not deadlock
+    sh(f"mkfifo f1 f2; cat {m1} > f1 & cat {m2} > f2 & timeout 120 {BIN}/RUFUS.Filter HashList f1 f2 fifo "
+       f"{g['k']} {g['minq']} {g['thresh']} 4; wait", work)
+    assert open(os.path.join(work, "fifo.Mutations.Mate1.fastq")).read().splitlines() == o1
+
+
+@pytest.mark.skipif(not os.path.exists(REFJF), reason="reference binaries (oracle/_ref) not present")
+def test_jhash_files_interoperate_with_real_jellyfish(run):
+    case, g, work, fq = run
+    names = SAMPLES[case]
+    for i, s in enumerate(names):
+        lo = g["L"] if i == 0 else g["ctlL"]
+        # the real tool reads our file: same records in the same order as our own dump
+        assert sh(f"{REFJF} dump -c {s}.Jhash", work).stdout == sh(f"{JF} dump -c {s}.Jhash", work).stdout
+        assert sh(f"{REFJF} histo -f {s}.Jhash", work).stdout == open(os.path.join(work, s + ".histo"), "rb").read()
+        # and the file the real tool writes for the same command has byte-identical records
+        sh(f"cat {fq[s][0]} {fq[s][1]} > {s}.both.fq; {REFJF} count --disk -m {g['k']} -L {lo} -s 16M -t 4 "
+           f"-o {s}.ref.Jhash -C {s}.both.fq", work)
+        assert records(os.path.join(work, s + ".Jhash")) == records(os.path.join(work, s + ".ref.Jhash"))
+        # we read the real file
+        assert sh(f"{JF} dump -c {s}.ref.Jhash", work).stdout == sh(f"{REFJF} dump -c {s}.ref.Jhash", work).stdout
+    ours = " ".join(s + ".Jhash" for s in names)
+    mixed = f"{names[0]}.Jhash {names[1]}.ref.Jhash {names[2]}.Jhash"
+    ref_merge = sh(f"{REFJF} merge {ours}", work).stdout
+    assert ref_merge == sh(f"{JF} merge {ours}", work).stdout          # same lines in the same order
+    assert sh(f"{REFJF} merge {mixed}", work).stdout == ref_merge      # real merge accepts a mix of both writers
+    assert sh(f"{JF} merge {mixed}", work).stdout == ref_merge
+    q = f"query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) {names[0]}.Jhash"
+    sh(f"{JF} merge {ours} > merge.out", work)
+    assert sh(f"{REFJF} {q}", work).stdout == sh(f"{JF} {q}", work).stdout

@@ -1,0 +1,348 @@
+// tools/jellyfish.cpp — drop-in for the `jellyfish` binary RUFUS calls (runRufus.sh:748-754,
+// RunJellyForRUFUS.sh:29-37, CheckJellyHashList.sh:12, Overlap.shorter.sh:245-255), with the work
+// done on the GPU through librufus_gpu.so. Same argv, same files:
+//
+//   jellyfish count [--disk] -m K [-C] [-L min] [-U max] -s SIZE [-t T] [-o OUT] IN...
+//        IN: FASTA/FASTQ files, FIFOs or /dev/stdin. OUT: a .Jhash byte-compatible with
+//        Jellyfish 2.2.5 binary/sorted (count_main.cc:214-354)
+//   jellyfish histo [-f] [-l low] [-h high] [-o OUT] DB          (histo_main.cc:46-110)
+//   jellyfish dump  [-c] [-t] [-L min] [-U max] [-o OUT] DB      (dump_main.cc)
+//   jellyfish query [-s FASTA]... [-o OUT] DB [MER...]           (query_main.cc:44-129)
+//   jellyfish merge DB DB...     the MODIFIED merge of src/modifiedJellyfish/jellyfish/merge_files.cc:86-154:
+//        prints `KMER<TAB>COUNT` for the k-mers present in exactly one input with count >= 5
+// Options RUFUS never passes are accepted where they are harmless and rejected otherwise.
+#include <algorithm>
+#include <memory>
+
+#include "rg_cli.hpp"
+
+static const char* next_arg(int& i, int argc, char** argv, const char* opt) {
+  if (i + 1 >= argc) die(std::string("Missing argument for ") + opt);
+  return argv[++i];
+}
+// "-m25" / "-m 25" / "--mer-len=25" / "--mer-len 25"
+static bool opt_value(const char* a, const char* shortf, const char* longf, int& i, int argc, char** argv,
+                      const char** val) {
+  const size_t ls = strlen(shortf), ll = strlen(longf);
+  if (strncmp(a, longf, ll) == 0 && ll > 0) {
+    if (a[ll] == '=') { *val = a + ll + 1; return true; }
+    if (a[ll] == 0) { *val = next_arg(i, argc, argv, longf); return true; }
+    return false;
+  }
+  if (ls > 0 && strncmp(a, shortf, ls) == 0 && a[1] != '-') {
+    if (a[ls] == 0) { *val = next_arg(i, argc, argv, shortf); return true; }
+    *val = a + ls;
+    return true;
+  }
+  return false;
+}
+
+static FILE* open_out(const char* path) {
+  if (!path) return stdout;
+  FILE* f = fopen(path, "w");
+  if (!f) die(std::string("Error opening output file '") + path + "'");
+  return f;
+}
+
+// ---------------------------------------------------------------------------- count
+static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
+  int k = 0, canonical = 0;
+  uint64_t size = 0, lower = 0, upper = 0;
+  uint32_t out_counter_len = 4;
+  const char* out = "mer_counts.jf";
+  std::vector<const char*> inputs;
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    const char* v = nullptr;
+    if (!strcmp(a, "-C") || !strcmp(a, "--canonical")) canonical = 1;
+    else if (!strcmp(a, "--disk") || !strcmp(a, "--text") || !strcmp(a, "--no-write")) { if (a[2] == 't') die("--text output is not supported"); }
+    else if (opt_value(a, "-m", "--mer-len", i, argc, argv, &v)) k = atoi(v);
+    else if (opt_value(a, "-s", "--size", i, argc, argv, &v)) size = parse_size(v);
+    else if (opt_value(a, "-t", "--threads", i, argc, argv, &v)) {}
+    else if (opt_value(a, "-o", "--output", i, argc, argv, &v)) out = v;
+    else if (opt_value(a, "-L", "--lower-count", i, argc, argv, &v)) lower = parse_size(v);
+    else if (opt_value(a, "-U", "--upper-count", i, argc, argv, &v)) upper = parse_size(v);
+    else if (opt_value(a, "-c", "--counter-len", i, argc, argv, &v)) {}
+    else if (opt_value(a, "-p", "--reprobes", i, argc, argv, &v)) { if (atoi(v) != 126) die("only the default --reprobes 126 is supported"); }
+    else if (opt_value(a, "", "--out-counter-len", i, argc, argv, &v)) out_counter_len = (uint32_t)atoi(v);
+    else if (opt_value(a, "-F", "--Files", i, argc, argv, &v) || opt_value(a, "-G", "--Generators", i, argc, argv, &v) ||
+             opt_value(a, "-g", "--generator", i, argc, argv, &v) || opt_value(a, "-Q", "--min-qual-char", i, argc, argv, &v) ||
+             opt_value(a, "", "--bf-size", i, argc, argv, &v) || opt_value(a, "", "--bc", i, argc, argv, &v) ||
+             opt_value(a, "", "--if", i, argc, argv, &v))
+      die(std::string("option not supported by the GPU count: ") + a);
+    else if (a[0] == '-' && a[1] != 0) die(std::string("unknown option ") + a);
+    else inputs.push_back(a);
+  }
+  if (k < 1 || k > 32 || (!canonical && k == 32)) die("mer length must be 1..32 (1..31 without -C)");
+  if (size == 0) die("Missing -s SIZE");
+  if (inputs.empty()) die("Missing input file");
+
+  rg_ctx* ctx = rg_init(0);
+  if (!ctx) die(rg_last_error());
+  // the table grows with the input (rg_table_reserve); -s only fixes the geometry written to the header
+  rg_table* t = rg_count_begin(ctx, k, canonical, 1ull << 22, RG_MODE_TILED);
+  if (!t) die(rg_last_error());
+  // two pinned buffers: the reader fills one while the other is copied and counted
+  const size_t chunk = 128u << 20;
+  ByteBuf fill, inflight;
+  fill.reserve(chunk + (8u << 20));
+  inflight.reserve(chunk + (8u << 20));
+  auto flush = [&](ByteBuf& b) {
+    check(rg_count_end(t), "count");                 // the previous chunk (in `inflight`) is done; spills resolved
+    check(rg_table_reserve(t, b.size()), "count");   // room for this chunk's k-mers, whatever they are
+    inflight.swap(b);
+    b.clear();
+    check(rg_count_push(t, inflight.data(), inflight.size()), "count");   // asynchronous
+  };
+  for (const char* path : inputs) {
+    FILE* f = fopen(path, "rb");
+    if (!f) die(std::string("Failed to open input file '") + path + "'");
+    read_sequences(f, path, fill, chunk, flush);
+    fclose(f);
+  }
+  if (!fill.empty()) flush(fill);
+  check(rg_count_end(t), "count");
+  check(rg_table_write_jhash(t, out, lower, upper, size, out_counter_len, full_argv + 1, full_argc - 1), "count");
+  rg_table_free(t);
+  rg_shutdown(ctx);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- helpers over a DB
+struct Db {
+  rg_ctx* ctx = nullptr;
+  rg_table* t = nullptr;
+  rg_jf_info info;
+};
+static Db open_db(rg_ctx* ctx, const char* path) {
+  Db d;
+  d.ctx = ctx;
+  d.t = rg_table_read_jhash(ctx, path, &d.info);
+  if (!d.t) die(rg_last_error());
+  return d;
+}
+
+// ---------------------------------------------------------------------------- histo
+static int histo_main(int argc, char** argv) {
+  uint64_t low = 1, high = 10000, inc = 1;
+  bool full = false;
+  const char* out = nullptr;
+  const char* db = nullptr;
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    const char* v = nullptr;
+    if (!strcmp(a, "-f") || !strcmp(a, "--full")) full = true;
+    else if (!strcmp(a, "-v") || !strcmp(a, "--verbose")) {}
+    else if (opt_value(a, "-l", "--low", i, argc, argv, &v)) low = parse_size(v);
+    else if (opt_value(a, "-h", "--high", i, argc, argv, &v)) high = parse_size(v);
+    else if (opt_value(a, "-i", "--increment", i, argc, argv, &v)) inc = parse_size(v);
+    else if (opt_value(a, "-t", "--threads", i, argc, argv, &v)) {}
+    else if (opt_value(a, "-o", "--output", i, argc, argv, &v)) out = v;
+    else if (a[0] == '-' && a[1] != 0) die(std::string("unknown option ") + a);
+    else db = a;
+  }
+  if (!db) die("Missing database file");
+  if (high < low) die("High count value must be >= to low count value");
+  if (inc != 1) die("only --increment 1 is supported");
+  rg_ctx* ctx = rg_init(0);
+  if (!ctx) die(rg_last_error());
+  Db d = open_db(ctx, db);
+  const uint64_t rows = rg_histo_rows(low, high);
+  std::vector<uint64_t> h(rows);
+  check(rg_histo(d.t, 1, low, high, h.data()), "histo");
+  FILE* f = open_out(out);
+  const uint64_t base = 1 >= low ? 0 : low - 1;     // histo_main.cc:64
+  for (uint64_t i = 0; i < rows; ++i)
+    if (h[i] > 0 || full) fprintf(f, "%llu %llu\n", (unsigned long long)(base + i), (unsigned long long)h[i]);
+  if (f != stdout) fclose(f);
+  rg_table_free(d.t);
+  rg_shutdown(ctx);
+  return 0;
+}
+
+// records of a table in the file order of its .Jhash
+static void ordered_records(Db& d, uint64_t lo, uint64_t hi, std::vector<uint64_t>& keys, std::vector<uint32_t>& counts) {
+  uint64_t n = 0;
+  check(rg_table_stats(d.t, &n, nullptr, nullptr), "stats");
+  keys.resize(n ? n : 1);
+  counts.resize(n ? n : 1);
+  uint64_t need = 0;
+  const int64_t got = rg_dump(d.t, lo, hi, keys.data(), counts.data(), keys.size(), &need);
+  check(got, "dump");
+  keys.resize((size_t)got);
+  counts.resize((size_t)got);
+  check(rg_jf_sort(d.ctx, keys.data(), counts.data(), keys.size(), d.info.size, d.info.k), "sort");
+}
+
+// ---------------------------------------------------------------------------- dump
+static int dump_main(int argc, char** argv) {
+  bool column = false, tab = false;
+  uint64_t lo = 1, hi = 0xFFFFFFFFull;
+  const char* out = nullptr;
+  const char* db = nullptr;
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    const char* v = nullptr;
+    if (!strcmp(a, "-c") || !strcmp(a, "--column")) column = true;
+    else if (!strcmp(a, "-t") || !strcmp(a, "--tab")) tab = true;
+    else if (!strcmp(a, "-ct") || !strcmp(a, "-tc")) column = tab = true;
+    else if (opt_value(a, "-L", "--lower-count", i, argc, argv, &v)) lo = parse_size(v);
+    else if (opt_value(a, "-U", "--upper-count", i, argc, argv, &v)) hi = parse_size(v);
+    else if (opt_value(a, "-o", "--output", i, argc, argv, &v)) out = v;
+    else if (a[0] == '-' && a[1] != 0) die(std::string("unknown option ") + a);
+    else db = a;
+  }
+  if (!db) die("Missing database file");
+  rg_ctx* ctx = rg_init(0);
+  if (!ctx) die(rg_last_error());
+  Db d = open_db(ctx, db);
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> counts;
+  ordered_records(d, lo ? lo : 1, hi, keys, counts);
+  FILE* f = open_out(out);
+  for (size_t i = 0; i < keys.size(); ++i) {
+    const std::string m = kmer_text(keys[i], d.info.k);
+    if (column) fprintf(f, "%s%c%u\n", m.c_str(), tab ? '\t' : ' ', counts[i]);
+    else fprintf(f, ">%u\n%s\n", counts[i], m.c_str());
+  }
+  if (f != stdout) fclose(f);
+  rg_table_free(d.t);
+  rg_shutdown(ctx);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- query
+// the k-mers of a sequence stream in order (mer_iterator.hpp:59-89), canonical if asked
+template <typename Bytes>
+static void kmers_of(const Bytes& seq, int k, bool canonical, std::vector<uint64_t>& out) {
+  const uint64_t mask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
+  uint64_t fwd = 0, rc = 0;
+  int filled = 0;
+  for (char ch : seq) {
+    int c;
+    switch (ch) {
+      case 'A': case 'a': c = 0; break;
+      case 'C': case 'c': c = 1; break;
+      case 'G': case 'g': c = 2; break;
+      case 'T': case 't': c = 3; break;
+      default: c = -1;
+    }
+    if (c < 0) { filled = 0; fwd = rc = 0; continue; }
+    fwd = ((fwd << 2) | (uint64_t)c) & mask;
+    rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
+    if (++filled >= k) out.push_back(canonical && rc < fwd ? rc : fwd);
+  }
+}
+
+static int query_main(int argc, char** argv) {
+  std::vector<const char*> seq_files, pos;
+  const char* out = nullptr;
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    const char* v = nullptr;
+    if (opt_value(a, "-s", "--sequence", i, argc, argv, &v)) seq_files.push_back(v);
+    else if (opt_value(a, "-o", "--output", i, argc, argv, &v)) out = v;
+    else if (!strcmp(a, "-l") || !strcmp(a, "--load") || !strcmp(a, "-L") || !strcmp(a, "--no-load")) {}
+    else if (!strcmp(a, "-i") || !strcmp(a, "--interactive")) die("--interactive is not supported");
+    else if (a[0] == '-' && a[1] != 0) die(std::string("unknown option ") + a);
+    else pos.push_back(a);
+  }
+  if (pos.empty()) die("Missing database file");
+  rg_ctx* ctx = rg_init(0);
+  if (!ctx) die(rg_last_error());
+  Db d = open_db(ctx, pos[0]);
+  const int k = d.info.k;
+  FILE* f = open_out(out);
+  auto answer = [&](const std::vector<uint64_t>& keys) {
+    std::vector<uint32_t> counts(keys.size() ? keys.size() : 1);
+    check(rg_query(d.t, keys.data(), keys.size(), 1, counts.data()), "query");
+    for (size_t i = 0; i < keys.size(); ++i) fprintf(f, "%s %u\n", kmer_text(keys[i], k).c_str(), counts[i]);
+  };
+  for (const char* path : seq_files) {
+    FILE* in = fopen(path, "rb");
+    if (!in) die(std::string("Failed to open input file '") + path + "'");
+    ByteBuf seq;
+    std::vector<uint64_t> keys;
+    read_sequences(in, path, seq, 64u << 20, [&](ByteBuf& b) {
+      keys.clear();
+      kmers_of(b, k, d.info.canonical, keys);
+      answer(keys);
+      b.clear();
+    });
+    fclose(in);
+    keys.clear();
+    kmers_of(seq, k, d.info.canonical, keys);
+    answer(keys);
+  }
+  std::vector<uint64_t> keys;
+  for (size_t i = 1; i < pos.size(); ++i) {
+    std::vector<char> m(pos[i], pos[i] + strlen(pos[i]));
+    std::vector<uint64_t> one;
+    if ((int)m.size() == k) kmers_of(m, k, d.info.canonical, one);
+    if (one.size() != 1) fprintf(stderr, "Invalid mer '%s'\n", pos[i]);
+    else keys.push_back(one[0]);
+  }
+  answer(keys);
+  if (f != stdout) fclose(f);
+  rg_table_free(d.t);
+  rg_shutdown(ctx);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- merge (modified)
+static int merge_main(int argc, char** argv) {
+  std::vector<const char*> files;
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    const char* v = nullptr;
+    if (opt_value(a, "-o", "--output", i, argc, argv, &v) || opt_value(a, "-L", "--lower-count", i, argc, argv, &v) ||
+        opt_value(a, "-U", "--upper-count", i, argc, argv, &v)) {}   // the modified merge ignores them (merge_files.cc:68-155)
+    else if (a[0] == '-' && a[1] != 0) die(std::string("unknown option ") + a);
+    else files.push_back(a);
+  }
+  if (files.size() < 2) die("Missing input files (at least 2)");
+  rg_ctx* ctx = rg_init(0);
+  if (!ctx) die(rg_last_error());
+  std::vector<Db> dbs;
+  for (const char* p : files) dbs.push_back(open_db(ctx, p));
+  for (size_t i = 1; i < dbs.size(); ++i) {          // merge_files.cc:193-202
+    const rg_jf_info &a = dbs[0].info, &b = dbs[i].info;
+    if (a.k != b.k) die(std::string("Can't merge hashes of different key lengths (") + files[i] + ")");
+    if (a.max_reprobe_offset != b.max_reprobe_offset) die(std::string("Can't merge hashes with different reprobing strategies (") + files[i] + ")");
+    if (a.size != b.size) die(std::string("Can't merge hash with different size (") + files[i] + ")");
+    if (memcmp(a.columns, b.columns, sizeof(a.columns)) != 0 || a.matrix_r != b.matrix_r)
+      die(std::string("Can't merge hash with different hash function (") + files[i] + ")");
+  }
+  std::vector<rg_table*> tabs;
+  std::vector<uint64_t> mins(dbs.size(), 1);
+  for (Db& d : dbs) tabs.push_back(d.t);
+  uint64_t cap = 1 << 20, need = 0;
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> counts;
+  int64_t n;
+  for (;;) {
+    keys.resize(cap);
+    counts.resize(cap);
+    n = rg_merge_unique(tabs.data(), mins.data(), (int)tabs.size(), 5, keys.data(), counts.data(), nullptr, cap, &need);
+    if (n == RG_ERR_SMALL) { cap = need + 1024; continue; }
+    check(n, "merge");
+    break;
+  }
+  check(rg_jf_sort(ctx, keys.data(), counts.data(), (uint64_t)n, dbs[0].info.size, dbs[0].info.k), "sort");
+  for (int64_t i = 0; i < n; ++i) printf("%s\t%u\n", kmer_text(keys[(size_t)i], dbs[0].info.k).c_str(), counts[(size_t)i]);
+  for (Db& d : dbs) rg_table_free(d.t);
+  rg_shutdown(ctx);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) die("Usage: jellyfish <count|histo|dump|query|merge> [options] (GPU build: rufus_b200)");
+  const std::string cmd = argv[1];
+  if (cmd == "count") return count_main(argc - 1, argv + 1, argc, argv);
+  if (cmd == "histo") return histo_main(argc - 1, argv + 1);
+  if (cmd == "dump") return dump_main(argc - 1, argv + 1);
+  if (cmd == "query") return query_main(argc - 1, argv + 1);
+  if (cmd == "merge") return merge_main(argc - 1, argv + 1);
+  if (cmd == "--version" || cmd == "-V") { printf("jellyfish 2.2.5 (%s)\n", rg_version()); return 0; }
+  die("Unknown command '" + cmd + "'");
+}

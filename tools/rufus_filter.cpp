@@ -1,0 +1,197 @@
+// tools/rufus_filter.cpp — drop-ins for bin/RUFUS.Filter (paired; src/RUFUS.Filter.cpp:26-301) and,
+// compiled with -DRG_SINGLE, bin/RUFUS.Filter.single (src/RUFUS.Filter.ss.cpp:25-211), with the
+// per-read k-mer lookups done on the GPU through librufus_gpu.so.
+//
+//   RUFUS.Filter        HashList Mate1.fq Mate2.fq OutStub K MinQ Threshold Threads
+//        -> OutStub.Mutations.Mate1.fastq / OutStub.Mutations.Mate2.fastq (the 4 lines of both mates,
+//           verbatim, of every pair where one mate has >= Threshold mutant k-mer windows)
+//   RUFUS.Filter.single HashList Reads.fq|stdin OutStub K MinQ Threshold Threads
+//        -> OutStub.Mutations.fastq (read name + ":MH<hits>")
+// The two mate files may be FIFOs: records are read 4 lines at a time, alternating between the
+// files, like the reference does (a lock-step reader never blocks the producer pair).
+// Like the reference, problems opening files are reported on stdout and the exit code stays 0
+// for the cases the reference returns 0 for (runRufus.sh only looks at the outputs).
+#include "rg_cli.hpp"
+
+struct Batch {
+  std::vector<char> seq, qual, text;       // text: the four lines of every record, '\n'-terminated
+  std::vector<uint64_t> offs, text_offs;   // per read
+  std::vector<uint32_t> name_len;          // length of line 1 (single-end: where ":MH" goes)
+  void clear() {
+    seq.clear(); qual.clear(); text.clear();
+    offs.assign(1, 0); text_offs.assign(1, 0); name_len.clear();
+  }
+  uint64_t n() const { return offs.size() - 1; }
+};
+
+// one 4-line record; false at end of input (a truncated record counts as the end, as getline would
+// leave empty strings the reference then scores as an empty read)
+static bool read_record(LineReader& lr, Batch& b) {
+  const char* l;
+  size_t n;
+  if (!lr.next(&l, &n)) return false;
+  b.name_len.push_back((uint32_t)n);
+  b.text.insert(b.text.end(), l, l + n);
+  b.text.push_back('\n');
+  size_t seq_len = 0;
+  if (lr.next(&l, &n)) {
+    b.seq.insert(b.seq.end(), l, l + n);
+    seq_len = n;
+    b.text.insert(b.text.end(), l, l + n);
+  }
+  b.text.push_back('\n');
+  if (lr.next(&l, &n)) b.text.insert(b.text.end(), l, l + n);
+  b.text.push_back('\n');
+  size_t qn = 0;
+  if (lr.next(&l, &n)) {
+    qn = n < seq_len ? n : seq_len;
+    b.qual.insert(b.qual.end(), l, l + qn);
+    b.text.insert(b.text.end(), l, l + n);
+  }
+  b.qual.insert(b.qual.end(), seq_len - qn, '\0');   // missing quality = below any MinQ
+  b.text.push_back('\n');
+  b.offs.push_back(b.seq.size());
+  b.text_offs.push_back(b.text.size());
+  return true;
+}
+
+static std::string slurp(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return std::string();
+  std::string s;
+  char buf[1 << 16];
+  size_t got;
+  while ((got = fread(buf, 1, sizeof(buf), f)) > 0) s.append(buf, got);
+  fclose(f);
+  return s;
+}
+
+int main(int argc, char** argv) {
+#ifdef RG_SINGLE
+  const int need = 8;
+  printf("Call is PreBuiltMutHash Mutant.fq  firstpassfile hashsize MinQ HashCountThreshold threads \n");
+#else
+  const int need = 9;
+  printf("Call is PreBuiltMutHash Mutant.fq1 Mutant.fq2 firstpassfile hashsize MinQ HashCountThreshold threads \n");
+#endif
+  if (argc < need) {
+    printf("Error, not enough arguments\n");
+    return 1;
+  }
+  int a = 1;
+  const char* hashlist = argv[a++];
+  const char* in1 = argv[a++];
+#ifndef RG_SINGLE
+  const char* in2 = argv[a++];
+#endif
+  const std::string stub = argv[a++];
+  const int k = atoi(argv[a++]);
+  const int minq = atoi(argv[a++]);
+  const int thresh = atoi(argv[a++]);
+  if (k < 1 || k > 32) die("HashSize must be 1..32");
+
+  FILE* hf = fopen(hashlist, "rb");
+  if (!hf) {
+    printf("Error, ParentHashFile could not be opened");
+    return 0;
+  }
+  fclose(hf);
+#ifdef RG_SINGLE
+  FILE* f1 = fopen(!strcmp(in1, "stdin") ? "/dev/stdin" : in1, "rb");
+#else
+  FILE* f1 = fopen(in1, "rb");
+  FILE* f2 = fopen(in2, "rb");
+  if (!f2) {
+    printf("Error, MutFile2 could not be opened");
+    return 0;
+  }
+#endif
+  if (!f1) {
+    printf("Error, MutFile could not be opened");
+    return 0;
+  }
+#ifdef RG_SINGLE
+  FILE* o1 = fopen((stub + ".Mutations.fastq").c_str(), "w");
+#else
+  FILE* o1 = fopen((stub + ".Mutations.Mate1.fastq").c_str(), "w");
+  FILE* o2 = fopen((stub + ".Mutations.Mate2.fastq").c_str(), "w");
+  if (!o2) {
+    printf("ERROR, Output file could not be opened -%s\n", stub.c_str());
+    return 0;
+  }
+#endif
+  if (!o1) {
+    printf("ERROR, Output file could not be opened -%s\n", stub.c_str());
+    return 0;
+  }
+
+  rg_ctx* ctx = rg_init(0);
+  if (!ctx) die(rg_last_error());
+  const std::string text = slurp(hashlist);
+#ifdef RG_SINGLE
+  rg_set* set = rg_set_from_hashlist_text(ctx, text.data(), text.size(), k, 0);
+#else
+  rg_set* set = rg_set_from_hashlist_text(ctx, text.data(), text.size(), k, 1);
+#endif
+  if (!set) die(rg_last_error());
+  printf("Mutant k-mers loaded: %llu\n", (unsigned long long)rg_set_size(set));
+
+  const uint64_t batch_reads = 1u << 20;
+  uint64_t n_in = 0, n_out = 0;
+  LineReader r1(f1);
+  Batch b1;
+#ifndef RG_SINGLE
+  LineReader r2(f2);
+  Batch b2;
+#endif
+  for (bool more = true; more;) {
+    b1.clear();
+#ifdef RG_SINGLE
+    while (b1.n() < batch_reads && (more = read_record(r1, b1))) {}
+    if (b1.n() == 0) break;
+    std::vector<int32_t> hits(b1.n());
+    check(rg_filter_single(set, b1.seq.data(), b1.qual.data(), b1.offs.data(), b1.n(), minq, hits.data()), "filter");
+    for (uint64_t i = 0; i < b1.n(); ++i)
+      if (hits[i] >= thresh) {
+        const char* rec = b1.text.data() + b1.text_offs[i];
+        fwrite(rec, 1, b1.name_len[i], o1);
+        fprintf(o1, ":MH%d", hits[i]);
+        fwrite(rec + b1.name_len[i], 1, b1.text_offs[i + 1] - b1.text_offs[i] - b1.name_len[i], o1);
+        ++n_out;
+      }
+#else
+    b2.clear();
+    while (b1.n() < batch_reads) {        // lock-step: one record from each file
+      if (!read_record(r1, b1)) { more = false; break; }
+      if (!read_record(r2, b2)) {
+        more = false;                     // mate 2 ended first: drop the unpaired mate-1 record
+        b1.offs.pop_back(); b1.text_offs.pop_back(); b1.name_len.pop_back();
+        b1.seq.resize(b1.offs.back()); b1.qual.resize(b1.offs.back()); b1.text.resize(b1.text_offs.back());
+        break;
+      }
+    }
+    if (b1.n() == 0) break;
+    std::vector<uint8_t> keep(b1.n());
+    check(rg_filter_pairs(set, b1.seq.data(), b1.qual.data(), b1.offs.data(), b2.seq.data(), b2.qual.data(),
+                          b2.offs.data(), b1.n(), minq, thresh, keep.data()), "filter");
+    for (uint64_t i = 0; i < b1.n(); ++i)
+      if (keep[i]) {
+        fwrite(b1.text.data() + b1.text_offs[i], 1, b1.text_offs[i + 1] - b1.text_offs[i], o1);
+        fwrite(b2.text.data() + b2.text_offs[i], 1, b2.text_offs[i + 1] - b2.text_offs[i], o2);
+        ++n_out;
+      }
+#endif
+    n_in += b1.n();
+  }
+  fclose(o1);
+  fclose(f1);
+#ifndef RG_SINGLE
+  fclose(o2);
+  fclose(f2);
+#endif
+  printf("Read in %llu records: Found %llu\n\nDone running RUFUS.Filter (GPU)\n", (unsigned long long)n_in,
+         (unsigned long long)n_out);
+  rg_set_free(set);
+  rg_shutdown(ctx);
+  return 0;
+}
