@@ -2,7 +2,7 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX  := $(firstword $(wildcard /usr/bin/g++) g++)
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Irufus_b200/csrc -ccbin $(CXX)
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude -Irufus_b200/csrc -ccbin $(CXX) $(EXTRA_NVFLAGS)
 CSRC := $(wildcard rufus_b200/csrc/*.cu)
 OBJS := $(CSRC:.cu=.o)
 LIB  := rufus_b200/librufus_gpu.so

@@ -335,7 +335,7 @@ static int prepare_buckets(rg_table* t, uint64_t n_keys) {
       cudaFree(t->part_keys);
       t->part_keys = nullptr;
     }
-    RG_CUDA_OK(cudaMalloc(&t->part_keys, cap * t->n_tiles * 8));
+    RG_CUDA_OK(cudaMalloc(&t->part_keys, cap * t->n_tiles * 8 + 64));   // + slack: 16-byte staging reads may touch one key past a slab
     t->part_cap = cap * t->n_tiles;
   }
   t->bucket_cap = (uint32_t)(t->part_cap / t->n_tiles);

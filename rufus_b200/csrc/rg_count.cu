@@ -133,10 +133,21 @@ int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads,
 // the table already holds data) — two streaming passes instead of one random
 // DRAM round trip per k-mer.
 // ---------------------------------------------------------------------------
-constexpr int TILE_THREADS = 1024;
-constexpr uint32_t TILE_RING_KEYS = 128;   // per-warp staging ring of the bucket stream (1 KiB x 32 warps)
+#ifndef TILE_THREADS_N
+#define TILE_THREADS_N 1024
+#endif
+constexpr int TILE_THREADS = TILE_THREADS_N;
+// per-warp staging ring of the bucket stream: 32 KiB in all (what is left beside the 192 KiB tile)
+constexpr uint32_t TILE_RING_KEYS = 4096 / (TILE_THREADS / 32);
+constexpr uint32_t TILE_QUARTER = TILE_RING_KEYS / 4;          // keys per cp.async group: 32 (8 B/lane) or 64 (16 B/lane)
+static_assert(TILE_QUARTER == 32 || TILE_QUARTER == 64, "ring quarter must be 32 or 64 keys");
 constexpr size_t TILE_SMEM = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (TILE_THREADS / 32) * TILE_RING_KEYS * 8;
 
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gmem_src)
@@ -230,16 +241,24 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64) +
                      warp * TILE_RING_KEYS;
-    const uint32_t chunk = (n + 31) >> 5;
+    constexpr uint32_t NWARPS = TILE_THREADS / 32, PER_LANE = TILE_QUARTER / 32;
+    const uint32_t chunk = (((n + NWARPS - 1) / NWARPS) + 1u) & ~1u;            // even: 16-byte aligned stream starts
     const uint32_t begin = min(n, warp * chunk);
     const uint32_t n_rel = min(n, begin + chunk) - begin;       // keys of this warp's stream
-    const uint64_t* gsrc = part_keys + (uint64_t)tile * bucket_cap + begin + lane;   // this lane's next key to stage
+    // this lane's next key(s) to stage
+    const uint64_t* gsrc = part_keys + (uint64_t)tile * bucket_cap + begin + lane * PER_LANE;
     uint32_t issued = 0;              // cp.async issued for stream positions [0, issued)
     auto issue_quarter = [&]() {
-      if (issued + lane < n_rel) cp_async_8(ring + (issued & (TILE_RING_KEYS - 32)) + lane, gsrc);
+      uint64_t* dst = ring + (issued & (TILE_RING_KEYS - TILE_QUARTER)) + lane * PER_LANE;
+      if (PER_LANE == 1) {
+        if (issued + lane < n_rel) cp_async_8(dst, gsrc);
+      } else {
+        // 16 bytes = 2 keys; the second may lie past the stream's end (still inside the bucket slab: never claimed)
+        if (issued + lane * 2 < n_rel) cp_async_16(dst, gsrc);
+      }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      gsrc += 32;
-      issued += 32;
+      gsrc += TILE_QUARTER;
+      issued += TILE_QUARTER;
     };
 #pragma unroll
     for (int q = 0; q < 4; ++q) issue_quarter();
@@ -263,7 +282,7 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
       }
       const uint32_t new_head = min(n_rel, head + (uint32_t)__popc(want));
       // ---- the reader left a quarter of the ring: refill it with the quarter 4 ahead
-      if ((new_head ^ head) >> 5) {
+      if ((new_head ^ head) / TILE_QUARTER) {
         __syncwarp();                 // every lane has read its claim before the slot is overwritten
         issue_quarter();
         asm volatile("cp.async.wait_group 2;" ::: "memory");

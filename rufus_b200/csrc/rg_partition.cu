@@ -22,6 +22,10 @@
 constexpr int PART_THREADS = 1024 / PART_CTAS;
 constexpr int PART_R = 16;                          // windows per thread: one 16-base word, so every shift below is static
 constexpr uint32_t PART_K = PART_THREADS * PART_R;  // windows (keys) counting-sorted at once
+#ifndef PART_RUN_ALIGN
+#define PART_RUN_ALIGN 1                            // runs are padded to this many keys; 1 = packed (measured best: 4 -> 0.83+0.62, 2 -> 0.74+0.58, 1 -> 0.73+0.53 ms)
+#endif
+constexpr uint32_t PART_PAD = PART_RUN_ALIGN - 1;
 constexpr int PART_TILES_PER_THREAD = 3;             // the sorted kernel handles up to 3 * 1024 tiles (shared memory caps it earlier)
 // 227 KiB opt-in limit per CTA (static + dynamic); 228 KiB per SM with 1 KiB reserved per resident CTA
 constexpr size_t PART_SMEM_LIMIT = PART_CTAS == 1 ? 232448 : (233472 / PART_CTAS - 1024);
@@ -338,7 +342,7 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
       gb[j] = 0;
       if (cnt[j]) {
         loff[t0 + j] = run;
-        gb[j] = atomicAdd(g.cursor + t0 + j, (cnt[j] + 3u) & ~3u);
+        gb[j] = atomicAdd(g.cursor + t0 + j, (cnt[j] + PART_PAD) & ~PART_PAD);
         run += cnt[j];
       }
     }
@@ -358,12 +362,12 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     for (int j = 0; j < PART_TILES_PER_THREAD; ++j) {
       if (cnt[j]) {
         const uint32_t t = t0 + j;
-        const uint32_t padded = (cnt[j] + 3u) & ~3u;
+        const uint32_t padded = (cnt[j] + PART_PAD) & ~PART_PAD;
         const uint32_t at = t * g.bucket_cap + gb[j];                // index of the run in part_keys
         if (gb[j] + padded <= g.bucket_cap) {
-          if (cnt[j] + 0 < padded) g.part_keys[at + padded - 1] = RG_EMPTY;   // at most 3 pad slots
-          if (cnt[j] + 1 < padded) g.part_keys[at + padded - 2] = RG_EMPTY;
-          if (cnt[j] + 2 < padded) g.part_keys[at + padded - 3] = RG_EMPTY;
+#pragma unroll
+          for (uint32_t q = 1; q <= PART_PAD; ++q)                            // at most PART_PAD pad slots
+            if (cnt[j] + q - 1 < padded) g.part_keys[at + padded - q] = RG_EMPTY;
           hist[t] = at - run;
         } else {
           // bucket overflow (heavy hitters): this run goes to the spill list (step 4); what it
