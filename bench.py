@@ -211,6 +211,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     trio = make_data(args.pairs, args.genome, args.seed, None if world == 1 else rank)

@@ -50,7 +50,9 @@ const char* rg_version(void);
 rg_ctx* rg_init(int device);
 void rg_shutdown(rg_ctx* ctx);
 /* Run on the caller's CUDA stream (a cudaStream_t passed as void*), e.g. torch's
- * current stream, so the caller's events time our kernels. NULL = library stream. */
+ * current stream, so the caller's events time our kernels and its other work (NCCL
+ * collectives, reductions) is ordered with ours. NULL = the library's own stream; pass
+ * cudaStreamLegacy ((void*)0x1) for the legacy default stream. */
 int rg_set_stream(rg_ctx* ctx, void* cuda_stream);
 int rg_sync(rg_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

@@ -163,7 +163,14 @@ class Context:
         self.device = device
 
     def use_stream(self, cuda_stream_ptr: int | None):
-        _check(lib().rg_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)), "rg_set_stream")
+        """Run on the caller's CUDA stream. None = the library's own stream; 0 = the legacy default
+        stream (what torch.cuda.current_stream().cuda_stream reports for torch's default stream),
+        passed to the library as cudaStreamLegacy (0x1) since a NULL handle means "library stream"."""
+        if cuda_stream_ptr is None:
+            p = 0
+        else:
+            p = cuda_stream_ptr or 1
+        _check(lib().rg_set_stream(self.h, C.c_void_p(p)), "rg_set_stream")
 
     def sync(self):
         _check(lib().rg_sync(self.h), "rg_sync")

@@ -32,12 +32,14 @@ def split_sizes_from_offsets(offsets) -> list[int]:
     return [o[i + 1] - o[i] for i in range(len(o) - 1)]
 
 
-def exchange_keys(keys, send_sizes, group=None):
+def exchange_keys(keys, send_sizes, group=None, async_op=False):
     """One ragged all-to-all of packed k-mers (torch tensor, int64 view of u64 keys).
 
     keys: 1-D tensor laid out as contiguous per-destination buckets; send_sizes[r] keys
-    go to rank r. Returns the tensor of keys this rank owns. Works on any backend
-    (NCCL on GPUs, gloo on CPU for the host-logic tests)."""
+    go to rank r. Returns the tensor of keys this rank owns (async_op=True: (tensor, work);
+    the caller waits on `work` before using the tensor, so that the transfer overlaps
+    whatever it enqueues in between). Works on any backend (NCCL on GPUs, gloo on CPU for
+    the host-logic tests)."""
     import torch
     import torch.distributed as dist
 
@@ -47,9 +49,9 @@ def exchange_keys(keys, send_sizes, group=None):
     dist.all_to_all_single(recv, send, group=group)
     recv_sizes = [int(x) for x in recv.tolist()]
     out = torch.empty(sum(recv_sizes), dtype=keys.dtype, device=keys.device)
-    dist.all_to_all_single(out, keys[: sum(send_sizes)], output_split_sizes=recv_sizes,
-                           input_split_sizes=list(send_sizes), group=group)
-    return out
+    work = dist.all_to_all_single(out, keys[: sum(send_sizes)], output_split_sizes=recv_sizes,
+                                  input_split_sizes=list(send_sizes), group=group, async_op=async_op)
+    return (out, work) if async_op else out
 
 
 def gather_varlen(local, group=None):
@@ -94,33 +96,42 @@ class DevicePipeline:
         self.hits2 = torch.empty(self.n_pairs, dtype=torch.int32, device=dev)
         self.keep = torch.empty(self.n_pairs, dtype=torch.uint8, device=dev)
         if world > 1:
-            n_win = max(int(s.numel()) for s in streams)
-            self.part_keys = torch.empty(n_win, dtype=torch.int64, device=dev)
+            # one send buffer per sample: the all-to-all of sample i runs (NCCL's stream) while the
+            # extraction of sample i+1 fills the next buffer
+            self.part_keys = [torch.empty(int(s.numel()), dtype=torch.int64, device=dev) for s in streams]
             self.part_offs = torch.empty(world + 1, dtype=torch.int64, device=dev)
         self.last = {}
 
-    def count_sample(self, i: int):
+    def extract_and_send(self, i: int):
+        """world > 1: extract + bucket sample i by owner rank, start its all-to-all (asynchronous)."""
         L = api.lib()
-        t = self.tables[i]
-        t.clear()
         s = self.streams[i]
-        if self.world == 1:
-            t.push_dev(s, s.numel(), self.read_len)
-        else:
-            rc = L.rg_extract_partition_dev(self.ctx.h, self.k, 1, api._ptr(s), s.numel(), self.read_len, self.world,
-                                            api._ptr(self.part_keys), api._ptr(self.part_offs))
-            api._check(rc, "rg_extract_partition_dev")
-            sizes = split_sizes_from_offsets(self.part_offs.tolist())
-            mine = exchange_keys(self.part_keys, sizes)
-            t.push_keys_dev(mine, mine.numel())
-            self.last.setdefault("sent_keys", []).append(sum(sizes) - sizes[self.rank])
+        rc = L.rg_extract_partition_dev(self.ctx.h, self.k, 1, api._ptr(s), s.numel(), self.read_len, self.world,
+                                        api._ptr(self.part_keys[i]), api._ptr(self.part_offs))
+        api._check(rc, "rg_extract_partition_dev")
+        sizes = split_sizes_from_offsets(self.part_offs.tolist())
+        self.last.setdefault("sent_keys", []).append(sum(sizes) - sizes[self.rank])
+        return exchange_keys(self.part_keys[i], sizes, async_op=True)
 
     def step(self) -> dict:
         torch = self.torch
         L = api.lib()
         self.last = {}
-        for i in range(len(self.tables)):
-            self.count_sample(i)          # enqueued only: no host synchronisation between the samples
+        n = len(self.tables)
+        for t in self.tables:
+            t.clear()
+        if self.world == 1:
+            for t, s in zip(self.tables, self.streams):
+                t.push_dev(s, s.numel(), self.read_len)   # enqueued only: no host synchronisation between the samples
+        else:
+            # software pipeline: exchange of sample i overlaps extraction of sample i+1 and insertion of sample i-1
+            inflight = self.extract_and_send(0)
+            for i in range(n):
+                nxt = self.extract_and_send(i + 1) if i + 1 < n else None
+                mine, work = inflight
+                work.wait()                                # the compute stream waits for the transfer, not the host
+                self.tables[i].push_keys_dev(mine, mine.numel())
+                inflight = nxt
         for t in self.tables:
             t.end(trim=False)             # one read-back of the status words per table (spill / foreign keys)
         # histogram of the subject (jellyfish histo -f); all-reduced over shards
