@@ -39,38 +39,69 @@ def log(*a):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region. NVML in a thread (a sample every
+    ~2 ms; the timed region of the default run is only tens of ms, too short for `nvidia-smi -lms`),
+    with nvidia-smi as the fallback when pynvml is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.sm, self.reasons, self.mx = gpu_index, [], set(), None
+        self._stop, self._thr, self._nvml = threading.Event(), None, None
+
+    def _poll(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:
+                log("clock sample failed:", e)
+                return
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception as e:  # nvidia-smi missing
-            log("clock sampler unavailable:", e)
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            import pynvml as n
+            n.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap: go through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.idx).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.idx), "pci_bus_id") else None
+            self._h = None
+            if bus is not None:
+                for i in range(n.nvmlDeviceGetCount()):
+                    h = n.nvmlDeviceGetHandleByIndex(i)
+                    if int(n.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        self._h = h
+                        break
+            if self._h is None:
+                self._h = n.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = int(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM))
+            self._nvml = n
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
+        except Exception as e:
+            log("NVML clock sampler unavailable:", e)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit()]
-        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1.0)
+        if not self.sm:      # fallback: one nvidia-smi query right after the timed region
+            try:
+                q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                    "-i", str(self.idx)], capture_output=True, text=True, timeout=20).stdout.split(",")
+                self.sm, self.mx = [int(q[0])], int(q[1])
+            except Exception as e:
+                log("clock sampler unavailable:", e)
+        return {"sm_mhz": int(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # --------------------------------------------------------------------------- data
@@ -183,7 +214,7 @@ def workload_config(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--pairs", type=int, default=500_000, help="read pairs per sample per GPU")
