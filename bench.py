@@ -222,6 +222,8 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs/sample of the CPU baseline sample")
     ap.add_argument("--mode", default="tiled", choices=["tiled", "direct"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: peer-to-peer partition into the owners' slabs, or extract + NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -260,7 +262,7 @@ def main():
     # distinct k-mers per shard: genomic (two haplotypes, ~3 % private) / world + ~6.2 error k-mers per read
     est = int((1.03 * args.genome) / world + 6.2 * 2 * args.pairs)
     pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, 150 * world, MINQ, THRESH,
-                                   mode=mode, rank=rank, world=world)
+                                   mode=mode, rank=rank, world=world, exchange=args.exchange)
 
     def barrier():
         if world > 1:
@@ -310,6 +312,8 @@ def main():
     kern = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in prof.items()}
     if world == 1:
         names = ["partition_kernel", "tile_insert_kernel"] if mode == api.MODE_TILED else ["count_direct_kernel"]
+    elif args.exchange == "p2p":
+        names = ["partition_p2p_kernel", "partition_groups_kernel", "tile_insert_kernel"]
     else:
         names = ["extract_parts_kernel<count>", "extract_parts_kernel<scatter>", "partition_keys_kernel",
                  "tile_insert_kernel"] if mode == api.MODE_TILED else ["extract_parts_kernel<count>",

@@ -120,6 +120,22 @@ int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_key
 /* restrict a table to the keys of shard `part` of `n_parts` (tile numbering is global) */
 int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts);
 
+/* Peer-to-peer multi-GPU counting (one process per GPU, NVLink peer memory; no collective in the
+ * data path): every GPU's partition pass sorts its reads into the hash-prefix groups of ALL shards
+ * and writes each run straight into the owner's slab; then every GPU finishes its own groups.
+ *   setup (once, after rg_table_set_shard): rg_table_p2p_prepare on every rank, all-gather the
+ *     64-byte handles of rg_table_p2p_export, rg_table_p2p_import each of them;
+ *   per sample: rg_count_p2p_begin -> barrier -> rg_count_p2p_scatter_dev -> barrier ->
+ *     rg_count_p2p_finish (the barriers are the caller's, e.g. a tiny all-reduce on the stream).
+ * groups_per_shard x n_parts must fit one partition pass (<= ~2900); max_keys_per_push bounds the
+ * keys a shard receives per sample (sizes the exported slabs; they cannot grow). */
+int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_keys_per_push);
+int rg_table_p2p_export(rg_table* t, void* handle64_out);
+int rg_table_p2p_import(rg_table* t, uint32_t rank, const void* handle64);
+int rg_count_p2p_begin(rg_table* t);
+int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride);
+int rg_count_p2p_finish(rg_table* t);
+
 /* ---- H1: histogram ------------------------------------------------------
  * replaces `jellyfish histo -l low -h high -i 1` (histo_main.cc:34-44,64-84) over
  * the entries a `-L min_count` dump would hold. out (HOST) has high+2-base rows

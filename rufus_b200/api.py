@@ -77,6 +77,12 @@ def lib():
         "rg_key_partition": (u32, [u64, u32]),
         "rg_count_push_keys_dev": (i32, [vp, vp, u64]),
         "rg_table_set_shard": (i32, [vp, u32, u32]),
+        "rg_table_p2p_prepare": (i32, [vp, u32, u64]),
+        "rg_table_p2p_export": (i32, [vp, vp]),
+        "rg_table_p2p_import": (i32, [vp, u32, vp]),
+        "rg_count_p2p_begin": (i32, [vp]),
+        "rg_count_p2p_scatter_dev": (i32, [vp, vp, u64, u32]),
+        "rg_count_p2p_finish": (i32, [vp]),
         "rg_histo_rows": (u64, [u64, u64]),
         "rg_histo": (i32, [vp, u64, u64, u64, vp]),
         "rg_dump": (i64, [vp, u64, u64, vp, vp, u64, C.POINTER(u64)]),

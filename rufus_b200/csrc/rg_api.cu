@@ -1,6 +1,7 @@
 // rg_api.cu — the C ABI of librufus_gpu.so (include/rufus_gpu.h): context,
 // table lifetime/growth, host<->device staging. No CPU compute path exists here:
 // every entry point ends in a kernel launch from rg_count.cu / rg_ops.cu / rg_filter.cu.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -40,6 +41,7 @@ rg_ctx* rg_init(int device) {
   ctx->stream = ctx->own_stream;
   RG_CUDA_OKP(cudaMallocHost(&ctx->h_scratch, 256 * sizeof(uint64_t)));
   RG_CUDA_OKP(cudaMalloc(&ctx->d_scratch, 256 * sizeof(uint64_t)));
+  if (const char* fg = getenv("RG_GROUPS_LOCAL")) ctx->force_groups = (uint32_t)atoi(fg);
   RG_CUDA_OKP(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     RG_CUDA_OKP(cudaEventCreateWithFlags(&ctx->slot_copied[i], cudaEventDisableTiming));
@@ -222,14 +224,56 @@ static int pool_ensure(rg_ctx* ctx, int i, uint64_t bytes) {
   return 0;
 }
 
-static int table_alloc_tiles(rg_table* t, uint32_t n_tiles) {
+// Tile count and group geometry for at least `wanted` tiles (header of rg_internal.cuh):
+//  * direct mode: no constraint;
+//  * tiled mode, small table: group_tiles = 1 (one partition pass), whole waves of tile-insert CTAs;
+//  * tiled mode, more tiles than one sorted pass can histogram in shared memory: 8 x SMs groups
+//    per shard (two passes: stream -> groups -> tiles);
+//  * peer-to-peer multi-GPU counting: p2p_groups groups per shard (the level-1 pass sorts into the
+//    groups of ALL shards at once).
+static void choose_geometry(const rg_table* t, uint32_t wanted, uint32_t* n_tiles, uint32_t* group_tiles) {
+  const rg_ctx* ctx = t->ctx;
+  const uint32_t sm = (uint32_t)ctx->sm_count;
+  *group_tiles = 1;
+  *n_tiles = wanted ? wanted : 1;
+  if (t->mode != RG_MODE_TILED) return;
+  const uint32_t max1 = rg_partition_max_buckets();
+  uint32_t groups = 0;
+  if (t->p2p_groups) groups = t->p2p_groups;
+  else if (ctx->force_groups) groups = ctx->force_groups;
+  else if (wanted > max1) groups = std::min(8 * sm, max1);
+  if (groups) {
+    if (groups > wanted) groups = wanted ? wanted : 1;
+    *group_tiles = (wanted + groups - 1) / groups;
+    *n_tiles = groups * *group_tiles;
+    return;
+  }
+  if (wanted > sm) {
+    const uint32_t rounded = (wanted + sm - 1) / sm * sm;   // tiled insert runs one CTA per tile: whole waves
+    *n_tiles = rounded <= max1 ? rounded : wanted;
+  }
+}
+
+static void drop_buckets(rg_table* t) {
+  if (t->part_cursor) { cudaFree(t->part_cursor); t->part_cursor = nullptr; }
+  if (t->part_keys) { cudaFree(t->part_keys); t->part_keys = nullptr; t->part_cap = 0; }
+  if (!t->p2p_block) {   // (the peer-to-peer block is exported: it lives as long as the table)
+    if (t->grp_cursor) { cudaFree(t->grp_cursor); t->grp_cursor = nullptr; }
+    if (t->grp_keys) { cudaFree(t->grp_keys); t->grp_keys = nullptr; t->grp_alloc_keys = 0; }
+  }
+}
+
+static int table_alloc_tiles(rg_table* t, uint32_t wanted) {
   rg_ctx* ctx = t->ctx;
+  uint32_t n_tiles, group_tiles;
+  choose_geometry(t, wanted, &n_tiles, &group_tiles);
   const uint64_t slots = (uint64_t)n_tiles << RG_TILE_BITS;
   RG_CUDA_OK(cudaMalloc(&t->keys, slots * 8));
   RG_CUDA_OK(cudaMalloc(&t->counts, slots * 4));
   RG_CUDA_OK(cudaMemsetAsync(t->keys, 0xFF, slots * 8, ctx->stream));
   RG_CUDA_OK(cudaMemsetAsync(t->counts, 0, slots * 4, ctx->stream));
   t->n_tiles = n_tiles;
+  t->group_tiles = group_tiles;
   t->n_tiles_global = n_tiles * t->shard_parts;
   t->tile_first = n_tiles * t->shard_part;
   return 0;
@@ -251,13 +295,16 @@ static int table_grow(rg_table* t, uint32_t new_tiles) {
   const uint64_t old_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
   t->keys = nullptr;
   t->counts = nullptr;
-  if (t->mode == RG_MODE_TILED && new_tiles > (uint32_t)ctx->sm_count)
-    new_tiles = (new_tiles + ctx->sm_count - 1) / ctx->sm_count * ctx->sm_count;
+  if (t->p2p_block) {
+    rg_set_error("count: a peer-to-peer table cannot grow (its slabs are exported); raise est_distinct");
+    t->keys = old_keys;
+    t->counts = old_counts;
+    return RG_ERR_FULL;
+  }
   int rc = table_alloc_tiles(t, new_tiles);
   if (rc) return rc;
   // bucket staging is sized per tile count: drop it, it is rebuilt on the next push
-  if (t->part_cursor) { cudaFree(t->part_cursor); t->part_cursor = nullptr; }
-  if (t->part_keys) { cudaFree(t->part_keys); t->part_keys = nullptr; t->part_cap = 0; }
+  drop_buckets(t);
   rc = rg_launch_rehash(t, old_keys, old_counts, old_slots);
   if (rc) return rc;
   RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -340,7 +387,34 @@ static int prepare_buckets(rg_table* t, uint64_t n_keys) {
   }
   t->bucket_cap = (uint32_t)(t->part_cap / t->n_tiles);
   RG_CUDA_OK(cudaMemsetAsync(t->part_cursor, 0, (uint64_t)t->n_tiles * sizeof(uint32_t), ctx->stream));
+  // two-level partition: the slabs of the groups (a peer-to-peer table owns fixed ones)
+  if (t->group_tiles > 1 && !t->p2p_block) {
+    const uint32_t n_groups = t->n_tiles / t->group_tiles;
+    const uint64_t gmean = n_keys / n_groups + 1;
+    uint64_t gcap = gmean + gmean / 4 + 4096;
+    gcap = (gcap + 3) & ~3ull;
+    if (!t->grp_cursor) RG_CUDA_OK(cudaMalloc(&t->grp_cursor, (uint64_t)n_groups * sizeof(uint32_t)));
+    if (t->grp_alloc_keys < gcap * n_groups) {
+      if (t->grp_keys) {
+        RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(t->grp_keys);
+        t->grp_keys = nullptr;
+      }
+      RG_CUDA_OK(cudaMalloc(&t->grp_keys, gcap * n_groups * 8 + 64));
+      t->grp_alloc_keys = gcap * n_groups;
+    }
+    t->grp_cap = (uint32_t)(t->grp_alloc_keys / n_groups);
+    RG_CUDA_OK(cudaMemsetAsync(t->grp_cursor, 0, (uint64_t)n_groups * sizeof(uint32_t), ctx->stream));
+  }
   return 0;
+}
+
+// after the level-1 launches of a push: (group slabs -> tile buckets,) then the tile inserts
+static int finish_tiled_push(rg_table* t) {
+  int rc = 0;
+  if (t->group_tiles > 1) rc = rg_launch_partition_groups(t);
+  if (rc == 0) rc = rg_launch_tile_insert(t);
+  return rc;
 }
 
 static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
@@ -364,7 +438,7 @@ static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, 
     if (rc) return rc;
     rc = rg_launch_partition(t, ep);
     if (rc) return rc;
-    rc = rg_launch_tile_insert(t);
+    rc = finish_tiled_push(t);
     if (rc) return rc;
   } else {
     rc = rg_launch_count_direct(t, ep);
@@ -414,11 +488,7 @@ rg_table* rg_count_begin(rg_ctx* ctx, int k, int canonical, uint64_t est_distinc
   t->canonical = canonical ? 1 : 0;
   t->mode = (mode == RG_MODE_AUTO) ? RG_MODE_TILED : mode;
   if (est_distinct == 0) est_distinct = 1ull << 24;
-  uint32_t n_tiles = tiles_for(est_distinct);
-  // tiled insert runs one CTA per tile: make the grid a whole number of waves over the SMs
-  if (t->mode == RG_MODE_TILED && n_tiles > (uint32_t)ctx->sm_count)
-    n_tiles = (n_tiles + ctx->sm_count - 1) / ctx->sm_count * ctx->sm_count;
-  if (table_alloc_tiles(t, n_tiles) != 0) {
+  if (table_alloc_tiles(t, tiles_for(est_distinct)) != 0) {
     delete t;
     return nullptr;
   }
@@ -441,6 +511,175 @@ int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts) {
   t->shard_parts = n_parts;
   t->n_tiles_global = t->n_tiles * n_parts;
   t->tile_first = t->n_tiles * part;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Peer-to-peer multi-GPU counting (one process per GPU, NVLink peer memory, no collective in the
+// data path): every GPU's level-1 partition pass sorts its reads into the groups of ALL shards and
+// writes each run straight into the OWNER's group slab (system-scope atomics reserve it), then
+// every GPU finishes its own groups locally (groups -> tiles -> tile inserts).
+//   rg_table_p2p_prepare : after rg_table_set_shard, before the first push; fixes the geometry and
+//                          allocates the exported block [cursors | status | spill | slabs]
+//   rg_table_p2p_export  : 64-byte CUDA IPC handle of that block (all-gather it between the ranks)
+//   rg_table_p2p_import  : attach rank r's block (r == own rank: local pointers)
+//   per sample: rg_count_p2p_begin (zero my cursors) -> barrier -> rg_count_p2p_scatter_dev ->
+//               barrier -> rg_count_p2p_finish
+// ---------------------------------------------------------------------------
+static void p2p_layout(const rg_table* t, uint64_t* off_status, uint64_t* off_spill, uint64_t* off_slabs,
+                       uint64_t* total) {
+  const uint64_t n_groups = t->n_tiles / t->group_tiles;
+  uint64_t o = ((n_groups * 4 + 255) / 256) * 256;
+  *off_status = o;
+  o += 256;
+  *off_spill = o;
+  o += ((t->p2p_spill_cap * 8 + 255) / 256) * 256;
+  *off_slabs = o;
+  o += n_groups * (uint64_t)t->grp_cap * 8 + 256;
+  *total = o;
+}
+static void p2p_pointers(const rg_table* t, void* base, uint32_t r, rg_table* into) {
+  uint64_t os, osp, osl, tot;
+  p2p_layout(t, &os, &osp, &osl, &tot);
+  char* b = static_cast<char*>(base);
+  into->peer_cursor[r] = reinterpret_cast<uint32_t*>(b);
+  into->peer_status[r] = reinterpret_cast<uint64_t*>(b + os);
+  into->peer_spill[r] = reinterpret_cast<uint64_t*>(b + osp);
+  into->peer_keys[r] = reinterpret_cast<uint64_t*>(b + osl);
+}
+
+int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_keys_per_push) {
+  if (!t || t->tiles_dirty || t->mode != RG_MODE_TILED || t->shard_parts > 8 || groups_per_shard == 0 ||
+      max_keys_per_push == 0 || t->p2p_block) {
+    rg_set_error("rg_table_p2p_prepare: needs an empty tiled table of at most 8 shards, once");
+    return RG_ERR_ARG;
+  }
+  rg_ctx* ctx = t->ctx;
+  if ((uint64_t)groups_per_shard * t->shard_parts > rg_partition_max_buckets()) {
+    rg_set_error("rg_table_p2p_prepare: too many groups for one partition pass");
+    return RG_ERR_ARG;
+  }
+  // re-shape the (empty) table for the group geometry
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t wanted = t->n_tiles;
+  cudaFree(t->keys);
+  cudaFree(t->counts);
+  t->keys = nullptr;
+  t->counts = nullptr;
+  drop_buckets(t);
+  t->p2p_groups = groups_per_shard;
+  int rc = table_alloc_tiles(t, wanted);
+  if (rc) return rc;
+  const uint64_t n_groups = t->n_tiles / t->group_tiles;
+  const uint64_t gmean = max_keys_per_push / n_groups + 1;
+  t->grp_cap = (uint32_t)((gmean + gmean / 2 + 4096 + 3) & ~3ull);
+  t->p2p_spill_cap = 1ull << 20;
+  t->p2p_max_keys = max_keys_per_push;
+  uint64_t os, osp, osl, tot;
+  p2p_layout(t, &os, &osp, &osl, &tot);
+  RG_CUDA_OK(cudaMalloc(&t->p2p_block, tot));
+  RG_CUDA_OK(cudaMemsetAsync(t->p2p_block, 0, osl, ctx->stream));
+  t->p2p_block_bytes = tot;
+  p2p_pointers(t, t->p2p_block, t->shard_part, t);
+  t->grp_cursor = t->peer_cursor[t->shard_part];
+  t->grp_keys = t->peer_keys[t->shard_part];
+  t->p2p_status = t->peer_status[t->shard_part];
+  t->p2p_spill = t->peer_spill[t->shard_part];
+  t->grp_alloc_keys = n_groups * (uint64_t)t->grp_cap;
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rg_table_p2p_export(rg_table* t, void* handle64) {
+  if (!t || !t->p2p_block || !handle64) return RG_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  RG_CUDA_OK(cudaIpcGetMemHandle(&h, t->p2p_block));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int rg_table_p2p_import(rg_table* t, uint32_t rank, const void* handle64) {
+  if (!t || !t->p2p_block || rank >= t->shard_parts || !handle64) return RG_ERR_ARG;
+  if (rank == t->shard_part) return 0;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  RG_CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  t->peer_mapped[rank] = base;
+  p2p_pointers(t, base, rank, t);
+  return 0;
+}
+
+int rg_count_p2p_begin(rg_table* t) {
+  if (!t || !t->p2p_block) return RG_ERR_ARG;
+  const uint64_t n_groups = t->n_tiles / t->group_tiles;
+  RG_CUDA_OK(cudaMemsetAsync(t->grp_cursor, 0, n_groups * 4, t->ctx->stream));
+  RG_CUDA_OK(cudaMemsetAsync(t->p2p_status, 0, 64, t->ctx->stream));
+  return 0;
+}
+
+int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride) {
+  if (!t || !t->p2p_block) return RG_ERR_ARG;
+  for (uint32_t r = 0; r < t->shard_parts; ++r)
+    if (!t->peer_keys[r]) {
+      rg_set_error("rg_count_p2p_scatter_dev: not every peer is imported");
+      return RG_ERR_ARG;
+    }
+  if (((uintptr_t)dev_stream & 15) != 0 || read_stride >= (1u << 31)) {
+    rg_set_error("count: device stream must be 16-byte aligned, read_stride < 2^31");
+    return RG_ERR_ARG;
+  }
+  ExtractParams ep;
+  ep.stream = dev_stream;
+  ep.n_bytes = n_bytes;
+  ep.brk = nullptr;
+  ep.read_stride = read_stride;
+  ep.k = t->k;
+  ep.canonical = t->canonical;
+  return rg_launch_partition_multi(t, ep);
+}
+
+// after every rank's scatter has completed (caller's barrier): my groups -> tiles -> inserts
+int rg_count_p2p_finish(rg_table* t) {
+  if (!t || !t->p2p_block) return RG_ERR_ARG;
+  rg_ctx* ctx = t->ctx;
+  // what the others could not place in my slabs comes through my exported spill list
+  uint64_t n_spill = 0;
+  RG_CUDA_OK(cudaMemcpyAsync(ctx->h_scratch, t->p2p_status, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  int rc = 0;
+  if (t->group_tiles > 1) {
+    // bucket slabs of my tiles, then groups -> tiles
+    rc = prepare_buckets(t, t->p2p_max_keys);
+    if (rc == 0) rc = rg_launch_partition_groups(t);
+    if (rc) return rc;
+    rc = rg_launch_tile_insert(t);
+  } else {
+    // a group IS a tile: the exported slabs are the tile buckets
+    uint64_t* pk = t->part_keys;
+    uint32_t* pc = t->part_cursor;
+    const uint32_t bc = t->bucket_cap;
+    t->part_keys = t->grp_keys;
+    t->part_cursor = t->grp_cursor;
+    t->bucket_cap = t->grp_cap;
+    rc = rg_launch_tile_insert(t);
+    t->part_keys = pk;
+    t->part_cursor = pc;
+    t->bucket_cap = bc;
+  }
+  if (rc) return rc;
+  t->tiles_dirty = true;
+  t->unchecked = true;
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  n_spill = ctx->h_scratch[0];
+  if (n_spill > t->p2p_spill_cap) {
+    rg_set_error("count: peer-to-peer spill list overflowed; raise max_keys_per_push");
+    return RG_ERR_FULL;
+  }
+  if (n_spill) {
+    rc = rg_launch_insert_keys(t, t->p2p_spill, n_spill, nullptr);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -482,7 +721,7 @@ int rg_count_push(rg_table* t, const char* host_stream, uint64_t n_bytes) {
     if (rc) return rc;
   }
   if (t->mode == RG_MODE_TILED) {
-    rc = rg_launch_tile_insert(t);
+    rc = finish_tiled_push(t);
     if (rc) return rc;
   }
   t->tiles_dirty = true;
@@ -533,7 +772,7 @@ int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_key
   if (t->mode == RG_MODE_TILED && n_keys >= (uint64_t)t->n_tiles * 64) {
     rc = prepare_buckets(t, n_keys);
     if (rc == 0) rc = rg_launch_partition_keys(t, dev_keys, n_keys);
-    if (rc == 0) rc = rg_launch_tile_insert(t);
+    if (rc == 0) rc = finish_tiled_push(t);
   } else {
     rc = rg_launch_insert_keys(t, dev_keys, n_keys, nullptr);
   }
@@ -567,6 +806,7 @@ int rg_table_trim(rg_table* t) {
   if (!t) return RG_ERR_ARG;
   RG_CUDA_OK(cudaStreamSynchronize(t->ctx->stream));
   if (t->part_keys) { cudaFree(t->part_keys); t->part_keys = nullptr; t->part_cap = 0; }
+  if (!t->p2p_block && t->grp_keys) { cudaFree(t->grp_keys); t->grp_keys = nullptr; t->grp_alloc_keys = 0; }
   if (t->stage) { cudaFree(t->stage); t->stage = nullptr; t->stage_bytes = 0; }
   if (t->brk) { cudaFree(t->brk); t->brk = nullptr; t->brk_words = 0; }
   if (t->d_offs) { cudaFree(t->d_offs); t->d_offs = nullptr; t->d_offs_cap = 0; }
@@ -597,6 +837,14 @@ void rg_table_free(rg_table* t) {
   cudaFree(t->spill);
   cudaFree(t->part_keys);
   cudaFree(t->part_cursor);
+  if (t->p2p_block) {
+    for (int i = 0; i < 8; ++i)
+      if (t->peer_mapped[i]) cudaIpcCloseMemHandle(t->peer_mapped[i]);
+    cudaFree(t->p2p_block);
+  } else {
+    cudaFree(t->grp_keys);
+    cudaFree(t->grp_cursor);
+  }
   cudaFree(t->stage);
   cudaFree(t->brk);
   cudaFree(t->d_offs);

@@ -190,7 +190,7 @@ __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_sr
 
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, const uint64_t* __restrict__ part_keys,
-                   const uint32_t* __restrict__ cursor, uint32_t bucket_cap, uint32_t n_tiles_global,
+                   const uint32_t* __restrict__ cursor, uint32_t bucket_cap, RgGeo geo,
                    int load_existing, uint64_t* status, uint64_t* spill, uint64_t spill_cap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
@@ -276,7 +276,7 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
       if (!have && my < n_rel) {
         key = ring[my & (TILE_RING_KEYS - 1)];
         uint32_t tile_unused;
-        rg_locate(key, n_tiles_global, tile_unused, slot);
+        rg_locate_in_group(key, geo, tile_unused, slot);
         probes = 0;
         have = key != RG_EMPTY;       // (pad slots of the partition runs are skipped)
       }
@@ -336,7 +336,7 @@ int rg_launch_tile_insert(rg_table* t) {
   {
     rg_launch_scope _ls(ctx, "tile_insert_kernel");
     tile_insert_kernel<<<t->n_tiles, TILE_THREADS, smem, ctx->stream>>>(t->keys, t->counts, t->part_keys, t->part_cursor,
-                                                                        t->bucket_cap, t->n_tiles_global,
+                                                                        t->bucket_cap, rg_view(t).geo,
                                                                         t->tiles_dirty ? 1 : 0, t->d_status, t->spill,
                                                                         t->spill_cap);
   }

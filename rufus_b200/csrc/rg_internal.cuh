@@ -16,9 +16,14 @@
 // One tile = 128 KiB of keys + 64 KiB of counts = 192 KiB: exactly what one CTA
 // stages in shared memory (227 KiB/SM on B200) in the tiled insert.
 //   h      = hash32(key)                  (lo * C1 + hi * C2 mod 2^32)
-//   p      = h * n_tiles_global           (64-bit product)
-//   tile   = p >> 32                      ("hash prefix": also the shard id of the multi-GPU partition)
-//   slot0  = low32(p) >> (32 - RG_TILE_BITS)   (the position of h inside its tile's hash range)
+//   p      = h * groups                   (64-bit product; groups = hash-prefix GROUPS over all shards)
+//   group  = p >> 32                      (the level-1 partition bucket; group / groups_per_shard = owning GPU)
+//   q      = low32(p) * group_tiles       (64-bit product; group_tiles = tiles per group, 1 for small tables)
+//   tile   = group * group_tiles + (q >> 32)
+//   slot0  = low32(q) >> (32 - RG_TILE_BITS)   (the position of h inside its tile's hash range)
+// With group_tiles == 1 a group IS a tile and one partition pass feeds the tile inserts; larger
+// tables (more tiles than the partition kernel can histogram in shared memory) use two passes:
+// stream -> groups, then group -> tiles.
 // ---------------------------------------------------------------------------
 #define RG_TILE_BITS 14
 #define RG_TILE_SLOTS (1u << RG_TILE_BITS)
@@ -41,6 +46,7 @@ struct rg_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
+  uint32_t force_groups = 0;   // RG_GROUPS_LOCAL (test knob): tiled tables use this many groups, i.e. the two-level partition
   // small pinned scratch for scalar read-backs
   uint64_t* h_scratch = nullptr;  // pinned, 64 u64
   uint64_t* d_scratch = nullptr;  // device, 64 u64
@@ -66,6 +72,7 @@ struct rg_table {
   uint32_t n_tiles = 0;         // tiles held by this table (this shard)
   uint32_t n_tiles_global = 0;  // n_tiles * n_parts
   uint32_t tile_first = 0;      // global id of local tile 0
+  uint32_t group_tiles = 1;     // tiles per hash-prefix group (level-2 fanout); n_tiles % group_tiles == 0
   uint32_t shard_part = 0, shard_parts = 1;
   uint64_t* keys = nullptr;     // [n_tiles * RG_TILE_SLOTS]
   uint32_t* counts = nullptr;
@@ -74,12 +81,30 @@ struct rg_table {
   uint64_t* spill = nullptr;    // keys that found their tile full
   uint64_t spill_cap = 0;
   bool tiles_dirty = false;     // table holds data (tiled insert must load tiles, not zero them)
+  uint32_t p2p_groups = 0;      // > 0: peer-to-peer multi-GPU counting with this many groups per shard
   bool unchecked = false;       // pushes were enqueued whose status words (spill / foreign) are not read back yet
   // tiled-mode staging
   uint64_t* part_keys = nullptr;     // bucketed keys
   uint64_t part_cap = 0;             // total key capacity
   uint32_t* part_cursor = nullptr;   // [n_tiles] fill of each bucket
   uint32_t bucket_cap = 0;
+  // two-level partition (group_tiles > 1) and peer-to-peer multi-GPU counting: slabs of the groups
+  uint64_t* grp_keys = nullptr;      // [n_groups_local][grp_cap]
+  uint32_t* grp_cursor = nullptr;    // [n_groups_local]
+  uint32_t grp_cap = 0;
+  uint64_t grp_alloc_keys = 0;       // keys allocated behind grp_keys
+  // peer-to-peer: one allocation [cursors | status | spill | slabs], exported with CUDA IPC
+  void* p2p_block = nullptr;
+  uint64_t p2p_block_bytes = 0;
+  uint64_t p2p_spill_cap = 0;
+  uint64_t p2p_max_keys = 0;         // keys one shard may receive per push (sizes the slabs)
+  uint64_t* p2p_status = nullptr;    // [0] = spill count of keys other GPUs could not place in a slab
+  uint64_t* p2p_spill = nullptr;
+  uint64_t* peer_keys[8] = {};
+  uint32_t* peer_cursor[8] = {};
+  uint64_t* peer_status[8] = {};
+  uint64_t* peer_spill[8] = {};
+  void* peer_mapped[8] = {};         // bases returned by cudaIpcOpenMemHandle (to close them)
   uint64_t* stage = nullptr;         // host->device staging for rg_count_push
   uint64_t stage_bytes = 0;
   uint32_t* brk = nullptr;           // read-start bitmap for offsets pushes
@@ -138,16 +163,33 @@ __host__ __device__ __forceinline__ uint32_t rg_hash32(uint64_t key) {
   return (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
 }
 
-// tile (global numbering) and home slot of a key
-__host__ __device__ __forceinline__ void rg_locate(uint64_t key, uint32_t n_tiles_global, uint32_t& tile,
-                                                   uint32_t& slot) {
-  const uint64_t p = (uint64_t)rg_hash32(key) * n_tiles_global;
-  tile = (uint32_t)(p >> 32);
-  slot = (uint32_t)p >> (32 - RG_TILE_BITS);
-}
+// table geometry as the kernels see it
+struct RgGeo {
+  uint32_t groups;        // hash-prefix groups over ALL shards (= n_tiles_global / group_tiles)
+  uint32_t group_tiles;   // tiles per group
+};
 
-__host__ __device__ __forceinline__ uint32_t rg_tile_of_key(uint64_t key, uint32_t n_tiles_global) {
-  return (uint32_t)(((uint64_t)rg_hash32(key) * n_tiles_global) >> 32);
+// level-1 bucket (hash-prefix group, global numbering) of a key
+__host__ __device__ __forceinline__ uint32_t rg_group_of_key(uint64_t key, uint32_t groups) {
+  return (uint32_t)(((uint64_t)rg_hash32(key) * groups) >> 32);
+}
+// kept for the callers that partition by shard only (n = number of shards)
+__host__ __device__ __forceinline__ uint32_t rg_tile_of_key(uint64_t key, uint32_t n) { return rg_group_of_key(key, n); }
+
+// tile (global numbering) and home slot of a key
+__host__ __device__ __forceinline__ void rg_locate(uint64_t key, RgGeo geo, uint32_t& tile, uint32_t& slot) {
+  const uint64_t p = (uint64_t)rg_hash32(key) * geo.groups;
+  const uint64_t q = (uint64_t)(uint32_t)p * geo.group_tiles;
+  tile = (uint32_t)(p >> 32) * geo.group_tiles + (uint32_t)(q >> 32);
+  slot = (uint32_t)q >> (32 - RG_TILE_BITS);
+}
+// tile inside its group and home slot (level-2 partition, tile insert)
+__host__ __device__ __forceinline__ void rg_locate_in_group(uint64_t key, RgGeo geo, uint32_t& tile_in_group,
+                                                            uint32_t& slot) {
+  const uint32_t r = rg_hash32(key) * geo.groups;            // low word of h * groups
+  const uint64_t q = (uint64_t)r * geo.group_tiles;
+  tile_in_group = (uint32_t)(q >> 32);
+  slot = (uint32_t)q >> (32 - RG_TILE_BITS);
 }
 
 // reverse complement of a jf key (first base in the MSBs of 2k bits)
@@ -170,8 +212,8 @@ struct TableView {
   uint64_t* keys;
   uint32_t* counts;
   uint32_t n_tiles;
-  uint32_t n_tiles_global;
   uint32_t tile_first;
+  RgGeo geo;
 };
 
 static inline TableView rg_view(const rg_table* t) {
@@ -179,15 +221,16 @@ static inline TableView rg_view(const rg_table* t) {
   v.keys = t->keys;
   v.counts = t->counts;
   v.n_tiles = t->n_tiles;
-  v.n_tiles_global = t->n_tiles_global;
   v.tile_first = t->tile_first;
+  v.geo.groups = t->n_tiles_global / t->group_tiles;
+  v.geo.group_tiles = t->group_tiles;
   return v;
 }
 
 // add `add` to key's counter in a global-memory table. Returns 0 ok, 1 tile full, 2 foreign shard.
 __device__ __forceinline__ int rg_table_add(const TableView& tv, uint64_t key, uint32_t add) {
   uint32_t tile, slot;
-  rg_locate(key, tv.n_tiles_global, tile, slot);
+  rg_locate(key, tv.geo, tile, slot);
   tile -= tv.tile_first;
   if (tile >= tv.n_tiles) return 2;
   const uint64_t base = (uint64_t)tile << RG_TILE_BITS;
@@ -207,7 +250,7 @@ __device__ __forceinline__ int rg_table_add(const TableView& tv, uint64_t key, u
 // count of key (0 if absent)
 __device__ __forceinline__ uint32_t rg_table_get(const TableView& tv, uint64_t key) {
   uint32_t tile, slot;
-  rg_locate(key, tv.n_tiles_global, tile, slot);
+  rg_locate(key, tv.geo, tile, slot);
   tile -= tv.tile_first;
   if (tile >= tv.n_tiles) return 0;
   const uint64_t base = (uint64_t)tile << RG_TILE_BITS;
@@ -238,6 +281,9 @@ int rg_table_finish(rg_table* t);
 int rg_launch_count_direct(rg_table* t, const ExtractParams& ep);
 int rg_launch_partition(rg_table* t, const ExtractParams& ep);   // into t->part_keys buckets
 int rg_launch_partition_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n);
+int rg_launch_partition_groups(rg_table* t);                      // level 2: group slabs -> tile buckets
+int rg_launch_partition_multi(rg_table* t, const ExtractParams& ep);   // level 1 into every GPU's group slabs
+uint32_t rg_partition_max_buckets();
 int rg_launch_tile_insert(rg_table* t);
 uint64_t rg_partition_pad_keys(uint32_t n_tiles, uint64_t n_units);                           // consume buckets
 int rg_launch_insert_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n, const uint32_t* dev_counts);

@@ -53,14 +53,32 @@ static size_t part_dynamic_smem(uint32_t n_tiles) {
   return (size_t)PART_K * 12 + (size_t)n_tiles * 8 + (size_t)((n_tiles + 31) / 32) * 4;
 }
 
+constexpr int PART_MAX_OWNERS = 8;
+
+// What one launch sorts into. A "bucket" is a hash-prefix GROUP (level 1: from the ASCII stream or a
+// key list) or a TILE inside one group (level 2: from the group slabs the level-1 pass filled).
 struct PartGeom {
-  uint32_t n_tiles_global, tile_first, n_tiles;
-  uint64_t* part_keys;
-  uint32_t* cursor;
-  uint32_t bucket_cap;
+  uint32_t n_buckets_global;   // level 1: groups over all shards (the multiplier of the hash)
+  uint32_t bucket_first;       // level 1: first bucket of this shard
+  uint32_t n_buckets;          // buckets sorted per super-chunk: level 1 local groups (MULTI: all groups), level 2 group_tiles
+  RgGeo geo;                   // level 2: locates the tile inside its group
+  uint64_t* out_keys;          // bucket slabs [n_buckets (x n_groups at level 2)][out_cap]
+  uint32_t* out_cursor;        // fill of every slab
+  uint32_t out_cap;
+  // level 2 input: the group slabs
+  const uint64_t* in_keys;
+  const uint32_t* in_cursor;
+  uint32_t in_cap, n_groups;
+  // overflow / foreign keys
   uint64_t* status;
   uint64_t* spill;
   uint64_t spill_cap;
+  // MULTI: the slabs of bucket b live on GPU b / buckets_per_owner (peer memory), same layout everywhere
+  uint32_t buckets_per_owner;
+  uint64_t* owner_keys[PART_MAX_OWNERS];
+  uint32_t* owner_cursor[PART_MAX_OWNERS];
+  uint64_t* owner_status[PART_MAX_OWNERS];
+  uint64_t* owner_spill[PART_MAX_OWNERS];
 };
 
 // exclusive scan of v over the block (blockDim.x multiple of 32); returns the prefix, total via *total
@@ -237,39 +255,47 @@ __device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, 
   }
 }
 
-// FROM_KEYS = false: windows of the ASCII stream; true: an already extracted key list.
-// PART_K keys are counting-sorted by tile in shared memory per super-chunk:
+// SRC: 0 = windows of the ASCII stream, 1 = an already extracted key list, 2 = the group slabs of a
+// level-1 pass (each CTA takes whole groups and sorts their keys by tile inside the group).
+// PART_K keys are counting-sorted by bucket in shared memory per super-chunk:
 //   1. keys -> ukeys[] (transposed: key w of thread t at w*1024+t, conflict-free) and ONE shared
-//      atomic per key on the tile histogram whose return value is the key's rank inside its run;
-//      (tile, rank) stays in a register
-//   2. block scan -> local offsets; one global atomicAdd per non-empty tile reserves a run rounded
-//      up to 4 keys (a full 32-byte sector); its latency hides behind step 3
-//   3. entry (tile, index of the key in ukeys) is scattered to its sorted position
-//   4. copy-out in sorted order: consecutive threads write consecutive keys of a run, pad slots
-//      get RG_EMPTY (the tile insert skips them), so every global write is a fully covered sector.
+//      atomic per key on the bucket histogram whose return value is the key's rank inside its run;
+//      (bucket, rank) stays in a register
+//   2. block scan -> local offsets; one global atomicAdd per non-empty bucket reserves the run; its
+//      latency hides behind step 3
+//   3. entry (bucket, index of the key in ukeys) is scattered to its sorted position
+//   4. copy-out in sorted order: consecutive threads write consecutive keys of a run
 // The ASCII of the next super-chunk is prefetched into registers during steps 1-2.
 // SHARDED: the table holds one hash-prefix shard (multi-GPU), so keys of other shards are counted as foreign.
-template <bool FROM_KEYS, bool SHARDED>
+// MULTI:   level 1 over ALL shards: runs are written straight into the owner GPU's slabs over NVLink
+//          peer memory, reserved with system-scope atomics on the owner's cursors (no collective).
+template <int SRC, bool SHARDED, bool MULTI>
 __global__ void __launch_bounds__(PART_THREADS, PART_CTAS)
-partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, uint64_t n_in, PartGeom g) {
+partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_arg, uint64_t n_in_arg, PartGeom g) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ PartStage sm;
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t scan_total;
   __shared__ uint32_t any_overflow;
+  // MULTI: the owners' base pointers, indexed per bucket / per key (a dynamically indexed kernel
+  // parameter array would be copied to local memory)
+  __shared__ uint64_t* s_owner_keys[PART_MAX_OWNERS];
+  __shared__ uint32_t* s_owner_cursor[PART_MAX_OWNERS];
+  if (MULTI && threadIdx.x < PART_MAX_OWNERS) {
+    s_owner_keys[threadIdx.x] = g.owner_keys[threadIdx.x];
+    s_owner_cursor[threadIdx.x] = g.owner_cursor[threadIdx.x];
+  }
   uint64_t* ukeys = reinterpret_cast<uint64_t*>(dyn);                        // [PART_K]
-  uint32_t* sorted = reinterpret_cast<uint32_t*>(dyn + (size_t)PART_K * 8);  // [PART_K] (tile << 16) | key index
-  uint32_t* hist = sorted + PART_K;       // [n_tiles] run length, then (step 2) offset of the run in part_keys - loff
-  uint32_t* loff = hist + g.n_tiles;      // [n_tiles] local offset of the run
-  uint32_t* ovf_bits = loff + g.n_tiles;  // [(n_tiles+31)/32] tiles whose bucket overflowed in this super-chunk
-  const uint32_t per_thread = (g.n_tiles + PART_THREADS - 1) / PART_THREADS;
-  const uint32_t ovf_words = (g.n_tiles + 31) >> 5;
+  uint32_t* sorted = reinterpret_cast<uint32_t*>(dyn + (size_t)PART_K * 8);  // [PART_K] (bucket << 16) | key index
+  uint32_t* hist = sorted + PART_K;       // [n_buckets] run length, then (step 3b) offset of the run in its slab array - loff
+  uint32_t* loff = hist + g.n_buckets;    // [n_buckets] local offset of the run
+  uint32_t* ovf_bits = loff + g.n_buckets;  // [(n_buckets+31)/32] buckets whose slab overflowed in this super-chunk
+  const uint32_t per_thread = (g.n_buckets + PART_THREADS - 1) / PART_THREADS;
+  const uint32_t ovf_words = (g.n_buckets + 31) >> 5;
 
-  const uint64_t n_units = FROM_KEYS ? n_in : ep.n_bytes;
-  const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
   PartPrefetch pf;
   uint32_t r_next = 0, r_step = 0;   // (start of the next super-chunk to prefetch) % read_stride, and its increment
-  if (!FROM_KEYS && ep.read_stride != 0) {
+  if (SRC == 0 && ep.read_stride != 0) {
     r_next = (uint32_t)(((uint64_t)blockIdx.x * PART_K) % ep.read_stride);
     r_step = (uint32_t)(((uint64_t)gridDim.x * PART_K) % ep.read_stride);
   }
@@ -277,40 +303,56 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     r_next += r_step;
     if (r_next >= ep.read_stride) r_next -= ep.read_stride;
   };
-  if (!FROM_KEYS && blockIdx.x < n_super) {
+  if (SRC == 0 && (uint64_t)blockIdx.x * PART_K < ep.n_bytes) {
     part_prefetch(pf, ep, (uint64_t)blockIdx.x * PART_K, r_next);
     advance_r();
     part_stage_store(sm, pf);
   }
   if (threadIdx.x == 0) any_overflow = 0;
   for (uint32_t i = threadIdx.x; i < ovf_words; i += PART_THREADS) ovf_bits[i] = 0;
-  for (uint64_t sc = blockIdx.x; sc < n_super; sc += gridDim.x) {
+
+  // level 2: this CTA takes groups blockIdx.x, +gridDim.x, ...; otherwise one pass over the whole input
+  const uint32_t n_outer = SRC == 2 ? g.n_groups : 1u;
+  for (uint32_t og = SRC == 2 ? blockIdx.x : 0u; og < n_outer; og += SRC == 2 ? gridDim.x : 1u) {
+  const uint64_t* in_keys = SRC == 2 ? g.in_keys + (uint64_t)og * g.in_cap : in_keys_arg;
+  const uint64_t n_in = SRC == 2 ? (uint64_t)min(g.in_cursor[og], g.in_cap) : n_in_arg;
+  const uint32_t slab0 = SRC == 2 ? og * g.n_buckets : 0u;      // first output slab of this group
+  const uint64_t n_units = SRC == 0 ? ep.n_bytes : n_in;
+  const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
+  const uint64_t sc_step = SRC == 2 ? 1u : gridDim.x;
+  for (uint64_t sc = SRC == 2 ? 0u : blockIdx.x; sc < n_super; sc += sc_step) {
     const uint64_t s0 = sc * PART_K;
-    for (uint32_t i = threadIdx.x; i < g.n_tiles; i += PART_THREADS) hist[i] = 0;
+    for (uint32_t i = threadIdx.x; i < g.n_buckets; i += PART_THREADS) hist[i] = 0;
     const bool more = sc + gridDim.x < n_super;
-    if (!FROM_KEYS && more) {
+    if (SRC == 0 && more) {
       part_prefetch(pf, ep, (sc + gridDim.x) * PART_K, r_next);
       advance_r();
     }
     __syncthreads();
-    // ---- 1. keys -> ukeys, rank inside the tile's run
-    uint32_t meta[PART_R];           // (tile << 16) | rank, or ~0 for a window without a k-mer
+    // ---- 1. keys -> ukeys, rank inside the bucket's run
+    uint32_t meta[PART_R];           // (bucket << 16) | rank, or ~0 for a window without a k-mer
     uint32_t foreign = 0;
     // branch-free: the hash is computed for every window, only the shared atomic is predicated
     auto take = [&](int w, uint64_t key, bool ok) {
-      uint32_t tile = rg_tile_of_key(key, g.n_tiles_global);
-      if (SHARDED) {
-        tile -= g.tile_first;
-        const bool mine = tile < g.n_tiles;
-        foreign += (ok && !mine) ? 1u : 0u;
-        ok = ok && mine;
+      uint32_t b;
+      if (SRC == 2) {
+        uint32_t slot_unused;
+        rg_locate_in_group(key, g.geo, b, slot_unused);
+      } else {
+        b = rg_group_of_key(key, g.n_buckets_global);
+        if (SHARDED) {
+          b -= g.bucket_first;
+          const bool mine = b < g.n_buckets;
+          foreign += (ok && !mine) ? 1u : 0u;
+          ok = ok && mine;
+        }
       }
       uint32_t m = 0xFFFFFFFFu;
-      if (ok) m = tile * 65536u + atomicAdd(&hist[tile], 1u);
+      if (ok) m = b * 65536u + atomicAdd(&hist[b], 1u);
       meta[w] = m;
       ukeys[w * PART_THREADS + threadIdx.x] = key;
     };
-    if (FROM_KEYS) {
+    if (SRC != 0) {
       uint64_t kk[PART_R];
 #pragma unroll
       for (int w = 0; w < PART_R; ++w) {
@@ -325,14 +367,14 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     if (SHARDED && foreign) atomicAdd((unsigned long long*)&g.status[1], (unsigned long long)foreign);
     __syncthreads();
     // ---- 2. local offsets (exclusive scan of the run lengths); the global run reservations (one
-    // atomicAdd per non-empty tile, run padded to 4 keys) are only ISSUED here: their results are
-    // consumed after step 3, which hides the round trip to L2
+    // atomicAdd per non-empty bucket) are only ISSUED here: their results are consumed after
+    // step 3, which hides the round trip to L2 (or to the peer GPU)
     const uint32_t t0 = threadIdx.x * per_thread;
     uint32_t cnt[PART_TILES_PER_THREAD], gb[PART_TILES_PER_THREAD];
     uint32_t sum = 0;
 #pragma unroll
     for (int j = 0; j < PART_TILES_PER_THREAD; ++j) {
-      cnt[j] = ((uint32_t)j < per_thread && t0 + j < g.n_tiles) ? hist[t0 + j] : 0u;
+      cnt[j] = ((uint32_t)j < per_thread && t0 + j < g.n_buckets) ? hist[t0 + j] : 0u;
       sum += cnt[j];
     }
     uint32_t run = block_exclusive_scan(sum, warp_sums, &scan_total);
@@ -341,39 +383,51 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     for (int j = 0; j < PART_TILES_PER_THREAD; ++j) {
       gb[j] = 0;
       if (cnt[j]) {
-        loff[t0 + j] = run;
-        gb[j] = atomicAdd(g.cursor + t0 + j, (cnt[j] + PART_PAD) & ~PART_PAD);
+        const uint32_t b = t0 + j;
+        const uint32_t want = (cnt[j] + PART_PAD) & ~PART_PAD;
+        if (MULTI) {
+          const uint32_t o = b / g.buckets_per_owner;
+          loff[b] = run | (o << 16);                 // the owner rides in the high half (run < 2^14)
+          gb[j] = atomicAdd_system(s_owner_cursor[o] + (b - o * g.buckets_per_owner), want);
+        } else {
+          loff[b] = run;
+          gb[j] = atomicAdd(g.out_cursor + slab0 + b, want);
+        }
         run += cnt[j];
       }
     }
     // the next super-chunk's bases are in registers by now; the stage buffers are free since step 1 ended
-    if (!FROM_KEYS && more) part_stage_store(sm, pf);
+    if (SRC == 0 && more) part_stage_store(sm, pf);
     __syncthreads();
-    // ---- 3. (tile, key index) entries in tile order
+    // ---- 3. (bucket, key index) entries in bucket order
 #pragma unroll
     for (int w = 0; w < PART_R; ++w) {
       const uint32_t m = meta[w];
-      const uint32_t tile = m >> 16;
-      if (m != 0xFFFFFFFFu) sorted[loff[tile] + (m & 0xFFFFu)] = tile * 65536u + (w * PART_THREADS + threadIdx.x);
+      const uint32_t b = m >> 16;
+      if (m != 0xFFFFFFFFu)
+        sorted[(loff[b] & 0xFFFFu) + (m & 0xFFFFu)] = b * 65536u + (w * PART_THREADS + threadIdx.x);
     }
-    // ---- 3b. the reservations have landed: pad slots, sorted index -> part_keys index (into hist[])
+    // ---- 3b. the reservations have landed: pad slots, sorted index -> slab-array index (into hist[])
     run = run0;
 #pragma unroll
     for (int j = 0; j < PART_TILES_PER_THREAD; ++j) {
       if (cnt[j]) {
-        const uint32_t t = t0 + j;
+        const uint32_t b = t0 + j;
         const uint32_t padded = (cnt[j] + PART_PAD) & ~PART_PAD;
-        const uint32_t at = t * g.bucket_cap + gb[j];                // index of the run in part_keys
-        if (gb[j] + padded <= g.bucket_cap) {
+        const uint32_t o = MULTI ? b / g.buckets_per_owner : 0u;
+        const uint32_t slab = MULTI ? b - o * g.buckets_per_owner : slab0 + b;   // slab index inside its owner's array
+        uint64_t* base = MULTI ? s_owner_keys[o] : g.out_keys;
+        const uint32_t at = slab * g.out_cap + gb[j];                            // index of the run in the slab array
+        if (gb[j] + padded <= g.out_cap) {
 #pragma unroll
-          for (uint32_t q = 1; q <= PART_PAD; ++q)                            // at most PART_PAD pad slots
-            if (cnt[j] + q - 1 < padded) g.part_keys[at + padded - q] = RG_EMPTY;
-          hist[t] = at - run;
+          for (uint32_t q = 1; q <= PART_PAD; ++q)                               // at most PART_PAD pad slots
+            if (cnt[j] + q - 1 < padded) base[at + padded - q] = RG_EMPTY;
+          hist[b] = at - run;
         } else {
-          // bucket overflow (heavy hitters): this run goes to the spill list (step 4); what it
+          // slab overflow (heavy hitters): this run goes to the spill list (step 4); what it
           // reserved below the capacity is neutralised with RG_EMPTY
-          for (uint32_t q = gb[j]; q < g.bucket_cap; ++q) g.part_keys[(uint64_t)t * g.bucket_cap + q] = RG_EMPTY;
-          atomicOr(&ovf_bits[t >> 5], 1u << (t & 31));
+          for (uint32_t q = gb[j]; q < g.out_cap; ++q) base[(uint64_t)slab * g.out_cap + q] = RG_EMPTY;
+          atomicOr(&ovf_bits[b >> 5], 1u << (b & 31));
           any_overflow = 1;
         }
         run += cnt[j];
@@ -387,15 +441,22 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
 #pragma unroll 4
       for (uint32_t i = threadIdx.x; i < total; i += PART_THREADS) {
         const uint32_t e = sorted[i];
-        g.part_keys[hist[e >> 16] + i] = ukeys[e & 0xFFFFu];
+        const uint32_t b = e >> 16;
+        uint64_t* base = MULTI ? s_owner_keys[loff[b] >> 16] : g.out_keys;
+        base[hist[b] + i] = ukeys[e & 0xFFFFu];
       }
     } else {
       for (uint32_t i = threadIdx.x; i < total; i += PART_THREADS) {
         const uint32_t e = sorted[i];
-        const uint32_t tile = e >> 16;
+        const uint32_t b = e >> 16;
         const uint64_t key = ukeys[e & 0xFFFFu];
-        if (!((ovf_bits[tile >> 5] >> (tile & 31)) & 1u)) {
-          g.part_keys[hist[tile] + i] = key;
+        const uint32_t o = MULTI ? loff[b] >> 16 : 0u;
+        if (!((ovf_bits[b >> 5] >> (b & 31)) & 1u)) {
+          uint64_t* base = MULTI ? s_owner_keys[o] : g.out_keys;
+          base[hist[b] + i] = key;
+        } else if (MULTI) {
+          const uint64_t sp = atomicAdd_system((unsigned long long*)&g.owner_status[o][0], 1ull);
+          if (sp < g.spill_cap) g.owner_spill[o][sp] = key;
         } else {
           const uint64_t sp = atomicAdd((unsigned long long*)&g.status[0], 1ull);
           if (sp < g.spill_cap) g.spill[sp] = key;
@@ -407,6 +468,7 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys, 
     }
     __syncthreads();
   }
+  }
 }
 
 // Fallback for tables with more tiles than the sorted kernel can histogram in shared memory:
@@ -417,14 +479,14 @@ partition_scatter_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys,
   using Stage = StageT<256, 16>;
   __shared__ Stage sm;
   auto put = [&](uint64_t key) {
-    const uint32_t tile = rg_tile_of_key(key, g.n_tiles_global) - g.tile_first;
-    if (tile >= g.n_tiles) {
+    const uint32_t tile = rg_group_of_key(key, g.n_buckets_global) - g.bucket_first;
+    if (tile >= g.n_buckets) {
       atomicAdd((unsigned long long*)&g.status[1], 1ull);
       return;
     }
-    const uint32_t at = atomicAdd(g.cursor + tile, 1u);
-    if (at < g.bucket_cap) {
-      g.part_keys[(uint64_t)tile * g.bucket_cap + at] = key;
+    const uint32_t at = atomicAdd(g.out_cursor + tile, 1u);
+    if (at < g.out_cap) {
+      g.out_keys[(uint64_t)tile * g.out_cap + at] = key;
     } else {
       const uint64_t sp = atomicAdd((unsigned long long*)&g.status[0], 1ull);
       if (sp < g.spill_cap) g.spill[sp] = key;
@@ -446,53 +508,68 @@ partition_scatter_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys,
   }
 }
 
-// does the sorted kernel's per-tile state fit shared memory for this tile count? (else: scatter fallback)
-static bool part_sorted_fits(uint32_t n_tiles) {
-  return n_tiles <= PART_TILES_PER_THREAD * PART_THREADS && part_dynamic_smem(n_tiles) + part_static_smem() <= PART_SMEM_LIMIT;
+// does the sorted kernel's per-bucket state fit shared memory for this bucket count?
+static bool part_sorted_fits(uint32_t n_buckets) {
+  return n_buckets <= PART_TILES_PER_THREAD * PART_THREADS && n_buckets < 65536 &&
+         part_dynamic_smem(n_buckets) + part_static_smem() <= PART_SMEM_LIMIT;
+}
+// the largest bucket count one sorted pass can take (level-1 fanout limit)
+uint32_t rg_partition_max_buckets() {
+  uint32_t n = PART_TILES_PER_THREAD * PART_THREADS;
+  while (n > 1 && !part_sorted_fits(n)) --n;
+  return n;
 }
 
-// upper bound on the pad keys one bucket can receive in a push of n_units windows/keys:
-// up to 3 per (super-chunk, bucket) run
-uint64_t rg_partition_pad_keys(uint32_t n_tiles, uint64_t n_units) {
-  if (!part_sorted_fits(n_tiles)) return 0;
-  return 3 * ((n_units + PART_K - 1) / PART_K);
+// upper bound on the pad keys one bucket can receive in a push of n_units windows/keys
+uint64_t rg_partition_pad_keys(uint32_t n_buckets, uint64_t n_units) {
+  if (!part_sorted_fits(n_buckets)) return 0;
+  return (uint64_t)PART_PAD * ((n_units + PART_K - 1) / PART_K);
 }
 
-template <bool FROM_KEYS>
+template <int SRC, bool MULTI>
 static int launch_sorted(rg_ctx* ctx, const char* name, const ExtractParams& ep, const uint64_t* keys, uint64_t n_keys,
-                         const PartGeom& g, uint64_t n_units) {
-  const size_t smem = part_dynamic_smem(g.n_tiles);
-  const bool sharded = g.n_tiles_global != g.n_tiles;
-  auto kern = sharded ? partition_sorted_kernel<FROM_KEYS, true> : partition_sorted_kernel<FROM_KEYS, false>;
+                         const PartGeom& g, uint64_t n_work, bool sharded) {
+  const size_t smem = part_dynamic_smem(g.n_buckets);
+  auto kern = sharded ? partition_sorted_kernel<SRC, true, MULTI> : partition_sorted_kernel<SRC, false, MULTI>;
   RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
   unsigned grid = rg_grid(ctx, PART_CTAS);
-  if (n_super < grid) grid = (unsigned)n_super;
+  if (n_work < grid) grid = (unsigned)n_work;
   rg_launch_scope _ls(ctx, name);
   kern<<<grid, PART_THREADS, smem, ctx->stream>>>(ep, keys, n_keys, g);
   return 0;
 }
 
-template <bool FROM_KEYS>
-static int launch_partition(rg_table* t, const ExtractParams& ep, const uint64_t* keys, uint64_t n_keys) {
-  rg_ctx* ctx = t->ctx;
-  PartGeom g;
-  g.n_tiles_global = t->n_tiles_global;
-  g.tile_first = t->tile_first;
-  g.n_tiles = t->n_tiles;
-  g.part_keys = t->part_keys;
-  g.cursor = t->part_cursor;
-  g.bucket_cap = t->bucket_cap;
+static void fill_common(PartGeom& g, rg_table* t) {
+  memset(&g, 0, sizeof(g));
+  g.geo.groups = t->n_tiles_global / t->group_tiles;
+  g.geo.group_tiles = t->group_tiles;
   g.status = t->d_status;
   g.spill = t->spill;
   g.spill_cap = t->spill_cap;
+}
+
+// level 1: stream / key list -> the table's groups (group_tiles == 1: straight into the tile buckets)
+template <bool FROM_KEYS>
+static int launch_partition(rg_table* t, const ExtractParams& ep, const uint64_t* keys, uint64_t n_keys) {
+  rg_ctx* ctx = t->ctx;
   const uint64_t n_units = FROM_KEYS ? n_keys : ep.n_bytes;
   if (n_units == 0) return 0;
+  PartGeom g;
+  fill_common(g, t);
+  const bool two_level = t->group_tiles > 1;
+  g.n_buckets_global = g.geo.groups;
+  g.n_buckets = t->n_tiles / t->group_tiles;
+  g.bucket_first = t->tile_first / t->group_tiles;
+  g.out_keys = two_level ? t->grp_keys : t->part_keys;
+  g.out_cursor = two_level ? t->grp_cursor : t->part_cursor;
+  g.out_cap = two_level ? t->grp_cap : t->bucket_cap;
+  const bool sharded = g.n_buckets_global != g.n_buckets;
   const char* name = FROM_KEYS ? "partition_keys_kernel" : "partition_kernel";
   int rc = 0;
-  if (part_sorted_fits(t->n_tiles) && (uint64_t)t->n_tiles * t->bucket_cap < (1ull << 32)) {
-    rc = launch_sorted<FROM_KEYS>(ctx, name, ep, keys, n_keys, g, n_units);
+  if (part_sorted_fits(g.n_buckets) && (uint64_t)g.n_buckets * g.out_cap < (1ull << 32)) {
+    const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
+    rc = launch_sorted<FROM_KEYS ? 1 : 0, false>(ctx, name, ep, keys, n_keys, g, n_super, sharded);
   } else {
     rg_launch_scope _ls(ctx, name);
     partition_scatter_kernel<FROM_KEYS><<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(ep, keys, n_keys, g);
@@ -507,4 +584,57 @@ int rg_launch_partition(rg_table* t, const ExtractParams& ep) { return launch_pa
 int rg_launch_partition_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n) {
   ExtractParams ep = {};
   return launch_partition<true>(t, ep, dev_keys, n);
+}
+
+// level 2: the group slabs -> the tile buckets of every group
+int rg_launch_partition_groups(rg_table* t) {
+  rg_ctx* ctx = t->ctx;
+  PartGeom g;
+  fill_common(g, t);
+  g.n_buckets = t->group_tiles;
+  g.n_groups = t->n_tiles / t->group_tiles;
+  g.in_keys = t->grp_keys;
+  g.in_cursor = t->grp_cursor;
+  g.in_cap = t->grp_cap;
+  g.out_keys = t->part_keys;
+  g.out_cursor = t->part_cursor;
+  g.out_cap = t->bucket_cap;
+  if (!part_sorted_fits(g.n_buckets) || (uint64_t)t->n_tiles * t->bucket_cap >= (1ull << 32)) {
+    rg_set_error("partition: group geometry out of range");
+    return RG_ERR_ARG;
+  }
+  ExtractParams ep = {};
+  int rc = launch_sorted<2, false>(ctx, "partition_groups_kernel", ep, nullptr, 0, g, g.n_groups, false);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// level 1 over ALL shards, straight into the owners' group slabs (peer memory)
+int rg_launch_partition_multi(rg_table* t, const ExtractParams& ep) {
+  rg_ctx* ctx = t->ctx;
+  if (ep.n_bytes == 0) return 0;
+  PartGeom g;
+  fill_common(g, t);
+  g.n_buckets_global = g.geo.groups;
+  g.n_buckets = g.geo.groups;
+  g.bucket_first = 0;
+  g.buckets_per_owner = t->n_tiles / t->group_tiles;
+  g.out_cap = t->grp_cap;
+  g.spill_cap = t->p2p_spill_cap;
+  for (uint32_t o = 0; o < t->shard_parts; ++o) {
+    g.owner_keys[o] = t->peer_keys[o];
+    g.owner_cursor[o] = t->peer_cursor[o];
+    g.owner_status[o] = t->peer_status[o];
+    g.owner_spill[o] = t->peer_spill[o];
+  }
+  if (!part_sorted_fits(g.n_buckets) || (uint64_t)g.buckets_per_owner * g.out_cap >= (1ull << 32)) {
+    rg_set_error("partition: too many groups for the peer-to-peer partition");
+    return RG_ERR_ARG;
+  }
+  const uint64_t n_super = (ep.n_bytes + PART_K - 1) / PART_K;
+  int rc = launch_sorted<0, true>(ctx, "partition_p2p_kernel", ep, nullptr, 0, g, n_super, false);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaGetLastError());
+  return 0;
 }

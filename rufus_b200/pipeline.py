@@ -77,7 +77,8 @@ class DevicePipeline:
 
     def __init__(self, ctx: api.Context, k: int, streams, subject_pairs, read_len: int, est_distinct: int,
                  min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
-                 mode: int = api.MODE_TILED, rank: int = 0, world: int = 1, max_mutant: int = 1 << 22):
+                 mode: int = api.MODE_TILED, rank: int = 0, world: int = 1, max_mutant: int = 1 << 22,
+                 exchange: str = "p2p", groups_per_shard: int = 37):
         import torch
 
         self.torch = torch
@@ -95,12 +96,38 @@ class DevicePipeline:
         self.hits1 = torch.empty(self.n_pairs, dtype=torch.int32, device=dev)
         self.hits2 = torch.empty(self.n_pairs, dtype=torch.int32, device=dev)
         self.keep = torch.empty(self.n_pairs, dtype=torch.uint8, device=dev)
-        if world > 1:
+        self.exchange = exchange if world > 1 else "none"
+        if self.exchange == "p2p":
+            # peer-to-peer: every rank's partition pass writes straight into the owners' group slabs
+            # (CUDA IPC mappings of one exported block per table); no collective in the data path
+            import torch.distributed as dist
+            L = api.lib()
+            self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            n_keys = max(int(s.numel()) for s in streams)      # weak scaling: a shard receives ~ what it sends
+            for t in self.tables:
+                api._check(L.rg_table_p2p_prepare(t.h, groups_per_shard, int(n_keys * 1.15) + (1 << 20)),
+                           "rg_table_p2p_prepare")
+                h = np.zeros(64, np.uint8)
+                api._check(L.rg_table_p2p_export(t.h, api._ptr(h)), "rg_table_p2p_export")
+                mine = torch.from_numpy(h).to(dev)
+                allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+                dist.all_gather(allh, mine)
+                for r in range(world):
+                    hr = np.ascontiguousarray(allh[r].cpu().numpy())
+                    api._check(L.rg_table_p2p_import(t.h, r, api._ptr(hr)), "rg_table_p2p_import")
+            dist.barrier()
+        elif world > 1:
             # one send buffer per sample: the all-to-all of sample i runs (NCCL's stream) while the
             # extraction of sample i+1 fills the next buffer
             self.part_keys = [torch.empty(int(s.numel()), dtype=torch.int64, device=dev) for s in streams]
             self.part_offs = torch.empty(world + 1, dtype=torch.int64, device=dev)
         self.last = {}
+
+    def stream_barrier(self):
+        """all ranks' kernels enqueued so far have completed before anything enqueued after it starts
+        (a 4-byte all-reduce on the compute stream; the host does not wait)"""
+        import torch.distributed as dist
+        dist.all_reduce(self.flag)
 
     def extract_and_send(self, i: int):
         """world > 1: extract + bucket sample i by owner rank, start its all-to-all (asynchronous)."""
@@ -123,6 +150,16 @@ class DevicePipeline:
         if self.world == 1:
             for t, s in zip(self.tables, self.streams):
                 t.push_dev(s, s.numel(), self.read_len)   # enqueued only: no host synchronisation between the samples
+        elif self.exchange == "p2p":
+            for t in self.tables:
+                api._check(L.rg_count_p2p_begin(t.h), "rg_count_p2p_begin")       # zero my slab cursors
+            self.stream_barrier()
+            for t, s in zip(self.tables, self.streams):                          # all samples: scatter to the owners
+                api._check(L.rg_count_p2p_scatter_dev(t.h, api._ptr(s), s.numel(), self.read_len),
+                           "rg_count_p2p_scatter_dev")
+            self.stream_barrier()
+            for t in self.tables:                                                # my groups -> tiles -> inserts
+                api._check(L.rg_count_p2p_finish(t.h), "rg_count_p2p_finish")
         else:
             # software pipeline: exchange of sample i overlaps extraction of sample i+1 and insertion of sample i-1
             inflight = self.extract_and_send(0)

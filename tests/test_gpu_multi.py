@@ -11,7 +11,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_two_gpu_sharded_pipeline_matches_oracle(tmp_path):
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_sharded_pipeline_matches_oracle(tmp_path, exchange):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -19,7 +20,7 @@ def test_two_gpu_sharded_pipeline_matches_oracle(tmp_path):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    env = dict(os.environ, RG_TMP=str(tmp_path))
+    env = dict(os.environ, RG_TMP=str(tmp_path), RG_EXCHANGE=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tools", "multigpu_check.py")], env=env, capture_output=True, text=True,

@@ -178,3 +178,32 @@ def test_from_pairs_roundtrip(ctx):
     assert np.array_equal(t.query(keys[:1000]), counts[:1000])
     assert t.query(np.array([(1 << 50) - 1 - int(keys[0])], np.uint64) + np.uint64(0)).size == 1
     t.free()
+
+
+def test_two_level_partition_matches_single_level(monkeypatch):
+    """Tables with more tiles than one sorted partition pass can histogram use two passes (stream ->
+    hash-prefix groups -> tiles). RG_GROUPS_LOCAL forces that geometry on a small table: same dump,
+    same histogram as the oracle, for the device-stream, host-stream and offsets entry points."""
+    monkeypatch.setenv("RG_GROUPS_LOCAL", "5")
+    c = api.Context(0)
+    try:
+        trio, _ = synth.make_trio(23, 200_000, 30_000)
+        s1, _, s2, _ = trio["Child"]
+        both = np.concatenate([s1, s2])
+        offs = np.arange(both.shape[0] + 1, dtype=np.uint64) * 150
+        okeys, ocounts = oracle.count(both.reshape(-1), offs, 25, True, 1)
+        t = api.KmerTable.count(c, both, offs, 25, True, est_distinct=3_000_000, mode=api.MODE_TILED)
+        keys, counts = t.dump(min_count=1)
+        assert np.array_equal(keys, okeys) and np.array_equal(counts, ocounts)
+        t.free()
+        # host stream entry point (pieces + halo) on the same geometry, twice into the same table
+        t = api.KmerTable(c, 25, True, 3_000_000, api.MODE_TILED)
+        stream = np.concatenate([both, np.full((both.shape[0], 1), 10, np.uint8)], axis=1).reshape(-1)
+        t.push_stream(stream)
+        t.push_stream(stream)
+        t.end()
+        keys, counts = t.dump(min_count=1)
+        assert np.array_equal(keys, okeys) and np.array_equal(counts, 2 * ocounts)
+        t.free()
+    finally:
+        c.close()

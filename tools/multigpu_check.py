@@ -31,7 +31,9 @@ def main():
     streams = [torch.from_numpy(np.concatenate([trio[s][0], trio[s][2]]).reshape(-1)).to(dev) for s in synth.SAMPLES]
     subj = tuple(torch.from_numpy(a.reshape(-1)).to(dev) for a in trio["Child"])
     est = int(1.1 * G / world + 14 * n_pairs)
-    pipe = pipeline.DevicePipeline(ctx, k, streams, subj, L, est, 5, 40 * world, 15, 1, rank=rank, world=world)
+    exchange = os.environ.get("RG_EXCHANGE", "p2p")
+    pipe = pipeline.DevicePipeline(ctx, k, streams, subj, L, est, 5, 40 * world, 15, 1, rank=rank, world=world,
+                                   exchange=exchange)
     r = pipe.step()
     r = pipe.step()          # twice: tables are cleared and re-used
     dumps = [t.dump(min_count=1) for t in pipe.tables]
