@@ -222,6 +222,9 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs/sample of the CPU baseline sample")
     ap.add_argument("--mode", default="tiled", choices=["tiled", "direct"])
+    ap.add_argument("--p2p-groups", type=int, default=37, help="hash-prefix groups per shard of the peer-to-peer partition")
+    ap.add_argument("--scatter-ctas", type=int, default=0,
+                    help="CTAs of the (NVLink-bound) peer-to-peer scatter when it overlaps the previous sample's inserts")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: peer-to-peer partition into the owners' slabs, or extract + NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -262,7 +265,8 @@ def main():
     # distinct k-mers per shard: genomic (two haplotypes, ~3 % private) / world + ~6.2 error k-mers per read
     est = int((1.03 * args.genome) / world + 6.2 * 2 * args.pairs)
     pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, 150 * world, MINQ, THRESH,
-                                   mode=mode, rank=rank, world=world, exchange=args.exchange)
+                                   mode=mode, rank=rank, world=world, exchange=args.exchange,
+                                   groups_per_shard=args.p2p_groups, scatter_ctas=args.scatter_ctas)
 
     def barrier():
         if world > 1:

@@ -54,6 +54,9 @@ void rg_shutdown(rg_ctx* ctx);
  * collectives, reductions) is ordered with ours. NULL = the library's own stream; pass
  * cudaStreamLegacy ((void*)0x1) for the legacy default stream. */
 int rg_set_stream(rg_ctx* ctx, void* cuda_stream);
+/* rg_set_stream without waiting for the work enqueued on the previous stream (the caller orders the
+ * streams with events): one context can feed two streams that run concurrently. */
+int rg_use_stream(rg_ctx* ctx, void* cuda_stream);
 int rg_sync(rg_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t rg_launch_count(rg_ctx* ctx);
@@ -133,7 +136,10 @@ int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_ke
 int rg_table_p2p_export(rg_table* t, void* handle64_out);
 int rg_table_p2p_import(rg_table* t, uint32_t rank, const void* handle64);
 int rg_count_p2p_begin(rg_table* t);
-int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride);
+/* max_ctas: CTAs of the scatter kernel (0 = one per SM). It is NVLink-bound: with fewer CTAs it leaves
+ * SMs to the finish kernels of the previous sample running on another stream. */
+int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
+                             uint32_t max_ctas);
 int rg_count_p2p_finish(rg_table* t);
 
 /* ---- H1: histogram ------------------------------------------------------

@@ -81,7 +81,8 @@ def lib():
         "rg_table_p2p_export": (i32, [vp, vp]),
         "rg_table_p2p_import": (i32, [vp, u32, vp]),
         "rg_count_p2p_begin": (i32, [vp]),
-        "rg_count_p2p_scatter_dev": (i32, [vp, vp, u64, u32]),
+        "rg_count_p2p_scatter_dev": (i32, [vp, vp, u64, u32, u32]),
+        "rg_use_stream": (i32, [vp, vp]),
         "rg_count_p2p_finish": (i32, [vp]),
         "rg_histo_rows": (u64, [u64, u64]),
         "rg_histo": (i32, [vp, u64, u64, u64, vp]),
@@ -177,6 +178,10 @@ class Context:
         else:
             p = cuda_stream_ptr or 1
         _check(lib().rg_set_stream(self.h, C.c_void_p(p)), "rg_set_stream")
+
+    def switch_stream(self, cuda_stream_ptr: int):
+        """use_stream without waiting for the previous stream's work (the caller orders them with events)"""
+        _check(lib().rg_use_stream(self.h, C.c_void_p(cuda_stream_ptr or 1)), "rg_use_stream")
 
     def sync(self):
         _check(lib().rg_sync(self.h), "rg_sync")

@@ -76,6 +76,14 @@ int rg_set_stream(rg_ctx* ctx, void* cuda_stream) {
   return 0;
 }
 
+// same without waiting for the work already enqueued on the previous stream: the caller orders the
+// two streams itself (events); lets one context feed two streams that run concurrently
+int rg_use_stream(rg_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return RG_ERR_ARG;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return 0;
+}
+
 int rg_sync(rg_ctx* ctx) {
   RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -528,7 +536,7 @@ int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts) {
 // ---------------------------------------------------------------------------
 static void p2p_layout(const rg_table* t, uint64_t* off_status, uint64_t* off_spill, uint64_t* off_slabs,
                        uint64_t* total) {
-  const uint64_t n_groups = t->n_tiles / t->group_tiles;
+  const uint64_t n_groups = (uint64_t)(t->n_tiles / t->group_tiles) * t->shard_parts;   // (group, source GPU) sub-slabs
   uint64_t o = ((n_groups * 4 + 255) / 256) * 256;
   *off_status = o;
   o += 256;
@@ -567,12 +575,14 @@ int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_ke
   t->keys = nullptr;
   t->counts = nullptr;
   drop_buckets(t);
-  t->p2p_groups = groups_per_shard;
-  int rc = table_alloc_tiles(t, wanted);
+  // at least two tiles per group: the sub-slabs of a group (one per source GPU) are merged by the
+  // groups -> tiles pass
+  t->p2p_groups = std::max<uint32_t>(1, std::min<uint32_t>(groups_per_shard, std::max<uint32_t>(wanted, 2) / 2));
+  int rc = table_alloc_tiles(t, std::max<uint32_t>(wanted, 2));
   if (rc) return rc;
-  const uint64_t n_groups = t->n_tiles / t->group_tiles;
+  const uint64_t n_groups = (uint64_t)(t->n_tiles / t->group_tiles) * t->shard_parts;      // sub-slabs I own
   const uint64_t gmean = max_keys_per_push / n_groups + 1;
-  t->grp_cap = (uint32_t)((gmean + gmean / 2 + 4096 + 3) & ~3ull);
+  t->grp_cap = (uint32_t)((gmean + gmean / 2 + 2048 + 3) & ~3ull);
   t->p2p_spill_cap = 1ull << 20;
   t->p2p_max_keys = max_keys_per_push;
   uint64_t os, osp, osl, tot;
@@ -586,6 +596,7 @@ int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_ke
   t->p2p_status = t->peer_status[t->shard_part];
   t->p2p_spill = t->peer_spill[t->shard_part];
   t->grp_alloc_keys = n_groups * (uint64_t)t->grp_cap;
+  RG_CUDA_OK(cudaMalloc(&t->p2p_src_cursor, (uint64_t)t->n_tiles_global / t->group_tiles * 4));
   RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -613,14 +624,15 @@ int rg_table_p2p_import(rg_table* t, uint32_t rank, const void* handle64) {
 
 int rg_count_p2p_begin(rg_table* t) {
   if (!t || !t->p2p_block) return RG_ERR_ARG;
-  const uint64_t n_groups = t->n_tiles / t->group_tiles;
-  RG_CUDA_OK(cudaMemsetAsync(t->grp_cursor, 0, n_groups * 4, t->ctx->stream));
+  RG_CUDA_OK(cudaMemsetAsync(t->p2p_src_cursor, 0, (uint64_t)t->n_tiles_global / t->group_tiles * 4, t->ctx->stream));
   RG_CUDA_OK(cudaMemsetAsync(t->p2p_status, 0, 64, t->ctx->stream));
   return 0;
 }
 
-int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride) {
+int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
+                             uint32_t max_ctas) {
   if (!t || !t->p2p_block) return RG_ERR_ARG;
+  t->p2p_ctas = max_ctas;
   for (uint32_t r = 0; r < t->shard_parts; ++r)
     if (!t->peer_keys[r]) {
       rg_set_error("rg_count_p2p_scatter_dev: not every peer is imported");
@@ -637,7 +649,15 @@ int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_byt
   ep.read_stride = read_stride;
   ep.k = t->k;
   ep.canonical = t->canonical;
-  return rg_launch_partition_multi(t, ep);
+  int rc = rg_launch_partition_multi(t, ep);
+  if (rc) return rc;
+  // publish the fills of my sub-slabs: owner o's cursor[g][me] = my local cursor of its group g
+  const uint32_t gl = t->n_tiles / t->group_tiles;
+  for (uint32_t o = 0; o < t->shard_parts; ++o)
+    RG_CUDA_OK(cudaMemcpy2DAsync(t->peer_cursor[o] + t->shard_part, (size_t)t->shard_parts * 4,
+                                 t->p2p_src_cursor + (uint64_t)o * gl, 4, 4, gl, cudaMemcpyDeviceToDevice,
+                                 t->ctx->stream));
+  return 0;
 }
 
 // after every rank's scatter has completed (caller's barrier): my groups -> tiles -> inserts
@@ -647,26 +667,10 @@ int rg_count_p2p_finish(rg_table* t) {
   // what the others could not place in my slabs comes through my exported spill list
   uint64_t n_spill = 0;
   RG_CUDA_OK(cudaMemcpyAsync(ctx->h_scratch, t->p2p_status, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  int rc = 0;
-  if (t->group_tiles > 1) {
-    // bucket slabs of my tiles, then groups -> tiles
-    rc = prepare_buckets(t, t->p2p_max_keys);
-    if (rc == 0) rc = rg_launch_partition_groups(t);
-    if (rc) return rc;
-    rc = rg_launch_tile_insert(t);
-  } else {
-    // a group IS a tile: the exported slabs are the tile buckets
-    uint64_t* pk = t->part_keys;
-    uint32_t* pc = t->part_cursor;
-    const uint32_t bc = t->bucket_cap;
-    t->part_keys = t->grp_keys;
-    t->part_cursor = t->grp_cursor;
-    t->bucket_cap = t->grp_cap;
-    rc = rg_launch_tile_insert(t);
-    t->part_keys = pk;
-    t->part_cursor = pc;
-    t->bucket_cap = bc;
-  }
+  // bucket slabs of my tiles, then (group, source) sub-slabs -> tiles, then the tile inserts
+  int rc = prepare_buckets(t, t->p2p_max_keys);
+  if (rc == 0) rc = rg_launch_partition_groups(t);
+  if (rc == 0) rc = rg_launch_tile_insert(t);
   if (rc) return rc;
   t->tiles_dirty = true;
   t->unchecked = true;
@@ -841,6 +845,7 @@ void rg_table_free(rg_table* t) {
     for (int i = 0; i < 8; ++i)
       if (t->peer_mapped[i]) cudaIpcCloseMemHandle(t->peer_mapped[i]);
     cudaFree(t->p2p_block);
+    cudaFree(t->p2p_src_cursor);
   } else {
     cudaFree(t->grp_keys);
     cudaFree(t->grp_cursor);

@@ -49,8 +49,8 @@ struct PartStage {
 
 constexpr size_t part_static_smem() { return sizeof(PartStage) + 33 * sizeof(uint32_t) + 256; }
 // ukeys (8 B) + sorted (tile,index) entries (4 B) per key; count->gdelta and loff per tile; overflow bitmap
-static size_t part_dynamic_smem(uint32_t n_tiles) {
-  return (size_t)PART_K * 12 + (size_t)n_tiles * 8 + (size_t)((n_tiles + 31) / 32) * 4;
+static size_t part_dynamic_smem(uint32_t n_tiles, uint32_t n_groups = 0) {
+  return (size_t)PART_K * 12 + (size_t)n_tiles * 8 + (size_t)((n_tiles + 31) / 32) * 4 + (size_t)(n_groups + 1) * 4;
 }
 
 constexpr int PART_MAX_OWNERS = 8;
@@ -68,13 +68,15 @@ struct PartGeom {
   // level 2 input: the group slabs
   const uint64_t* in_keys;
   const uint32_t* in_cursor;
-  uint32_t in_cap, n_groups;
+  uint32_t in_cap, n_groups;     // n_groups input slabs, in_per_group of them per group (1, or the GPU count)
+  uint32_t in_per_group;
   // overflow / foreign keys
   uint64_t* status;
   uint64_t* spill;
   uint64_t spill_cap;
-  // MULTI: the slabs of bucket b live on GPU b / buckets_per_owner (peer memory), same layout everywhere
-  uint32_t buckets_per_owner;
+  // MULTI: the slabs of bucket b live on GPU b / buckets_per_owner (peer memory), same layout everywhere:
+  // [buckets_per_owner][n_sources][out_cap]; this GPU writes sub-slab my_source and counts in a LOCAL cursor
+  uint32_t buckets_per_owner, n_sources, my_source;
   uint64_t* owner_keys[PART_MAX_OWNERS];
   uint32_t* owner_cursor[PART_MAX_OWNERS];
   uint64_t* owner_status[PART_MAX_OWNERS];
@@ -311,19 +313,42 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_a
   if (threadIdx.x == 0) any_overflow = 0;
   for (uint32_t i = threadIdx.x; i < ovf_words; i += PART_THREADS) ovf_bits[i] = 0;
 
-  // level 2: this CTA takes groups blockIdx.x, +gridDim.x, ...; otherwise one pass over the whole input
-  const uint32_t n_outer = SRC == 2 ? g.n_groups : 1u;
-  for (uint32_t og = SRC == 2 ? blockIdx.x : 0u; og < n_outer; og += SRC == 2 ? gridDim.x : 1u) {
-  const uint64_t* in_keys = SRC == 2 ? g.in_keys + (uint64_t)og * g.in_cap : in_keys_arg;
-  const uint64_t n_in = SRC == 2 ? (uint64_t)min(g.in_cursor[og], g.in_cap) : n_in_arg;
-  const uint32_t slab0 = SRC == 2 ? og * g.n_buckets : 0u;      // first output slab of this group
-  const uint64_t n_units = SRC == 0 ? ep.n_bytes : n_in;
-  const uint64_t n_super = (n_units + PART_K - 1) / PART_K;
-  const uint64_t sc_step = SRC == 2 ? 1u : gridDim.x;
-  for (uint64_t sc = SRC == 2 ? 0u : blockIdx.x; sc < n_super; sc += sc_step) {
+  // Work items = super-chunks. Level 2: the super-chunks of ALL groups, numbered group after group
+  // (gstart[] = exclusive prefix of the groups' chunk counts, built here from the slab cursors), so
+  // that the whole grid is busy whatever the number of groups.
+  uint32_t* gstart = ovf_bits + ovf_words;        // [n_groups + 1], level 2 only
+  uint64_t total_items;
+  if (SRC == 2) {
+    __syncthreads();
+    uint32_t run_g = 0;
+    for (uint32_t base = 0; base < g.n_groups; base += PART_THREADS) {
+      const uint32_t gi = base + threadIdx.x;
+      const uint32_t c = gi < g.n_groups ? (min(g.in_cursor[gi], g.in_cap) + PART_K - 1) / PART_K : 0u;
+      const uint32_t ex = block_exclusive_scan(c, warp_sums, &scan_total);
+      if (gi < g.n_groups) gstart[gi] = run_g + ex;
+      __syncthreads();
+      run_g += scan_total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) gstart[g.n_groups] = run_g;
+    __syncthreads();
+    total_items = run_g;
+  } else {
+    total_items = ((SRC == 0 ? ep.n_bytes : n_in_arg) + PART_K - 1) / PART_K;
+  }
+  uint32_t og = 0;                                 // level 2: group of the current item
+  for (uint64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    if (SRC == 2)
+      while (item >= gstart[og + 1]) ++og;
+    const uint64_t* in_keys = SRC == 2 ? g.in_keys + (uint64_t)og * g.in_cap : in_keys_arg;
+    const uint64_t n_in = SRC == 2 ? (uint64_t)min(g.in_cursor[og], g.in_cap) : n_in_arg;
+    // first output slab of this group (peer-to-peer: the input slabs are (group, source GPU) pairs)
+    const uint32_t slab0 = SRC == 2 ? (og / g.in_per_group) * g.n_buckets : 0u;
+    const uint64_t sc = SRC == 2 ? item - gstart[og] : item;
+    const uint64_t n_super = total_items;
     const uint64_t s0 = sc * PART_K;
     for (uint32_t i = threadIdx.x; i < g.n_buckets; i += PART_THREADS) hist[i] = 0;
-    const bool more = sc + gridDim.x < n_super;
+    const bool more = item + gridDim.x < n_super;
     if (SRC == 0 && more) {
       part_prefetch(pf, ep, (sc + gridDim.x) * PART_K, r_next);
       advance_r();
@@ -386,9 +411,11 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_a
         const uint32_t b = t0 + j;
         const uint32_t want = (cnt[j] + PART_PAD) & ~PART_PAD;
         if (MULTI) {
+          // every source GPU fills its OWN sub-slab of the owner's group slab: the cursor is local
+          // (no atomics over NVLink), only the keys travel
           const uint32_t o = b / g.buckets_per_owner;
           loff[b] = run | (o << 16);                 // the owner rides in the high half (run < 2^14)
-          gb[j] = atomicAdd_system(s_owner_cursor[o] + (b - o * g.buckets_per_owner), want);
+          gb[j] = atomicAdd(g.out_cursor + b, want);
         } else {
           loff[b] = run;
           gb[j] = atomicAdd(g.out_cursor + slab0 + b, want);
@@ -415,7 +442,8 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_a
         const uint32_t b = t0 + j;
         const uint32_t padded = (cnt[j] + PART_PAD) & ~PART_PAD;
         const uint32_t o = MULTI ? b / g.buckets_per_owner : 0u;
-        const uint32_t slab = MULTI ? b - o * g.buckets_per_owner : slab0 + b;   // slab index inside its owner's array
+        // slab index inside its owner's array (MULTI: [group of the owner][source GPU])
+        const uint32_t slab = MULTI ? (b - o * g.buckets_per_owner) * g.n_sources + g.my_source : slab0 + b;
         uint64_t* base = MULTI ? s_owner_keys[o] : g.out_keys;
         const uint32_t at = slab * g.out_cap + gb[j];                            // index of the run in the slab array
         if (gb[j] + padded <= g.out_cap) {
@@ -467,7 +495,6 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_a
       for (uint32_t i = threadIdx.x; i < ovf_words; i += PART_THREADS) ovf_bits[i] = 0;
     }
     __syncthreads();
-  }
   }
 }
 
@@ -528,12 +555,13 @@ uint64_t rg_partition_pad_keys(uint32_t n_buckets, uint64_t n_units) {
 
 template <int SRC, bool MULTI>
 static int launch_sorted(rg_ctx* ctx, const char* name, const ExtractParams& ep, const uint64_t* keys, uint64_t n_keys,
-                         const PartGeom& g, uint64_t n_work, bool sharded) {
-  const size_t smem = part_dynamic_smem(g.n_buckets);
+                         const PartGeom& g, uint64_t n_work, bool sharded, uint32_t max_ctas = 0) {
+  const size_t smem = part_dynamic_smem(g.n_buckets, g.n_groups);
   auto kern = sharded ? partition_sorted_kernel<SRC, true, MULTI> : partition_sorted_kernel<SRC, false, MULTI>;
   RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   unsigned grid = rg_grid(ctx, PART_CTAS);
+  if (max_ctas && max_ctas < grid) grid = max_ctas;
   if (n_work < grid) grid = (unsigned)n_work;
   rg_launch_scope _ls(ctx, name);
   kern<<<grid, PART_THREADS, smem, ctx->stream>>>(ep, keys, n_keys, g);
@@ -592,19 +620,22 @@ int rg_launch_partition_groups(rg_table* t) {
   PartGeom g;
   fill_common(g, t);
   g.n_buckets = t->group_tiles;
-  g.n_groups = t->n_tiles / t->group_tiles;
+  g.in_per_group = t->p2p_block ? t->shard_parts : 1;
+  g.n_groups = t->n_tiles / t->group_tiles * g.in_per_group;
   g.in_keys = t->grp_keys;
   g.in_cursor = t->grp_cursor;
   g.in_cap = t->grp_cap;
   g.out_keys = t->part_keys;
   g.out_cursor = t->part_cursor;
   g.out_cap = t->bucket_cap;
-  if (!part_sorted_fits(g.n_buckets) || (uint64_t)t->n_tiles * t->bucket_cap >= (1ull << 32)) {
+  if (!part_sorted_fits(g.n_buckets) || (uint64_t)t->n_tiles * t->bucket_cap >= (1ull << 32) ||
+      part_dynamic_smem(g.n_buckets, g.n_groups) + part_static_smem() > PART_SMEM_LIMIT) {
     rg_set_error("partition: group geometry out of range");
     return RG_ERR_ARG;
   }
   ExtractParams ep = {};
-  int rc = launch_sorted<2, false>(ctx, "partition_groups_kernel", ep, nullptr, 0, g, g.n_groups, false);
+  // work items = super-chunks over all groups (their number is only known on the device): a full grid
+  int rc = launch_sorted<2, false>(ctx, "partition_groups_kernel", ep, nullptr, 0, g, 1ull << 32, false);
   if (rc) return rc;
   RG_CUDA_OK(cudaGetLastError());
   return 0;
@@ -620,7 +651,10 @@ int rg_launch_partition_multi(rg_table* t, const ExtractParams& ep) {
   g.n_buckets = g.geo.groups;
   g.bucket_first = 0;
   g.buckets_per_owner = t->n_tiles / t->group_tiles;
+  g.n_sources = t->shard_parts;
+  g.my_source = t->shard_part;
   g.out_cap = t->grp_cap;
+  g.out_cursor = t->p2p_src_cursor;
   g.spill_cap = t->p2p_spill_cap;
   for (uint32_t o = 0; o < t->shard_parts; ++o) {
     g.owner_keys[o] = t->peer_keys[o];
@@ -628,12 +662,12 @@ int rg_launch_partition_multi(rg_table* t, const ExtractParams& ep) {
     g.owner_status[o] = t->peer_status[o];
     g.owner_spill[o] = t->peer_spill[o];
   }
-  if (!part_sorted_fits(g.n_buckets) || (uint64_t)g.buckets_per_owner * g.out_cap >= (1ull << 32)) {
+  if (!part_sorted_fits(g.n_buckets) || (uint64_t)g.buckets_per_owner * g.n_sources * g.out_cap >= (1ull << 32)) {
     rg_set_error("partition: too many groups for the peer-to-peer partition");
     return RG_ERR_ARG;
   }
   const uint64_t n_super = (ep.n_bytes + PART_K - 1) / PART_K;
-  int rc = launch_sorted<0, true>(ctx, "partition_p2p_kernel", ep, nullptr, 0, g, n_super, false);
+  int rc = launch_sorted<0, true>(ctx, "partition_p2p_kernel", ep, nullptr, 0, g, n_super, false, t->p2p_ctas);
   if (rc) return rc;
   RG_CUDA_OK(cudaGetLastError());
   return 0;

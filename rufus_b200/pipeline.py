@@ -78,7 +78,7 @@ class DevicePipeline:
     def __init__(self, ctx: api.Context, k: int, streams, subject_pairs, read_len: int, est_distinct: int,
                  min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
                  mode: int = api.MODE_TILED, rank: int = 0, world: int = 1, max_mutant: int = 1 << 22,
-                 exchange: str = "p2p", groups_per_shard: int = 37):
+                 exchange: str = "p2p", groups_per_shard: int = 37, scatter_ctas: int = 0):
         import torch
 
         self.torch = torch
@@ -103,6 +103,10 @@ class DevicePipeline:
             import torch.distributed as dist
             L = api.lib()
             self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.flag2 = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.scatter_stream = torch.cuda.Stream(device=dev)
+            # measured: 96 CTAs at N=2 (the scatter is still close to compute-bound), 64 beyond (NVLink-bound)
+            self.scatter_ctas = scatter_ctas or (96 if world <= 2 else 64)
             n_keys = max(int(s.numel()) for s in streams)      # weak scaling: a shard receives ~ what it sends
             for t in self.tables:
                 api._check(L.rg_table_p2p_prepare(t.h, groups_per_shard, int(n_keys * 1.15) + (1 << 20)),
@@ -151,14 +155,28 @@ class DevicePipeline:
             for t, s in zip(self.tables, self.streams):
                 t.push_dev(s, s.numel(), self.read_len)   # enqueued only: no host synchronisation between the samples
         elif self.exchange == "p2p":
+            import torch.distributed as dist
+            main = torch.cuda.current_stream()
+            side = self.scatter_stream
             for t in self.tables:
                 api._check(L.rg_count_p2p_begin(t.h), "rg_count_p2p_begin")       # zero my slab cursors
-            self.stream_barrier()
-            for t, s in zip(self.tables, self.streams):                          # all samples: scatter to the owners
-                api._check(L.rg_count_p2p_scatter_dev(t.h, api._ptr(s), s.numel(), self.read_len),
-                           "rg_count_p2p_scatter_dev")
-            self.stream_barrier()
-            for t in self.tables:                                                # my groups -> tiles -> inserts
+            self.stream_barrier()                                                # every rank has zeroed
+            side.wait_event(main.record_event())
+            # The scatter of sample i+1 (NVLink-bound, a reduced grid) runs on a side stream while the
+            # finish kernels of sample i (groups -> tiles -> inserts) take the remaining SMs.
+            arrived = []
+            self.ctx.switch_stream(side.cuda_stream)
+            with torch.cuda.stream(side):
+                for i, (t, s) in enumerate(zip(self.tables, self.streams)):
+                    # the first scatter has nothing to overlap with: it takes every SM
+                    ctas = 0 if i == 0 else self.scatter_ctas
+                    api._check(L.rg_count_p2p_scatter_dev(t.h, api._ptr(s), s.numel(), self.read_len, ctas),
+                               "rg_count_p2p_scatter_dev")
+                    dist.all_reduce(self.flag2)                                  # every rank's scatter of this sample is done
+                    arrived.append(side.record_event())
+            self.ctx.switch_stream(main.cuda_stream)
+            for t, ev in zip(self.tables, arrived):
+                main.wait_event(ev)
                 api._check(L.rg_count_p2p_finish(t.h), "rg_count_p2p_finish")
         else:
             # software pipeline: exchange of sample i overlaps extraction of sample i+1 and insertion of sample i-1
