@@ -210,6 +210,13 @@ int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* othe
                         int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_dev,
                         uint32_t* counts_dev, uint64_t cap);
 
+/* ---- S2: RUFUS.Build, the legacy selection (src/RUFUS.Build.cpp:224-283) -------------
+ * { (x, c_S(x), sum_i c_i(x)) : min_subject <= c_S(x) <= max_subject, sum over the control tables
+ * <= max_control_sum }. Unordered; RG_ERR_SMALL / *needed as rg_dump. */
+int64_t rg_build_select(rg_table* subj, int64_t min_subject, int64_t max_subject, rg_table* const* controls,
+                        int n_controls, int64_t max_control_sum, uint64_t* keys_host, uint32_t* counts_host,
+                        uint32_t* control_sums_host, uint64_t cap, uint64_t* needed);
+
 /* ---- F1/F2: read pull ---------------------------------------------------
  * RUFUS.Filter (src/RUFUS.Filter.cpp:121-143,196-277) and RUFUS.Filter.single
  * (src/RUFUS.Filter.ss.cpp:100-121,164-201). */

@@ -139,3 +139,21 @@ def filter_single(s, q, o, k, minq, rset):
     hits = np.zeros(o.size - 1, np.int32)
     lib().ro_filter_single(_p(s), _p(q), _p(o), o.size - 1, k, minq, _p(rset), rset.size, _p(hits))
     return hits
+
+
+def build_select(subj, controls, min_subject: int, max_subject: int, max_control_sum: int):
+    """RUFUS.Build (src/RUFUS.Build.cpp:224-262) restated on sorted (keys, counts) tables: the subject
+    entries with min_subject <= count <= max_subject (:226) whose summed count over the control tables
+    (:245-252, a control contributes only where the k-mer is present) is <= max_control_sum (:257).
+    Returns (keys, subject counts, control sums) in key order = the order of the sorted text dump."""
+    sk, sc = subj
+    sel = (sc >= min_subject) & (sc <= max_subject)
+    keys, counts = sk[sel], sc[sel]
+    total = np.zeros(keys.size, np.int64)
+    for ck, cc in controls:
+        pos = np.searchsorted(ck, keys)
+        pos[pos >= ck.size] = 0
+        hit = (ck.size > 0) & (ck[pos] == keys) if ck.size else np.zeros(keys.size, bool)
+        total += np.where(hit, cc[pos].astype(np.int64), 0)
+    keep = total <= max_control_sum
+    return keys[keep], counts[keep], total[keep].astype(np.uint32)

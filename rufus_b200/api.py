@@ -97,6 +97,7 @@ def lib():
         "rg_merge_unique": (i64, [vp, vp, i32, u64, vp, vp, vp, u64, C.POINTER(u64)]),
         "rg_subtract": (i64, [vp, u64, vp, vp, i32, u64, i64, i64, vp, vp, u64, C.POINTER(u64)]),
         "rg_subtract_dev": (i64, [vp, u64, vp, vp, i32, u64, i64, i64, vp, vp, u64]),
+        "rg_build_select": (i64, [vp, i64, i64, vp, i32, i64, vp, vp, vp, u64, C.POINTER(u64)]),
         "rg_rufus_pack": (u64, [C.c_char_p, i32]),
         "rg_rufus_revcomp": (i32, [C.c_char_p, i32, C.c_char_p]),
         "rg_set_from_hashlist_text": (vp, [vp, C.c_char_p, u64, i32, i32]),
@@ -378,6 +379,27 @@ def subtract(subj, others, subj_min: int = 2, other_min=None, floor: int = 5, mi
             o = np.argsort(keys, kind="stable")
             keys, counts = keys[o], counts[o]
         return keys.copy(), counts.copy()
+
+
+def build_select(subj, controls, min_subject: int, max_subject: int, max_control_sum: int, sort: bool = True):
+    """RUFUS.Build (legacy): subject k-mers with min <= c_S <= max whose summed control count is <= max_control_sum.
+    Returns (keys, subject counts, control sums)."""
+    cap = 1 << 16
+    while True:
+        keys, counts, sums = np.empty(cap, np.uint64), np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+        need = C.c_uint64()
+        n = lib().rg_build_select(subj.h, min_subject, max_subject, _handles(controls), len(controls), max_control_sum,
+                                  _ptr(keys), _ptr(counts), _ptr(sums), cap, C.byref(need))
+        if n == ERR_SMALL:
+            cap = int(need.value) + 1024
+            continue
+        if n < 0:
+            raise _err("rg_build_select")
+        keys, counts, sums = keys[:n], counts[:n], sums[:n]
+        if sort:
+            o = np.argsort(keys, kind="stable")
+            keys, counts, sums = keys[o], counts[o], sums[o]
+        return keys.copy(), counts.copy(), sums.copy()
 
 
 class MutantSet:

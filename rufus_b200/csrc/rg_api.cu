@@ -1074,6 +1074,48 @@ int64_t rg_subtract(rg_table* subj, uint64_t subj_min, rg_table* const* others, 
   return n;
 }
 
+// RUFUS.Build (legacy selection, src/RUFUS.Build.cpp:224-283)
+int64_t rg_build_select(rg_table* subj, int64_t min_subject, int64_t max_subject, rg_table* const* controls,
+                        int n_controls, int64_t max_control_sum, uint64_t* keys_host, uint32_t* counts_host,
+                        uint32_t* control_sums_host, uint64_t cap, uint64_t* needed) {
+  if (!subj) return RG_ERR_ARG;
+  rg_ctx* ctx = subj->ctx;
+  OtherTables ot;
+  int rc = rg_table_finish(subj);
+  if (rc) return rc;
+  rc = fill_others(ot, controls, nullptr, n_controls, subj->k);
+  if (rc) return rc;
+  if (needed) *needed = 0;
+  if (max_subject < 0 || max_control_sum < 0) return 0;     // nothing can pass
+  const uint64_t lo = min_subject > 1 ? (uint64_t)min_subject : 1, hi = (uint64_t)max_subject;
+  uint64_t* dk = nullptr;
+  uint32_t *dc = nullptr, *ds = nullptr;
+  RG_CUDA_OK(cudaMalloc(&dk, (cap ? cap : 1) * 8));
+  RG_CUDA_OK(cudaMalloc(&dc, (cap ? cap : 1) * 4));
+  RG_CUDA_OK(cudaMalloc(&ds, (cap ? cap : 1) * 4));
+  int64_t n = rg_launch_build_select(subj, lo, hi, ot, (uint64_t)max_control_sum, dk, dc, ds, cap, ctx->d_scratch);
+  uint64_t got = 0;
+  if (n == 0) n = read_scalars(ctx, ctx->d_scratch, 1, &got);
+  if (n == 0) {
+    if (needed) *needed = got;
+    if (got > cap) {
+      rg_set_error("rg_build_select: output buffer too small");
+      n = RG_ERR_SMALL;
+    } else {
+      n = copy_out(ctx, got, dk, dc, keys_host, counts_host);
+      if (n >= 0 && got) {
+        cudaError_t e = cudaMemcpyAsync(control_sums_host, ds, got * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rg_set_error(cudaGetErrorString(e)); n = RG_ERR_CUDA; }
+      }
+    }
+  }
+  cudaFree(dk);
+  cudaFree(dc);
+  cudaFree(ds);
+  return n;
+}
+
 int64_t rg_merge_unique(rg_table* const* tabs, const uint64_t* mins, int n_tabs, uint64_t floor, uint64_t* keys_host,
                         uint32_t* counts_host, int32_t* which_host, uint64_t cap, uint64_t* needed) {
   if (!tabs || n_tabs < 1 || n_tabs > 17) {

@@ -305,6 +305,8 @@ struct OtherTables {
 };
 int rg_launch_subtract(rg_table* subj, uint64_t lo, uint64_t hi, const OtherTables& others, uint64_t* d_keys,
                        uint32_t* d_counts, uint64_t cap, uint64_t* d_cursor);
+int rg_launch_build_select(rg_table* subj, uint64_t lo, uint64_t hi, const OtherTables& others, uint64_t max_ctl_sum,
+                           uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_sums, uint64_t cap, uint64_t* d_cursor);
 int rg_launch_rehash(rg_table* dst, const uint64_t* old_keys, const uint32_t* old_counts, uint64_t n_slots);
 
 int rg_launch_set_build(rg_set* s, const uint64_t* d_vals, uint64_t n);

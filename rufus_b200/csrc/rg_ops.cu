@@ -186,6 +186,59 @@ subtract_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// RUFUS.Build (src/RUFUS.Build.cpp:224-283, the legacy selection): subject entries with
+// lo <= c_S <= hi whose SUMMED count over the control tables is <= max_ctl_sum. Emits the key, the
+// subject count and the control sum (out_sums, parallel to out_counts).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+build_select_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n_slots,
+                    uint64_t lo, uint64_t hi, OtherTables others, uint64_t max_ctl_sum, uint64_t* out_keys,
+                    uint32_t* out_counts, uint32_t* out_sums, uint64_t cap, unsigned long long* cursor) {
+  const uint64_t n_round = (n_slots + 31) & ~31ull;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t c = 0;
+    uint64_t key = 0, sum = 0;
+    if (i < n_slots) c = __ldg(counts + i);
+    bool sel = c != 0 && c >= lo && c <= hi;
+    if (sel) {
+      key = __ldg(keys + i);
+      for (int o = 0; o < others.n; ++o) sum += rg_table_get(others.tv[o], key);
+      sel = sum <= max_ctl_sum;
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
+    if (m == 0) continue;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (sel) {
+      const unsigned long long at = base + __popc(m & ((1u << lane) - 1));
+      if (at < cap) {
+        out_keys[at] = key;
+        out_counts[at] = c;
+        out_sums[at] = sum > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)sum;
+      }
+    }
+  }
+}
+
+int rg_launch_build_select(rg_table* subj, uint64_t lo, uint64_t hi, const OtherTables& others, uint64_t max_ctl_sum,
+                           uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_sums, uint64_t cap, uint64_t* d_cursor) {
+  rg_ctx* ctx = subj->ctx;
+  const uint64_t n_slots = (uint64_t)subj->n_tiles << RG_TILE_BITS;
+  RG_CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), ctx->stream));
+  {
+    rg_launch_scope _ls(ctx, "build_select_kernel");
+    build_select_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(subj->keys, subj->counts, n_slots, lo, hi, others,
+                                                                  max_ctl_sum, d_keys, d_counts, d_sums, cap,
+                                                                  reinterpret_cast<unsigned long long*>(d_cursor));
+  }
+  RG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int rg_launch_subtract(rg_table* subj, uint64_t lo, uint64_t hi, const OtherTables& others, uint64_t* d_keys,
                        uint32_t* d_counts, uint64_t cap, uint64_t* d_cursor) {
   rg_ctx* ctx = subj->ctx;

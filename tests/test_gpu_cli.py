@@ -128,3 +128,25 @@ def test_jhash_files_interoperate_with_real_jellyfish(run):
     q = f"query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) {names[0]}.Jhash"
     sh(f"{JF} merge {ours} > merge.out", work)
     assert sh(f"{REFJF} {q}", work).stdout == sh(f"{JF} {q}", work).stdout
+
+
+def test_rufus_build_matches_reference_goldens(tmp_path):
+    """tools/bin/RUFUS.Build (legacy selection, src/RUFUS.Build.cpp) on the committed sorted dumps vs the
+    outputs of the reference binary (tests/golden/build_golden.json), byte for byte incl. order."""
+    import json
+    gold = json.load(open(os.path.join(GOLDEN, "build_golden.json")))
+    work = str(tmp_path)
+    done = set()
+    for c in gold["cases"]:
+        case = c["case"]
+        names = SAMPLES[case]
+        if case not in done:
+            for i, s in enumerate(names):
+                txt = gzip.open(os.path.join(GOLDEN, case, s + ".dump.sorted.gz")).read().decode()
+                open(os.path.join(work, f"{case}.{s}.tab"), "w").write(txt.replace(" ", "\t") if i == 0 else txt)
+            done.add(case)
+        ctl = " ".join(f"-c {case}.{s}.tab" for s in names[1:])
+        sh(f"{BIN}/RUFUS.Build {ctl} -s {case}.{names[0]}.tab -o out -hs {c['k']} -mS {c['mS']} -max {c['max']} "
+           f"-mC {c['mC']} -t 1 -d ' '", work)
+        assert open(os.path.join(work, "out")).read().splitlines() == c["lines"], (case, c["mS"], c["max"], c["mC"])
+        assert os.path.exists(os.path.join(work, "out.Buld.Log"))

@@ -207,3 +207,21 @@ def test_two_level_partition_matches_single_level(monkeypatch):
         t.free()
     finally:
         c.close()
+
+
+def test_build_select_matches_oracle(ctx):
+    """rg_build_select (RUFUS.Build) vs the oracle on a synthetic trio"""
+    trio, _ = synth.make_trio(31, 100_000, 10_000)
+    tabs, otabs = [], []
+    for s in synth.SAMPLES:
+        s1, _, s2, _ = trio[s]
+        both = np.concatenate([s1, s2])
+        offs = np.arange(both.shape[0] + 1, dtype=np.uint64) * 150
+        tabs.append(api.KmerTable.count(ctx, both, offs, 25, True, mode=api.MODE_TILED))
+        otabs.append(oracle.count(both.reshape(-1), offs, 25, True, 1))
+    for mS, mx, mC in ((5, 60, 0), (2, 1000, 3), (1, 3, 100)):
+        k1, c1, s1 = api.build_select(tabs[0], tabs[1:], mS, mx, mC)
+        k2, c2, s2 = oracle.build_select(otabs[0], otabs[1:], mS, mx, mC)
+        assert np.array_equal(k1, k2) and np.array_equal(c1, c2) and np.array_equal(s1, s2), (mS, mx, mC)
+    for t in tabs:
+        t.free()

@@ -83,3 +83,29 @@ def test_count_semantics_small():
     keys, counts = oracle.count(seq, offs, 3, False, 1)
     txt = dict(zip(kmer.keys_to_text(keys, 3), counts.tolist()))
     assert txt == {"ACG": 2, "CGT": 2, "GTA": 1, "TAC": 1}
+
+
+def test_build_select_matches_reference_rufus_build():
+    """oracle.build_select vs the committed outputs of the reference RUFUS.Build (tests/golden/make_build_golden.py)"""
+    import gzip
+    import json
+    from rufus_b200 import kmer
+    gold = json.load(open(os.path.join(GOLDEN, "build_golden.json")))
+    names = {"testRun": ("Child", "Mother", "Father"), "edge": ("Subj", "CtlA", "CtlB")}
+    tabs = {}
+    for c in gold["cases"]:
+        case, k = c["case"], c["k"]
+        if case not in tabs:
+            tabs[case] = []
+            for s in names[case]:
+                rows = [l.split() for l in gzip.open(os.path.join(GOLDEN, case, s + ".dump.sorted.gz")).read().decode().splitlines()]
+                keys = np.array([kmer.text_to_key(r[0]) for r in rows], np.uint64)
+                counts = np.array([int(r[1]) for r in rows], np.uint32)
+                o = np.argsort(keys, kind="stable")
+                tabs[case].append((keys[o], counts[o]))
+        sub, ctl = tabs[case][0], tabs[case][1:]
+        keys, counts, sums = oracle.build_select(sub, ctl, c["mS"], c["max"], c["mC"])
+        text = kmer.keys_to_text(keys, k)
+        pack = oracle.lib().ro_rufus_pack
+        lines = [f"{pack(t.encode(), len(t))}\t{int(s)}\t{int(n)}\t{t}" for t, n, s in zip(text, counts, sums)]
+        assert lines == c["lines"], (case, c["mS"], c["max"], c["mC"])
