@@ -244,6 +244,12 @@ int rg_filter_pairs_fixed_dev(rg_set* s, const char* s1_dev, const char* q1_dev,
 /* keep[i] = hits(mate1)>=thresh || hits(mate2)>=thresh; HOST buffers */
 int rg_filter_pairs(rg_set* s, const char* s1, const char* q1, const uint64_t* o1, const char* s2, const char* q2,
                     const uint64_t* o2, uint64_t n_pairs, int minq, int thresh, uint8_t* keep_host);
+/* AnnotateOverlap (src/AnnotateOverlap.cpp:95-146), the `.hashcount.fastq` depth line: per BASE, the
+ * number of mutant k-mer windows covering it (capped at 255; the tool prints min(depth,93)+33). A
+ * window counts when it holds no 'N', every quality-33 >= minq (the tool: 3), it or its reverse
+ * complement is in the set, and it is not the read's last window (`i < length-K`). HOST buffers. */
+int rg_annotate(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint64_t n_reads, int minq,
+                uint8_t* depth_host);
 /* single-end: hits per read, last base included; HOST buffers */
 int rg_filter_single(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint64_t n_reads,
                      int minq, int32_t* hits_host);

@@ -157,3 +157,30 @@ def build_select(subj, controls, min_subject: int, max_subject: int, max_control
         total += np.where(hit, cc[pos].astype(np.int64), 0)
     keep = total <= max_control_sum
     return keys[keep], counts[keep], total[keep].astype(np.uint32)
+
+
+def annotate(seq, qual, offs, k: int, rset, minq: int = 3) -> np.ndarray:
+    """AnnotateOverlap (src/AnnotateOverlap.cpp:95-146) restated: per-base depth of mutant k-mer windows.
+    Window i of a read of length L is examined for i < L - k (:101), counts when it holds no 'N' and every
+    quality-33 >= minq (:104-115) and its rufus key or its reverse complement's is in the set (:117-128;
+    `rset` holds k-mer and reverse complement, like the tool's two lookups). Small inputs only."""
+    seq = np.ascontiguousarray(seq, np.uint8).reshape(-1)
+    qual = np.ascontiguousarray(qual, np.uint8).reshape(-1)
+    offs = np.ascontiguousarray(offs, np.uint64)
+    members = set(int(x) for x in np.asarray(rset, np.uint64).tolist())
+    code = {ord("C"): 2, ord("G"): 1, ord("T"): 3}
+    depth = np.zeros(seq.size, np.uint8)
+    for r in range(offs.size - 1):
+        a, b = int(offs[r]), int(offs[r + 1])
+        s, q = seq[a:b], qual[a:b]
+        for i in range(0, max(0, (b - a) - k)):
+            w, wq = s[i:i + k], q[i:i + k]
+            if (w == ord("N")).any() or (wq.astype(np.int64).astype(np.int8).astype(np.int64) - 33 < minq).any():
+                continue
+            v = 0
+            for j, c in enumerate(w.tolist()):
+                v |= code.get(c, 0) << (2 * j)
+            if v in members:
+                d = depth[a + i:a + i + k].astype(np.int64) + 1
+                depth[a + i:a + i + k] = np.minimum(d, 255).astype(np.uint8)
+    return depth

@@ -111,6 +111,7 @@ def lib():
         "rg_filter_pairs_fixed_dev": (i32, [vp, vp, vp, vp, vp, u32, u64, i32, i32, vp, vp, vp]),
         "rg_filter_pairs": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, i32, i32, vp]),
         "rg_filter_single": (i32, [vp, vp, vp, vp, u64, i32, vp]),
+        "rg_annotate": (i32, [vp, vp, vp, vp, u64, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -443,6 +444,14 @@ class MutantSet:
         _check(lib().rg_filter_single(self.h, _ptr(s), _ptr(q), _ptr(o), o.size - 1, minq, _ptr(hits)),
                "rg_filter_single")
         return hits
+
+    def annotate(self, s, q, o, minq: int = 3) -> np.ndarray:
+        """AnnotateOverlap: per-base depth of mutant k-mer windows (the .hashcount.fastq quality line)"""
+        s, q = _u8(s), _u8(q)
+        o = np.ascontiguousarray(o, np.uint64)
+        depth = np.zeros(int(o[-1]), np.uint8)
+        _check(lib().rg_annotate(self.h, _ptr(s), _ptr(q), _ptr(o), o.size - 1, minq, _ptr(depth)), "rg_annotate")
+        return depth
 
     def free(self):
         if self.h:

@@ -1378,7 +1378,8 @@ int rg_filter_pairs_fixed_dev(rg_set* s, const char* s1, const char* q1, const c
 // the two staging slots in pieces that end on read boundaries (copy of piece i+1 overlaps the
 // filter kernel of piece i); device scratch comes from the context's grow-only pool.
 static int filter_host_mate(rg_set* s, const char* seq, const char* qual, const uint64_t* offs_host,
-                            const uint64_t* offs_dev, uint64_t n_reads, int minq, int skip_last, int32_t* hits_dev) {
+                            const uint64_t* offs_dev, uint64_t n_reads, int minq, int skip_last, int32_t* hits_dev,
+                            uint8_t* hit_flags_dev = nullptr) {
   rg_ctx* ctx = s->ctx;
   RG_CUDA_OK(cudaMemsetAsync(hits_dev, 0, n_reads * sizeof(int32_t), ctx->stream));
   const uint64_t half = (ctx->slot_bytes / 2) & ~255ull;     // sequence in the first half of a slot, quality in the second
@@ -1404,7 +1405,7 @@ static int filter_host_mate(rg_set* s, const char* seq, const char* qual, const 
       rc = slot_publish(ctx, i);
       if (rc == 0)
         rc = rg_launch_filter_hits(s, ctx->slot[i], ctx->slot[i] + half, offs_dev, 0, n_reads, len, b0, false, minq,
-                                   skip_last, hits_dev);
+                                   skip_last, hits_dev, hit_flags_dev);
       if (rc == 0) rc = slot_release(ctx, i);
       if (rc) return rc;
     }
@@ -1444,6 +1445,33 @@ int rg_filter_pairs(rg_set* s, const char* s1, const char* q1, const uint64_t* o
   if (rc == 0) rc = rg_launch_keep(ctx, h1, h2, n_pairs, thresh, d_keep);
   if (rc) return rc;
   RG_CUDA_OK(cudaMemcpyAsync(keep_host, d_keep, n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// AnnotateOverlap (src/AnnotateOverlap.cpp:95-146): per-base depth of mutant k-mer windows. A window
+// counts when it has no 'N', every quality is >= minq (the tool uses 3), it or its reverse complement
+// is in the set, and it is not the last window of the read (the tool's `i < length - K` bound).
+int rg_annotate(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint64_t n_reads, int minq,
+                uint8_t* depth_host) {
+  if (!s) return RG_ERR_ARG;
+  if (n_reads == 0) return 0;
+  rg_ctx* ctx = s->ctx;
+  const uint64_t n_bytes = offs[n_reads];
+  int rc = slots_ensure(ctx);
+  if (rc == 0) rc = upload_offsets(ctx, 0, offs, n_reads);
+  if (rc == 0) rc = pool_ensure(ctx, 2, n_reads * 4);
+  if (rc == 0) rc = pool_ensure(ctx, 4, n_bytes + 16);
+  if (rc == 0) rc = pool_ensure(ctx, 5, n_bytes + 16);
+  if (rc) return rc;
+  uint8_t* flags = static_cast<uint8_t*>(ctx->pool[4]);
+  uint8_t* cov = static_cast<uint8_t*>(ctx->pool[5]);
+  RG_CUDA_OK(cudaMemsetAsync(flags, 0, n_bytes + 16, ctx->stream));
+  rc = filter_host_mate(s, seq, qual, offs, static_cast<const uint64_t*>(ctx->pool[0]), n_reads, minq, 1,
+                        static_cast<int32_t*>(ctx->pool[2]), flags);
+  if (rc == 0) rc = rg_launch_coverage(ctx, flags, static_cast<const uint64_t*>(ctx->pool[0]), n_reads, n_bytes, s->k, cov);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaMemcpyAsync(depth_host, cov, n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

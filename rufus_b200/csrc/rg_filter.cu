@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(FILTER_THREADS)
 filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, const uint64_t* __restrict__ offs,
                    uint32_t read_len, uint64_t n_reads, uint64_t n_bytes, uint64_t pos_base, int k, int minq,
                    int skip_last, const uint64_t* __restrict__ table, uint32_t slots, const uint32_t* __restrict__ g_bitmap,
-                   uint32_t bitmap_bits, int has_all_ones, int32_t* __restrict__ hits) {
+                   uint32_t bitmap_bits, int has_all_ones, int32_t* __restrict__ hits,
+                   uint8_t* __restrict__ hit_flags) {
   extern __shared__ __align__(16) uint32_t s_bitmap[];   // bitmap_bits-bit prefilter of the set
   __shared__ FilterStage sm;
   {
@@ -255,14 +256,17 @@ filter_hits_kernel(const char* __restrict__ seq, const char* __restrict__ qual, 
         r1 = (r + 1) * read_len;
       }
       const uint64_t end_excl = skip_last ? (r1 > 0 ? r1 - 1 : 0) : r1;   // window must end before this
-      if (gp + k <= end_excl) atomicAdd(hits + r, 1);
+      if (gp + k <= end_excl) {
+        atomicAdd(hits + r, 1);
+        if (hit_flags) hit_flags[gp] = 1;      // AnnotateOverlap: which window starts hit (per-base depth comes next)
+      }
     }
   }
 }
 
 int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint32_t read_len,
                           uint64_t n_reads, uint64_t n_bytes, uint64_t pos_base, bool zero_hits, int minq, int skip_last,
-                          int32_t* hits) {
+                          int32_t* hits, uint8_t* hit_flags) {
   rg_ctx* ctx = s->ctx;
   if (zero_hits) RG_CUDA_OK(cudaMemsetAsync(hits, 0, n_reads * sizeof(int32_t), ctx->stream));
   if (n_bytes == 0 || n_reads == 0) return 0;
@@ -281,7 +285,41 @@ int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const ui
     filter_hits_kernel<<<grid, FILTER_THREADS, smem, ctx->stream>>>(seq, qual, offs, read_len, n_reads, n_bytes,
                                                                     pos_base, s->k, minq, skip_last, s->table, s->slots,
                                                                     s->bitmap,
-                                                                    s->bitmap_bits, s->has_all_ones, hits);
+                                                                    s->bitmap_bits, s->has_all_ones, hits, hit_flags);
+  }
+  RG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// AnnotateOverlap (src/AnnotateOverlap.cpp:117-146): depth[j] = number of hit windows covering base j,
+// i.e. hit window starts in [j-k+1, j] that belong to the same read.
+__global__ void coverage_kernel(const uint8_t* __restrict__ hit_flags, const uint64_t* __restrict__ offs,
+                                uint64_t n_reads, uint64_t n_bytes, int k, uint8_t* __restrict__ cov) {
+  for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n_bytes;
+       j += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t lo = 0, hi = n_reads;            // read that owns base j: largest r with offs[r] <= j
+    while (hi - lo > 1) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (offs[mid] <= j) lo = mid; else hi = mid;
+    }
+    uint64_t r = lo;
+    while (offs[r + 1] <= j && r + 1 < n_reads) ++r;
+    const uint64_t r0 = offs[r];
+    const uint64_t first = (j + 1 >= (uint64_t)k + r0) ? j + 1 - k : r0;
+    uint32_t c = 0;
+    for (uint64_t i = first; i <= j; ++i) c += hit_flags[i];
+    cov[j] = (uint8_t)(c > 255 ? 255 : c);
+  }
+}
+
+int rg_launch_coverage(rg_ctx* ctx, const uint8_t* hit_flags, const uint64_t* offs, uint64_t n_reads, uint64_t n_bytes,
+                       int k, uint8_t* cov) {
+  if (n_bytes == 0) return 0;
+  unsigned grid = (unsigned)((n_bytes + 255) / 256);
+  if (grid > rg_grid(ctx, 8)) grid = rg_grid(ctx, 8);
+  {
+    rg_launch_scope _ls(ctx, "coverage_kernel");
+    coverage_kernel<<<grid, 256, 0, ctx->stream>>>(hit_flags, offs, n_reads, n_bytes, k, cov);
   }
   RG_CUDA_OK(cudaGetLastError());
   return 0;

@@ -314,7 +314,9 @@ int rg_launch_jf_to_rufus(rg_ctx* ctx, const uint64_t* d_jf, uint64_t n, int k, 
 // pos_base: stream position of seq[0] (offs / read_len are absolute); zero_hits: clear hits[0..n_reads) first
 int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint32_t read_len,
                           uint64_t n_reads, uint64_t n_bytes, uint64_t pos_base, bool zero_hits, int minq, int skip_last,
-                          int32_t* hits);
+                          int32_t* hits, uint8_t* hit_flags = nullptr);
+int rg_launch_coverage(rg_ctx* ctx, const uint8_t* hit_flags, const uint64_t* offs, uint64_t n_reads, uint64_t n_bytes,
+                       int k, uint8_t* cov);
 int rg_launch_keep(rg_ctx* ctx, const int32_t* h1, const int32_t* h2, uint64_t n, int thresh, uint8_t* keep);
 
 // RAII: times one kernel launch when profiling is on, and counts the launch

@@ -150,3 +150,20 @@ def test_rufus_build_matches_reference_goldens(tmp_path):
            f"-mC {c['mC']} -t 1 -d ' '", work)
         assert open(os.path.join(work, "out")).read().splitlines() == c["lines"], (case, c["mS"], c["max"], c["mC"])
         assert os.path.exists(os.path.join(work, "out.Buld.Log"))
+
+
+def test_annotate_overlap_matches_reference_golden(tmp_path):
+    """tools/bin/AnnotateOverlap (the .hashcount.fastq writer) vs the committed output of the reference binary"""
+    import json
+    d = os.path.join(GOLDEN, "annotate")
+    g = json.load(open(os.path.join(d, "golden.json")))
+    r = subprocess.run([os.path.join(BIN, "AnnotateOverlap"), os.path.join(d, "HashList"), os.path.join(d, "reads.fastq"),
+                        str(tmp_path / "hash.out")], capture_output=True, check=True)
+    assert r.stdout.decode().splitlines()[3::4][:len(g["depth_lines"])] == g["depth_lines"]
+    assert md5(r.stdout) == g["stdout_md5"]
+    assert md5(open(tmp_path / "hash.out", "rb").read()) == g["hashout_md5"]
+    # stdin form (Overlap.shorter.sh pipes the contigs in)
+    r2 = subprocess.run([os.path.join(BIN, "AnnotateOverlap"), os.path.join(d, "HashList"), "stdin",
+                         str(tmp_path / "hash2.out")], input=open(os.path.join(d, "reads.fastq"), "rb").read(),
+                        capture_output=True, check=True)
+    assert r2.stdout == r.stdout

@@ -225,3 +225,29 @@ def test_build_select_matches_oracle(ctx):
         assert np.array_equal(k1, k2) and np.array_equal(c1, c2) and np.array_equal(s1, s2), (mS, mx, mC)
     for t in tabs:
         t.free()
+
+
+def test_annotate_matches_oracle(ctx):
+    """rg_annotate (AnnotateOverlap's per-base depth) vs the oracle on reads with planted mutant k-mers, N and low quality"""
+    rng = np.random.default_rng(5)
+    k, n, L = 25, 200, 120
+    seq = rng.integers(0, 4, (n, L)).astype(np.uint8)
+    seq = np.frombuffer(b"ACGT", np.uint8)[seq]
+    qual = np.full((n, L), ord("I"), np.uint8)
+    qual[rng.random((n, L)) < 0.02] = ord("#")          # Q2 < 3
+    seq[rng.random((n, L)) < 0.01] = ord("N")
+    kmers = []
+    for i in range(0, n, 3):
+        p = int(rng.integers(0, L - k))
+        kmers.append(bytes(seq[i, p:p + k]).decode())
+    kmers = [m for m in kmers if "N" not in m]
+    # every 2nd planted k-mer is listed as its reverse complement
+    comp = str.maketrans("ACGT", "TGCA")
+    listed = [m if i % 2 else m.translate(comp)[::-1] for i, m in enumerate(kmers)]
+    text = "".join(f"{m} 7\n" for m in listed).encode()
+    offs = np.arange(n + 1, dtype=np.uint64) * L
+    mset = api.MutantSet.from_hashlist_text(ctx, text, k, paired=True)
+    got = mset.annotate(seq, qual, offs, 3)
+    want = oracle.annotate(seq, qual, offs, k, oracle.rufus_set_from_kmers(listed), 3)
+    assert np.array_equal(got, want) and int(want.max()) > 0
+    mset.free()

@@ -109,3 +109,19 @@ def test_build_select_matches_reference_rufus_build():
         pack = oracle.lib().ro_rufus_pack
         lines = [f"{pack(t.encode(), len(t))}\t{int(s)}\t{int(n)}\t{t}" for t, n, s in zip(text, counts, sums)]
         assert lines == c["lines"], (case, c["mS"], c["max"], c["mC"])
+
+
+def test_annotate_matches_reference_annotate_overlap():
+    """oracle.annotate vs the committed output of the reference AnnotateOverlap (tests/golden/make_annotate_golden.py)"""
+    import json
+    from rufus_b200 import fastq
+    d = os.path.join(GOLDEN, "annotate")
+    g = json.load(open(os.path.join(d, "golden.json")))
+    r = fastq.read_fastq(os.path.join(d, "reads.fastq"))
+    kmers = [l.split()[0] for l in open(os.path.join(d, "HashList")).read().splitlines()]
+    depth = oracle.annotate(r.seq, r.qual, r.offs, len(kmers[0]), oracle.rufus_set_from_kmers(kmers), 3)
+    got = ["".join(chr(min(int(x), 93) + 33) for x in depth[int(r.offs[i]):int(r.offs[i + 1])]) for i in range(len(r))]
+    assert got[:len(g["depth_lines"])] == g["depth_lines"]
+    names = [n.decode() for n in r.names]
+    text = "".join(f"{names[i]}:MH0\n{bytes(r.seq[int(r.offs[i]):int(r.offs[i+1])]).decode()}\n+\n{got[i]}\n" for i in range(len(r)))
+    assert hashlib.md5(text.encode()).hexdigest() == g["stdout_md5"]
