@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs/sample of the CPU baseline sample")
     ap.add_argument("--mode", default="tiled", choices=["tiled", "direct"])
-    ap.add_argument("--p2p-groups", type=int, default=37, help="hash-prefix groups per shard of the peer-to-peer partition")
+    ap.add_argument("--p2p-groups", type=int, default=0, help="hash-prefix groups per shard of the peer-to-peer partition")
     ap.add_argument("--scatter-ctas", type=int, default=0,
                     help="CTAs of the (NVLink-bound) peer-to-peer scatter when it overlaps the previous sample's inserts")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

@@ -458,8 +458,26 @@ static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, 
 }
 
 // every reader of a table goes through this: resolve what the enqueued pushes left behind
+static int p2p_collect_spill(rg_table* t) {
+  rg_ctx* ctx = t->ctx;
+  t->p2p_pending = false;
+  uint64_t n_spill = 0;
+  int rc = read_scalars(ctx, t->p2p_status, 1, &n_spill);
+  if (rc) return rc;
+  if (n_spill > t->p2p_spill_cap) {
+    rg_set_error("count: peer-to-peer spill list overflowed; raise max_keys_per_push");
+    return RG_ERR_FULL;
+  }
+  if (n_spill) return rg_launch_insert_keys(t, t->p2p_spill, n_spill, nullptr);
+  return 0;
+}
+
 int rg_table_finish(rg_table* t) {
   if (!t->unchecked) return 0;
+  if (t->p2p_pending) {
+    const int prc = p2p_collect_spill(t);
+    if (prc) return prc;
+  }
   const int rc = table_resolve_spill(t);
   if (rc == 0) t->unchecked = false;
   return rc;
@@ -660,13 +678,11 @@ int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_byt
   return 0;
 }
 
-// after every rank's scatter has completed (caller's barrier): my groups -> tiles -> inserts
+// after every rank's scatter has completed (caller's barrier): my groups -> tiles -> inserts.
+// Asynchronous: what the other GPUs could not place in my slabs (their overflow goes to my exported
+// spill list) is picked up by rg_count_end / the first reader (rg_table_finish).
 int rg_count_p2p_finish(rg_table* t) {
   if (!t || !t->p2p_block) return RG_ERR_ARG;
-  rg_ctx* ctx = t->ctx;
-  // what the others could not place in my slabs comes through my exported spill list
-  uint64_t n_spill = 0;
-  RG_CUDA_OK(cudaMemcpyAsync(ctx->h_scratch, t->p2p_status, 8, cudaMemcpyDeviceToHost, ctx->stream));
   // bucket slabs of my tiles, then (group, source) sub-slabs -> tiles, then the tile inserts
   int rc = prepare_buckets(t, t->p2p_max_keys);
   if (rc == 0) rc = rg_launch_partition_groups(t);
@@ -674,16 +690,7 @@ int rg_count_p2p_finish(rg_table* t) {
   if (rc) return rc;
   t->tiles_dirty = true;
   t->unchecked = true;
-  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  n_spill = ctx->h_scratch[0];
-  if (n_spill > t->p2p_spill_cap) {
-    rg_set_error("count: peer-to-peer spill list overflowed; raise max_keys_per_push");
-    return RG_ERR_FULL;
-  }
-  if (n_spill) {
-    rc = rg_launch_insert_keys(t, t->p2p_spill, n_spill, nullptr);
-    if (rc) return rc;
-  }
+  t->p2p_pending = true;
   return 0;
 }
 

@@ -97,6 +97,7 @@ struct rg_table {
   void* p2p_block = nullptr;
   uint64_t p2p_block_bytes = 0;
   uint64_t p2p_spill_cap = 0;
+  bool p2p_pending = false;          // a finished peer-to-peer push whose exported spill list is not collected yet
   uint32_t p2p_ctas = 0;             // CTAs of the scatter kernel (0 = one per SM); fewer leave SMs to a concurrent stream
   uint64_t p2p_max_keys = 0;         // keys one shard may receive per push (sizes the slabs)
   uint32_t* p2p_src_cursor = nullptr;  // LOCAL fill of my sub-slab in every group of every shard [groups_global]

@@ -78,7 +78,7 @@ class DevicePipeline:
     def __init__(self, ctx: api.Context, k: int, streams, subject_pairs, read_len: int, est_distinct: int,
                  min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
                  mode: int = api.MODE_TILED, rank: int = 0, world: int = 1, max_mutant: int = 1 << 22,
-                 exchange: str = "p2p", groups_per_shard: int = 37, scatter_ctas: int = 0):
+                 exchange: str = "p2p", groups_per_shard: int = 0, scatter_ctas: int = 0):
         import torch
 
         self.torch = torch
@@ -108,6 +108,8 @@ class DevicePipeline:
             # measured: 96 CTAs at N=2 (the scatter is still close to compute-bound), 64 beyond (NVLink-bound)
             self.scatter_ctas = scatter_ctas or (96 if world <= 2 else 64)
             n_keys = max(int(s.numel()) for s in streams)      # weak scaling: a shard receives ~ what it sends
+            # fewer, longer runs travel better over NVLink (measured: N=2 37 groups/shard, N=8 16 > 37 > 74)
+            groups_per_shard = groups_per_shard or (37 if world <= 2 else max(8, 128 // world))
             for t in self.tables:
                 api._check(L.rg_table_p2p_prepare(t.h, groups_per_shard, int(n_keys * 1.15) + (1 << 20)),
                            "rg_table_p2p_prepare")
