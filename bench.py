@@ -315,7 +315,8 @@ def main():
         pass
     kern = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in prof.items()}
     if world == 1:
-        names = ["partition_kernel", "tile_insert_kernel"] if mode == api.MODE_TILED else ["count_direct_kernel"]
+        names = ["partition_kernel", "partition_groups_kernel", "tile_insert_kernel"] if mode == api.MODE_TILED \
+            else ["count_direct_kernel"]          # (partition_groups_kernel only runs for tables beyond one partition pass)
     elif args.exchange == "p2p":
         names = ["partition_p2p_kernel", "partition_groups_kernel", "tile_insert_kernel"]
     else:

@@ -235,8 +235,8 @@ static int pool_ensure(rg_ctx* ctx, int i, uint64_t bytes) {
 // Tile count and group geometry for at least `wanted` tiles (header of rg_internal.cuh):
 //  * direct mode: no constraint;
 //  * tiled mode, small table: group_tiles = 1 (one partition pass), whole waves of tile-insert CTAs;
-//  * tiled mode, more tiles than one sorted pass can histogram in shared memory: 8 x SMs groups
-//    per shard (two passes: stream -> groups -> tiles);
+//  * tiled mode, more tiles than one sorted pass can histogram in shared memory: one group per SM
+//    (two passes: stream -> groups -> tiles);
 //  * peer-to-peer multi-GPU counting: p2p_groups groups per shard (the level-1 pass sorts into the
 //    groups of ALL shards at once).
 static void choose_geometry(const rg_table* t, uint32_t wanted, uint32_t* n_tiles, uint32_t* group_tiles) {
@@ -249,7 +249,7 @@ static void choose_geometry(const rg_table* t, uint32_t wanted, uint32_t* n_tile
   uint32_t groups = 0;
   if (t->p2p_groups) groups = t->p2p_groups;
   else if (ctx->force_groups) groups = ctx->force_groups;
-  else if (wanted > max1) groups = std::min(8 * sm, max1);
+  else if (wanted > max1) groups = std::min(sm, max1);   // measured on 9472 tiles: 148 groups 5.3+4.9 ms, 1184 groups 6.0+5.1 ms
   if (groups) {
     if (groups > wanted) groups = wanted ? wanted : 1;
     *group_tiles = (wanted + groups - 1) / groups;
