@@ -251,3 +251,27 @@ def test_annotate_matches_oracle(ctx):
     want = oracle.annotate(seq, qual, offs, k, oracle.rufus_set_from_kmers(listed), 3)
     assert np.array_equal(got, want) and int(want.max()) > 0
     mset.free()
+
+
+def test_two_level_partition_growth_and_heavy_hitters(monkeypatch):
+    """the same stress on the two-level geometry: slabs of groups AND of tiles overflow (poly-A reads),
+    the table starts far too small and grows between pushes"""
+    monkeypatch.setenv("RG_GROUPS_LOCAL", "3")
+    c = api.Context(0)
+    try:
+        rng = np.random.default_rng(4)
+        reads = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=(60_000, 100))]
+        reads[:8000] = ord("A")
+        offs = np.arange(reads.shape[0] + 1, dtype=np.uint64) * 100
+        t = api.KmerTable(c, 21, True, est_distinct=200_000, mode=api.MODE_TILED)
+        half = 30_000
+        t.push_reads(reads[:half], offs[:half + 1])
+        t.end(trim=False)
+        t.push_reads(reads[half:], offs[: reads.shape[0] - half + 1])
+        t.end()
+        keys, counts = t.dump()
+        okeys, ocounts = oracle.count(reads.reshape(-1), offs, 21, True, 1)
+        assert np.array_equal(keys, okeys) and np.array_equal(counts, ocounts)
+        t.free()
+    finally:
+        c.close()

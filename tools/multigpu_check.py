@@ -26,6 +26,13 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     k, L, n_pairs, G = 25, 150, 40_000, 300_000
     trio, _ = synth.make_trio(17, G, n_pairs, slice_id=rank)
+    if os.environ.get("RG_HEAVY", "1") == "1":
+        # heavy hitters: poly-A / poly-AC reads make single groups overflow their slabs, so the owner's
+        # exported spill list (p2p) and the bucket overflow paths are part of what is checked
+        for s in synth.SAMPLES:
+            trio[s][0][:3000] = ord("A")
+            trio[s][2][:1500, 0::2] = ord("A")
+            trio[s][2][:1500, 1::2] = ord("C")
     ctx = api.Context(local)
     ctx.use_stream(torch.cuda.current_stream().cuda_stream)
     streams = [torch.from_numpy(np.concatenate([trio[s][0], trio[s][2]]).reshape(-1)).to(dev) for s in synth.SAMPLES]
