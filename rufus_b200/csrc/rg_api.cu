@@ -908,16 +908,16 @@ int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint6
   }
   rg_ctx* ctx = t->ctx;
   const uint64_t nb = rg_histo_rows(low, high);
-  uint64_t* d_out = nullptr;
-  RG_CUDA_OK(cudaMalloc(&d_out, nb * 8));
   int rc = rg_table_finish(t);
-  if (rc == 0) rc = rg_launch_histo(t, min_count, histo_base(low), nb, d_out);
+  if (rc == 0) rc = pool_ensure(ctx, 5, nb * 8);
+  if (rc) return rc;
+  uint64_t* d_out = static_cast<uint64_t*>(ctx->pool[5]);
+  rc = rg_launch_histo(t, min_count, histo_base(low), nb, d_out);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(out_host, d_out, nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { rg_set_error(cudaGetErrorString(e)); rc = RG_ERR_CUDA; }
   }
-  cudaFree(d_out);
   return rc;
 }
 
@@ -1261,11 +1261,12 @@ rg_set* rg_set_from_jf_keys_dev(rg_ctx* ctx, const uint64_t* jf_keys_dev, uint64
   uint64_t* d = nullptr;
   int rc = 0;
   if (n) {
-    if (cudaMalloc(&d, 2 * n * 8) != cudaSuccess) {
-      rg_set_error("rg_set: out of device memory");
+    rc = pool_ensure(ctx, 5, 2 * n * 8);      // scratch: the 2n rufus keys (k-mer + reverse complement)
+    if (rc) {
       rg_set_free(s);
       return nullptr;
     }
+    d = static_cast<uint64_t*>(ctx->pool[5]);
     rc = rg_launch_jf_to_rufus(ctx, jf_keys_dev, n, k, d);
   }
   // k == 32: poly-A's reverse complement is the all-ones rufus key; canonical jf key 0 marks it
@@ -1277,8 +1278,6 @@ rg_set* rg_set_from_jf_keys_dev(rg_ctx* ctx, const uint64_t* jf_keys_dev, uint64
       if (h[i] == 0) s->has_all_ones = 1;
   }
   if (rc == 0) rc = set_finish(s, d, 2 * n);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(d);
   if (rc) {
     rg_set_free(s);
     return nullptr;
