@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs/sample of the CPU baseline sample")
     ap.add_argument("--mode", default="tiled", choices=["tiled", "direct"])
+    ap.add_argument("--est-scale", type=float, default=1.0, help="scale the distinct k-mer estimate (table load factor)")
     ap.add_argument("--p2p-groups", type=int, default=0, help="hash-prefix groups per shard of the peer-to-peer partition")
     ap.add_argument("--scatter-ctas", type=int, default=0,
                     help="CTAs of the (NVLink-bound) peer-to-peer scatter when it overlaps the previous sample's inserts")
@@ -263,7 +264,7 @@ def main():
     subj = tuple(torch.from_numpy(a.reshape(-1)).to(dev) for a in trio["Child"])
     bases_per_step = sum(int(s.numel()) for s in streams)
     # distinct k-mers per shard: genomic (two haplotypes, ~3 % private) / world + ~6.2 error k-mers per read
-    est = int((1.03 * args.genome) / world + 6.2 * 2 * args.pairs)
+    est = int(((1.03 * args.genome) / world + 6.2 * 2 * args.pairs) * args.est_scale)
     pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, 150 * world, MINQ, THRESH,
                                    mode=mode, rank=rank, world=world, exchange=args.exchange,
                                    groups_per_shard=args.p2p_groups, scatter_ctas=args.scatter_ctas)

@@ -105,8 +105,9 @@ class DevicePipeline:
             self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
             self.flag2 = torch.zeros(1, dtype=torch.int32, device=dev)
             self.scatter_stream = torch.cuda.Stream(device=dev)
-            # measured: 96 CTAs at N=2 (the scatter is still close to compute-bound), 64 beyond (NVLink-bound)
-            self.scatter_ctas = scatter_ctas or (96 if world <= 2 else 64)
+            # measured: N=2 96 CTAs (118.9 vs 113.4 Gbases/s without overlap); N=8 full grid 320 > 64: 306 >
+            # 48: 280 ~ 96: 279 > 32: 203 (0 = one CTA per SM: the two streams interleave by themselves)
+            self.scatter_ctas = scatter_ctas or (96 if world <= 2 else 0)
             n_keys = max(int(s.numel()) for s in streams)      # weak scaling: a shard receives ~ what it sends
             # fewer, longer runs travel better over NVLink (measured: N=2 37 groups/shard, N=8 16 > 37 > 74)
             groups_per_shard = groups_per_shard or (37 if world <= 2 else max(8, 128 // world))
