@@ -42,3 +42,31 @@ def load_case(case):
 
 def both_mates(pair):
     return fastq.concat(pair[0], pair[1])
+
+
+def overlap_fuzz_input(seed: int, n_reads: int = 70) -> str:
+    """a small random .fastqd: reads of a 1.5 kb genome on both strands, 1 % substitutions, 0.5 % N,
+    30 % of the reads with per-base depths in {1,2,3,7} (end trimming), strand strings of 1-3 of + - ."""
+    import random
+    rnd = random.Random(seed)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    genome = "".join(rnd.choice("ACGT") for _ in range(1500))
+    recs = []
+    for i in range(n_reads):
+        L = rnd.randint(60, 160)
+        p = rnd.randint(0, len(genome) - L)
+        s = list(genome[p:p + L])
+        for j in range(L):
+            r = rnd.random()
+            if r < 0.01:
+                s[j] = rnd.choice("ACGT")
+            elif r < 0.015:
+                s[j] = "N"
+        s = "".join(s)
+        if rnd.random() < 0.5:
+            s = "".join(comp[c] for c in reversed(s))
+        q = "".join(rnd.choice("#,5AFJ") for _ in range(L))
+        d = [rnd.choice([1, 1, 2, 3, 7]) for _ in range(L)] if rnd.random() < 0.3 else [1] * L
+        st = "".join(rnd.choice("+-.") for _ in range(rnd.randint(1, 3)))
+        recs.append(f"@r{i}\n{s}\n+\n{q}\n{st}\n{' '.join(map(str, d))}\n")
+    return "".join(recs)

@@ -125,3 +125,41 @@ def test_annotate_matches_reference_annotate_overlap():
     names = [n.decode() for n in r.names]
     text = "".join(f"{names[i]}:MH0\n{bytes(r.seq[int(r.offs[i]):int(r.offs[i+1])]).decode()}\n+\n{got[i]}\n" for i in range(len(r)))
     assert hashlib.md5(text.encode()).hexdigest() == g["stdout_md5"]
+
+
+def test_overlap_oracle_matches_reference_overlap():
+    """oracle/overlap_oracle.py (greedy assembly, SURVEY §8a O1-O5: the next row to build) vs the outputs of the
+    reference Overlap binary for the three rounds of Overlap.shorter.sh:141,153,165 (tests/golden/overlap)"""
+    import json
+    import overlap_oracle as oo
+    d = os.path.join(GOLDEN, "overlap")
+    g = json.load(open(os.path.join(d, "golden.json")))
+    for a in g["rounds"]:
+        text = open(os.path.join(d, a[0])).read()
+        fq, fqd, _ = oo.overlap(text, a[1], int(a[2]), int(a[3]), int(a[5]), int(a[6]), int(a[8]), a[5], int(a[9]))
+        assert fqd == open(os.path.join(d, a[7] + ".fastqd")).read(), a
+        assert fq == open(os.path.join(d, a[7] + ".fastq")).read(), a
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Overlap")),
+                    reason="reference binaries (oracle/_ref) not present")
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_overlap_oracle_differential_vs_reference_binary(seed, tmp_path):
+    """random overlapping reads (both strands, substitutions, N, depths > 1 that trigger end trimming, mixed
+    strand strings) through the reference binary and the restatement. Depth 0 is left out: the reference
+    reverses depth strings with Util::RevQual, which drops NUL bytes, and then indexes past the end."""
+    import random
+    import subprocess
+    import overlap_oracle as oo
+    from cases import overlap_fuzz_input
+    text = overlap_fuzz_input(seed)
+    args = [[".98", "100", "1", "FP", "20", "1", "o", "0", "1"], [".95", "40", "1", "FP", "20", "1", "o", "1", "1"],
+            [".9", "30", "2", "X", "15", "2", "o", "2", "1"]][seed % 3]
+    open(tmp_path / "in.fastqd", "w").write(text)
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "Overlap"), "in.fastqd", *args], cwd=tmp_path, check=True,
+                   stdout=subprocess.DEVNULL)
+    fq, fqd, bad = oo.overlap(text, args[0], int(args[1]), int(args[2]), int(args[4]), int(args[5]), int(args[7]),
+                              args[4], 1)
+    assert fqd == open(tmp_path / "o.fastqd").read()
+    assert fq == open(tmp_path / "o.fastq").read()
+    assert bad == open(tmp_path / "o.fastqbad.fastq").read()
