@@ -254,6 +254,33 @@ int rg_annotate(rg_set* s, const char* seq, const char* qual, const uint64_t* of
 int rg_filter_single(rg_set* s, const char* seq, const char* qual, const uint64_t* offs, uint64_t n_reads,
                      int minq, int32_t* hits_host);
 
+/* ---- O2-O4: the device side of the greedy overlap assembly (src/Overlap.cpp) -----------
+ * The greedy loop is serial and stays with the caller (tools/overlap.cpp); the seed index, the
+ * seed lookups and the Align3 placement search run on the GPU.
+ *  rg_overlap_build     O2, RebuildHashTable (:34-76): load the reads, index the SearchHash-mers
+ *                       (and their reverse complements) of reads >= first
+ *  rg_overlap_update    a merge replaced read idx by a contig (:1066-1070); the index is not
+ *                       updated, like the reference's (:1083,:1101)
+ *  rg_overlap_seed_hits O3 lookups of PrepairSearchList (:78-103): per query, the read indices
+ *                       > q_ai[q] that share a seed, one entry per shared occurrence
+ *  rg_overlap_align     O4, Align3 (:169-360): A against the current sequence of every candidate.
+ *                       Per candidate: best of the "shorter inside longer" placements (score1,
+ *                       overlap1, perfect1) and best over all three placement families
+ *                       (score_all, overlap_all); -1 = nothing accepted. The caller applies the
+ *                       PerfectMatch short-circuit across candidates (see tools/overlap.cpp). */
+typedef struct rg_overlap rg_overlap;
+typedef struct rg_align_result {
+  int32_t score1, overlap1, perfect1, score_all, overlap_all;
+} rg_align_result;
+rg_overlap* rg_overlap_create(rg_ctx* ctx, int search_hash);
+void rg_overlap_free(rg_overlap* ov);
+int rg_overlap_build(rg_overlap* ov, const char* seq, const uint64_t* offs, uint64_t n_reads, uint64_t first);
+int rg_overlap_update(rg_overlap* ov, uint64_t idx, const char* seq, uint64_t len);
+int64_t rg_overlap_seed_hits(rg_overlap* ov, const char* qseq, const uint64_t* qoffs, const uint64_t* q_ai, uint64_t nq,
+                             uint32_t* hits_host, uint64_t cap, uint64_t* hit_offs_host);
+int rg_overlap_align(rg_overlap* ov, const char* a, uint64_t a_len, const uint32_t* cand, uint64_t n_cand,
+                     float min_percent, int min_overlap, rg_align_result* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,12 @@ def lib():
         "rg_filter_pairs_fixed_dev": (i32, [vp, vp, vp, vp, vp, u32, u64, i32, i32, vp, vp, vp]),
         "rg_filter_pairs": (i32, [vp, vp, vp, vp, vp, vp, vp, u64, i32, i32, vp]),
         "rg_filter_single": (i32, [vp, vp, vp, vp, u64, i32, vp]),
+        "rg_overlap_create": (vp, [vp, i32]),
+        "rg_overlap_free": (None, [vp]),
+        "rg_overlap_build": (i32, [vp, vp, vp, u64, u64]),
+        "rg_overlap_update": (i32, [vp, u64, vp, u64]),
+        "rg_overlap_seed_hits": (i64, [vp, vp, vp, vp, u64, vp, u64, vp]),
+        "rg_overlap_align": (i32, [vp, vp, u64, vp, u64, C.c_float, i32, vp]),
         "rg_annotate": (i32, [vp, vp, vp, vp, u64, i32, vp]),
     }
     for name, (res, args) in sig.items():

@@ -167,3 +167,42 @@ def test_annotate_overlap_matches_reference_golden(tmp_path):
                          str(tmp_path / "hash2.out")], input=open(os.path.join(d, "reads.fastq"), "rb").read(),
                         capture_output=True, check=True)
     assert r2.stdout == r.stdout
+
+
+def test_overlap_matches_reference_goldens(tmp_path):
+    """tools/bin/Overlap (greedy assembly; seed index, seed lookups and Align3 on the GPU) on the three rounds of
+    Overlap.shorter.sh:141,153,165 vs the committed outputs of the reference binary (tests/golden/overlap)"""
+    import json
+    d = os.path.join(GOLDEN, "overlap")
+    g = json.load(open(os.path.join(d, "golden.json")))
+    work = str(tmp_path)
+    shutil.copy(os.path.join(d, "in.sam.fastqd"), work)
+    for a in g["rounds"]:
+        sh(f"{BIN}/Overlap " + " ".join(a), work)       # each round reads the previous round's OUR output
+        for ext in (".fastqd", ".fastq"):
+            assert open(os.path.join(work, a[7] + ext)).read() == open(os.path.join(d, a[7] + ext)).read(), (a, ext)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_overlap_fuzz_matches_oracle(tmp_path, seed):
+    """random overlapping reads (both strands, substitutions, N, depths > 1, mixed strand strings): our Overlap vs
+    the oracle restatement (itself pinned to the reference binary, tests/test_oracle.py), and vs the binary when present"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import overlap_oracle as oo
+    from cases import overlap_fuzz_input
+    text = overlap_fuzz_input(seed, n_reads=90)
+    args = [[".98", "100", "1", "FP", "20", "1", "o", "0", "1"], [".95", "40", "1", "FP", "20", "1", "o", "1", "1"],
+            [".9", "30", "2", "X", "15", "2", "o", "2", "1"]][seed % 3]
+    open(tmp_path / "in.fastqd", "w").write(text)
+    sh(f"{BIN}/Overlap in.fastqd " + " ".join(args), str(tmp_path))
+    fq, fqd, bad = oo.overlap(text, args[0], int(args[1]), int(args[2]), int(args[4]), int(args[5]), int(args[7]), args[4], 1)
+    assert open(tmp_path / "o.fastqd").read() == fqd
+    assert open(tmp_path / "o.fastq").read() == fq
+    assert open(tmp_path / "o.fastqbad.fastq").read() == bad
+    ref = os.path.join(ROOT, "oracle", "_ref", "Overlap")
+    if os.path.exists(ref):
+        os.makedirs(tmp_path / "ref")
+        shutil.copy(tmp_path / "in.fastqd", tmp_path / "ref")
+        sh(f"{ref} in.fastqd " + " ".join(args), str(tmp_path / "ref"))
+        assert open(tmp_path / "ref" / "o.fastqd").read() == fqd
