@@ -149,16 +149,6 @@ void rg_set_error(const std::string& msg);
 // ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint64_t rg_mix64(uint64_t h) {
-  // murmur3 fmix64 — a bijection on 64 bits
-  h ^= h >> 33;
-  h *= 0xff51afd7ed558ccdull;
-  h ^= h >> 33;
-  h *= 0xc4ceb9fe1a85ec53ull;
-  h ^= h >> 33;
-  return h;
-}
-
 // table hash: two 32-bit multiply-adds (both on the FMA pipe, nothing on the integer ALU pipe that the
 // extraction saturates). Checked against the previous xor-shift-multiply hash on real k-mer sets: same
 // tile-load variance (Poisson) and the same mean probe length (profiles/README.md).

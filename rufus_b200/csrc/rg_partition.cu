@@ -6,14 +6,12 @@
 // shared-memory atomics are cheap (0.14 cyc/lane/SM), MATCH.ANY is not (2 cyc/lane),
 // and per-key 8-byte scattered global stores are the wall (a write footprint of
 // (#CTAs x #buckets) open lines overflows L2). So the CTA counting-sorts a
-// SUPER-CHUNK of windows in shared memory and writes each bucket's keys as ONE
-// contiguous, 32-byte-aligned run:
-//   1. extract keys -> ukeys[] (smem), histogram the bucket ids (ATOMS)
-//   2. block scan -> local offsets; one global atomicAdd per non-empty bucket reserves
-//      a run rounded up to 4 keys (a full 32-byte sector)
-//   3. place window indices into spos[] in bucket order (ATOMS rank)
-//   4. half-warp per bucket copies its run out; the pad slots get RG_EMPTY (the tile
-//      insert skips them), so every global write is a fully covered sector.
+// SUPER-CHUNK of 16384 windows in shared memory and writes each bucket's keys as ONE
+// contiguous run (see partition_sorted_kernel for the four steps). The same kernel body
+// serves three sources (ASCII stream, key list, the group slabs of a first pass) and
+// three destinations (tile buckets, group slabs, the group slabs of OTHER GPUs over
+// NVLink peer memory): small tables take one pass, tables beyond ~2900 tiles two
+// (stream -> hash-prefix groups -> tiles), multi-GPU counting uses the first pass to route.
 #include "rg_extract.cuh"
 
 #ifndef PART_CTAS

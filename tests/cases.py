@@ -44,13 +44,13 @@ def both_mates(pair):
     return fastq.concat(pair[0], pair[1])
 
 
-def overlap_fuzz_input(seed: int, n_reads: int = 70) -> str:
+def overlap_fuzz_input(seed: int, n_reads: int = 70, genome_len: int = 1500) -> str:
     """a small random .fastqd: reads of a 1.5 kb genome on both strands, 1 % substitutions, 0.5 % N,
     30 % of the reads with per-base depths in {1,2,3,7} (end trimming), strand strings of 1-3 of + - ."""
     import random
     rnd = random.Random(seed)
     comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
-    genome = "".join(rnd.choice("ACGT") for _ in range(1500))
+    genome = "".join(rnd.choice("ACGT") for _ in range(genome_len))
     recs = []
     for i in range(n_reads):
         L = rnd.randint(60, 160)
