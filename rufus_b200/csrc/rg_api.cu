@@ -425,14 +425,8 @@ static int finish_tiled_push(rg_table* t) {
   return rc;
 }
 
-static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
-                         const uint32_t* brk) {
-  rg_ctx* ctx = t->ctx;
-  if (n_bytes == 0) return 0;
-  if (((uintptr_t)dev_stream & 15) != 0) {
-    rg_set_error("count: device stream must be 16-byte aligned");
-    return RG_ERR_ARG;
-  }
+static int push_dev_piece(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
+                          const uint32_t* brk, uint32_t skip) {
   ExtractParams ep;
   ep.stream = dev_stream;
   ep.n_bytes = n_bytes;
@@ -440,6 +434,7 @@ static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, 
   ep.read_stride = read_stride;
   ep.k = t->k;
   ep.canonical = t->canonical;
+  ep.skip = skip;
   int rc;
   if (t->mode == RG_MODE_TILED) {
     rc = prepare_buckets(t, n_bytes);
@@ -453,7 +448,44 @@ static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, 
     if (rc) return rc;
   }
   t->tiles_dirty = true;
-  t->unchecked = true;      // status words are read back by table_finish (rg_count_end or the first reader)
+  t->unchecked = true;      // status words are read back by rg_table_finish (rg_count_end or the first reader)
+  return 0;
+}
+
+// A push larger than RG_PUSH_SPLIT bytes is counted in pieces (the bucket slabs are indexed with 32
+// bits). Fixed-stride input is cut at read boundaries; otherwise a piece starts 32 bytes early (the
+// stream pointer and the read-start bitmap stay aligned) and skips the windows that start inside that
+// halo and were counted with the previous piece — except those reaching into the new bytes.
+static uint64_t g_push_split = 1ull << 31;
+static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
+                         const uint32_t* brk) {
+  if (n_bytes == 0) return 0;
+  if (((uintptr_t)dev_stream & 15) != 0 || read_stride >= (1u << 31)) {
+    rg_set_error("count: device stream must be 16-byte aligned (and read_stride < 2^31)");
+    return RG_ERR_ARG;
+  }
+  if (const char* e = getenv("RG_PUSH_SPLIT")) g_push_split = std::max<uint64_t>(4096, strtoull(e, nullptr, 10));
+  if (n_bytes <= g_push_split) return push_dev_piece(t, dev_stream, n_bytes, read_stride, brk, 0);
+  if (read_stride) {
+    // pieces of whole reads whose starts stay 16-byte aligned: multiples of lcm(stride, 16)
+    uint64_t unit = read_stride;
+    while (unit % 16) unit += read_stride;
+    const uint64_t piece = std::max<uint64_t>(unit, g_push_split / unit * unit);
+    for (uint64_t off = 0; off < n_bytes; off += piece) {
+      const int rc = push_dev_piece(t, dev_stream + off, std::min(piece, n_bytes - off), read_stride, nullptr, 0);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  const uint64_t piece = g_push_split & ~31ull;
+  for (uint64_t off = 0; off < n_bytes; off += piece) {
+    const uint64_t halo = off ? 32 : 0;
+    // windows starting at halo positions < 32-(k-1) lie entirely in the previous piece
+    const uint32_t skip = off ? (uint32_t)(32 - (t->k - 1)) : 0u;
+    const int rc = push_dev_piece(t, dev_stream + off - halo, std::min(piece, n_bytes - off) + halo, 0,
+                                  brk ? brk + (off - halo) / 32 : nullptr, t->k - 1 >= 32 ? 0u : skip);
+    if (rc) return rc;
+  }
   return 0;
 }
 

@@ -33,7 +33,7 @@ count_direct_kernel(ExtractParams ep, TableView tv, uint64_t* status, uint64_t* 
       } else if (rc == 2) {
         atomicAdd((unsigned long long*)&status[1], 1ull);
       }
-    });
+    }, c == 0 ? ep.skip : 0u);
   }
 }
 

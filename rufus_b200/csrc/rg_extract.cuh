@@ -115,14 +115,17 @@ __device__ __forceinline__ uint64_t reverse_groups(uint64_t x) {
 
 // Thread `t` rolls through its R windows (starting at local bases t*R .. t*R+R-1) and calls
 // emit(w, key) for w = 0..R-1 with key == RG_EMPTY when the window holds no k-mer.
+// skip_local: windows starting before this chunk-local position are dropped (first chunk of a split push)
 template <int NT, int R, typename Emit>
-__device__ __forceinline__ void roll_windows(const StageT<NT, R>& sm, int t, int k, int canonical, Emit&& emit) {
+__device__ __forceinline__ void roll_windows(const StageT<NT, R>& sm, int t, int k, int canonical, Emit&& emit,
+                                             uint32_t skip_local = 0) {
   const int p0 = t * R;
   // validity of each of the R windows: k good bases and no read start strictly inside
   const uint64_t good = ~bits_at(sm.bad, p0);
   const uint64_t nobrk = ~bits_at(sm.brk, p0 + 1);          // bit j: no read starts at base p0+j+1
   uint64_t valid = and_run(good, k);
   if (k > 1) valid &= and_run(nobrk, k - 1);
+  if ((uint32_t)p0 < skip_local) valid &= ~((skip_local - p0 >= 64u) ? ~0ull : ((1ull << (skip_local - p0)) - 1ull));
   // little-endian window X (base i at bits 2i): rc (Jellyfish order) = ~X, fwd = reverse of X
   const int j = p0 >> 4, sh = (p0 & 15) * 2;
   uint64_t lo = ((uint64_t)sm.codes[j + 1] << 32) | sm.codes[j];

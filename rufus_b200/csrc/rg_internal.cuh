@@ -266,6 +266,7 @@ struct ExtractParams {
   uint32_t read_stride;    // optional fixed read stride
   int k;
   int canonical;
+  uint32_t skip = 0;       // windows starting before this position are not emitted (the halo of a split push)
 };
 
 // read back the status words of the enqueued pushes and resolve spills (every reader calls it first)

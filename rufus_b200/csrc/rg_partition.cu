@@ -211,7 +211,8 @@ __device__ __forceinline__ void part_stage_store(PartStage& sm, const PartPrefet
 // two funnel shifts + one mask per strand (the low word needs no mask), a 64-bit compare and a
 // select: 10 integer-ALU instructions. k <= 16 takes the generic path.
 template <typename Emit>
-__device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, int canonical, Emit&& emit) {
+__device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, int canonical, Emit&& emit,
+                                             uint32_t skip_local = 0) {
   const int p0 = t * PART_R;
   const uint64_t good = ~bits_at(sm.bad, p0);
   const uint64_t nobrk = ~bits_at(sm.brk, p0 + 1);          // bit j: no read starts at base p0+j+1
@@ -219,7 +220,9 @@ __device__ __forceinline__ void part_windows(const PartStage& sm, int t, int k, 
   if (k > 1) valid &= and_run(nobrk, k - 1);
   const uint32_t W0 = sm.fwd[t], W1 = sm.fwd[t + 1], W2 = sm.fwd[t + 2];
   const uint32_t V0 = sm.rcw[t], V1 = sm.rcw[t + 1], V2 = sm.rcw[t + 2];
-  const uint32_t valid16 = (uint32_t)valid;
+  uint32_t valid16 = (uint32_t)valid;
+  // first super-chunk of a split push: the windows that start inside the halo belong to the previous piece
+  if ((uint32_t)p0 < skip_local) valid16 &= ~((skip_local - p0 >= 32u) ? 0xFFFFFFFFu : ((1u << (skip_local - p0)) - 1u));
   if (k > 16) {
     const int down = 64 - 2 * k;                            // 0..30
     const uint32_t himask = (k == 32) ? 0xFFFFFFFFu : ((1u << (2 * k - 32)) - 1u);
@@ -385,7 +388,7 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_a
 #pragma unroll
       for (int w = 0; w < PART_R; ++w) take(w, kk[w], kk[w] != RG_EMPTY);
     } else {
-      part_windows(sm, threadIdx.x, ep.k, ep.canonical, take);
+      part_windows(sm, threadIdx.x, ep.k, ep.canonical, take, s0 == 0 ? ep.skip : 0u);
     }
     if (SHARDED && foreign) atomicAdd((unsigned long long*)&g.status[1], (unsigned long long)foreign);
     __syncthreads();
@@ -528,7 +531,7 @@ partition_scatter_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys,
       __syncthreads();
       roll_windows(sm, threadIdx.x, ep.k, ep.canonical, [&](int, uint64_t key) {
         if (key != RG_EMPTY) put(key);
-      });
+      }, c == 0 ? ep.skip : 0u);
     }
   }
 }

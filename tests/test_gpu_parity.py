@@ -275,3 +275,42 @@ def test_two_level_partition_growth_and_heavy_hitters(monkeypatch):
         t.free()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_split_device_pushes(ctx, mode, monkeypatch):
+    """device pushes beyond RG_PUSH_SPLIT bytes are counted in pieces: whole reads for fixed-stride input, a 32-byte
+    halo whose already-counted windows are skipped otherwise. Same table as one push."""
+    import torch
+    monkeypatch.setenv("RG_PUSH_SPLIT", "70000")
+    trio, _ = synth.make_trio(41, 60_000, 3_000)
+    s1, _, s2, _ = trio["Child"]
+    both = np.concatenate([s1, s2])                                        # [6000, 150]
+    offs = np.arange(both.shape[0] + 1, dtype=np.uint64) * 150
+    okeys, ocounts = oracle.count(both.reshape(-1), offs, 25, True, 1)
+    dev = torch.device("cuda", 0)
+    # (a) fixed stride, no separators
+    t = api.KmerTable(ctx, 25, True, 2_000_000, mode)
+    flat = torch.from_numpy(both.reshape(-1).copy()).to(dev)
+    t.push_dev(flat, flat.numel(), 150)
+    t.end()
+    keys, counts = t.dump(min_count=1)
+    assert np.array_equal(keys, okeys) and np.array_equal(counts, ocounts)
+    t.free()
+    # (b) separator-delimited stream (151-byte rows): pieces cut anywhere, windows across the cut counted once
+    t = api.KmerTable(ctx, 25, True, 2_000_000, mode)
+    rows = np.concatenate([both, np.full((both.shape[0], 1), 10, np.uint8)], axis=1).reshape(-1)
+    stream = torch.from_numpy(rows.copy()).to(dev)
+    t.push_dev(stream, stream.numel(), 0)
+    t.end()
+    keys, counts = t.dump(min_count=1)
+    assert np.array_equal(keys, okeys) and np.array_equal(counts, ocounts)
+    t.free()
+    # (c) one long read without separators: every cut is inside a run of k-mers
+    t = api.KmerTable(ctx, 25, True, 2_000_000, mode)
+    t.push_dev(flat, flat.numel(), 0)
+    t.end()
+    keys, counts = t.dump(min_count=1)
+    k2, c2 = oracle.count(both.reshape(-1), np.array([0, both.size], np.uint64), 25, True, 1)
+    assert np.array_equal(keys, k2) and np.array_equal(counts, c2)
+    t.free()
