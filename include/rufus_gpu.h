@@ -280,6 +280,10 @@ int64_t rg_overlap_seed_hits(rg_overlap* ov, const char* qseq, const uint64_t* q
                              uint32_t* hits_host, uint64_t cap, uint64_t* hit_offs_host);
 int rg_overlap_align(rg_overlap* ov, const char* a, uint64_t a_len, const uint32_t* cand, uint64_t n_cand,
                      float min_percent, int min_overlap, rg_align_result* out_host);
+/* the read and its reverse complement (same length) against their two candidate lists in one launch */
+int rg_overlap_align_both(rg_overlap* ov, const char* a, const char* a_rev, uint64_t a_len, const uint32_t* cand,
+                          uint64_t n_cand, const uint32_t* cand_rev, uint64_t n_cand_rev, float min_percent,
+                          int min_overlap, rg_align_result* out_host, rg_align_result* out_rev_host);
 
 #ifdef __cplusplus
 }

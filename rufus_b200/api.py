@@ -117,6 +117,7 @@ def lib():
         "rg_overlap_update": (i32, [vp, u64, vp, u64]),
         "rg_overlap_seed_hits": (i64, [vp, vp, vp, vp, u64, vp, u64, vp]),
         "rg_overlap_align": (i32, [vp, vp, u64, vp, u64, C.c_float, i32, vp]),
+        "rg_overlap_align_both": (i32, [vp, vp, vp, u64, vp, u64, vp, u64, C.c_float, i32, vp, vp]),
         "rg_annotate": (i32, [vp, vp, vp, vp, u64, i32, vp]),
     }
     for name, (res, args) in sig.items():

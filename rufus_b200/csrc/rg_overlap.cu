@@ -44,6 +44,9 @@ struct rg_overlap {
   uint64_t d_query_cap = 0;
   void* d_misc = nullptr;
   uint64_t d_misc_cap = 0;
+  // pinned staging of one align call: [A | rc(A) | candidates] up, results down
+  char* h_stage = nullptr;
+  uint64_t h_stage_cap = 0;
 };
 
 #define OV_INVALID 0xFFFFFFFFFFFFFFFFull
@@ -149,8 +152,10 @@ constexpr int OV_THREADS = 128;
 
 __global__ void __launch_bounds__(OV_THREADS)
 ov_align_kernel(const char* __restrict__ arena, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
-                const char* __restrict__ A, int alen, const uint32_t* __restrict__ cand, float minp, int min_overlap,
-                rg_align_result* __restrict__ out) {
+                const char* __restrict__ A0, const char* __restrict__ A1, uint32_t n_first, int alen,
+                const uint32_t* __restrict__ cand, float minp, int min_overlap, rg_align_result* __restrict__ out) {
+  // candidates [0, n_first) are aligned against A0 (the read), the rest against A1 (its reverse complement)
+  const char* __restrict__ A = blockIdx.x < n_first ? A0 : A1;
   const uint32_t j = cand[blockIdx.x];
   const char* B = arena + off[j];
   const int blen = (int)len[j];
@@ -248,6 +253,7 @@ void rg_overlap_free(rg_overlap* ov) {
   cudaFree(ov->owners);
   cudaFree(ov->d_query);
   cudaFree(ov->d_misc);
+  cudaFreeHost(ov->h_stage);
   delete ov;
 }
 
@@ -350,7 +356,7 @@ int rg_overlap_update(rg_overlap* ov, uint64_t idx, const char* seq, uint64_t le
   RG_CUDA_OK(cudaMemcpyAsync(ov->off + idx, &ov->h_off[idx], 8, cudaMemcpyHostToDevice, ctx->stream));
   RG_CUDA_OK(cudaMemcpyAsync(ov->len + idx, &ov->h_len[idx], 4, cudaMemcpyHostToDevice, ctx->stream));
   ov->arena_used += len;
-  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));      // the host buffers above may go away
+  // (pageable sources are staged by the runtime before cudaMemcpyAsync returns: no synchronisation needed)
   return 0;
 }
 
@@ -416,33 +422,63 @@ int64_t rg_overlap_seed_hits(rg_overlap* ov, const char* qseq, const uint64_t* q
   return (int64_t)total;
 }
 
-// O4: A against the CURRENT sequences of the candidate reads
-int rg_overlap_align(rg_overlap* ov, const char* a, uint64_t a_len, const uint32_t* cand, uint64_t n_cand,
-                     float min_percent, int min_overlap, rg_align_result* out_host) {
-  if (!ov || (n_cand && (!a || !cand || !out_host)) || a_len >= 0x7FFFFFFFull) return RG_ERR_ARG;
-  if (n_cand == 0) return 0;
+// O4: A (and optionally its reverse complement) against the CURRENT sequences of the candidate reads,
+// one launch and one synchronisation for both strands
+int rg_overlap_align_both(rg_overlap* ov, const char* a, const char* a_rev, uint64_t a_len, const uint32_t* cand,
+                          uint64_t n_cand, const uint32_t* cand_rev, uint64_t n_cand_rev, float min_percent,
+                          int min_overlap, rg_align_result* out_host, rg_align_result* out_rev_host) {
+  const uint64_t n_all = n_cand + n_cand_rev;
+  if (!ov || a_len >= 0x7FFFFFFFull || (n_cand && (!a || !cand || !out_host)) ||
+      (n_cand_rev && (!a_rev || !cand_rev || !out_rev_host)))
+    return RG_ERR_ARG;
+  if (n_all == 0) return 0;
   rg_ctx* ctx = ov->ctx;
-  for (uint64_t c = 0; c < n_cand; ++c)
-    if (cand[c] >= ov->n_reads) {
+  for (uint64_t c = 0; c < n_all; ++c)
+    if ((c < n_cand ? cand[c] : cand_rev[c - n_cand]) >= ov->n_reads) {
       rg_set_error("rg_overlap_align: candidate index out of range");
       return RG_ERR_ARG;
     }
-  int rc = ov_reserve((void**)&ov->d_query, &ov->d_query_cap, a_len + 16, ctx);
-  if (rc == 0) rc = ov_reserve(&ov->d_misc, &ov->d_misc_cap, n_cand * (4 + sizeof(rg_align_result)) + 64, ctx);
+  // one staged upload [A | rc(A) | candidates] and one staged download per call
+  const uint64_t a_pad = (a_len + 63) & ~63ull;
+  const uint64_t up_bytes = 2 * a_pad + ((n_all * 4 + 63) & ~63ull), down_bytes = n_all * sizeof(rg_align_result);
+  int rc = ov_reserve(&ov->d_misc, &ov->d_misc_cap, up_bytes + down_bytes, ctx);
   if (rc) return rc;
-  uint32_t* d_cand = static_cast<uint32_t*>(ov->d_misc);
-  rg_align_result* d_out = reinterpret_cast<rg_align_result*>(static_cast<char*>(ov->d_misc) + ((n_cand * 4 + 63) & ~63ull));
-  RG_CUDA_OK(cudaMemcpyAsync(ov->d_query, a, a_len, cudaMemcpyHostToDevice, ctx->stream));
-  RG_CUDA_OK(cudaMemcpyAsync(d_cand, cand, n_cand * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (ov->h_stage_cap < up_bytes + down_bytes) {
+    RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFreeHost(ov->h_stage);
+    ov->h_stage = nullptr;
+    ov->h_stage_cap = 0;
+    const uint64_t want = 2 * (up_bytes + down_bytes) + 4096;
+    RG_CUDA_OK(cudaMallocHost(&ov->h_stage, want));
+    ov->h_stage_cap = want;
+  }
+  char* h_up = ov->h_stage;
+  if (n_cand) memcpy(h_up, a, a_len);
+  if (n_cand_rev) memcpy(h_up + a_pad, a_rev, a_len);
+  if (n_cand) memcpy(h_up + 2 * a_pad, cand, n_cand * 4);
+  if (n_cand_rev) memcpy(h_up + 2 * a_pad + n_cand * 4, cand_rev, n_cand_rev * 4);
+  char* d_up = static_cast<char*>(ov->d_misc);
+  rg_align_result* d_out = reinterpret_cast<rg_align_result*>(d_up + up_bytes);
+  rg_align_result* h_out = reinterpret_cast<rg_align_result*>(ov->h_stage + up_bytes);
+  RG_CUDA_OK(cudaMemcpyAsync(d_up, h_up, up_bytes, cudaMemcpyHostToDevice, ctx->stream));
   {
     rg_launch_scope _ls(ctx, "ov_align_kernel");
-    ov_align_kernel<<<(unsigned)n_cand, OV_THREADS, 0, ctx->stream>>>(ov->arena, ov->off, ov->len, ov->d_query, (int)a_len,
-                                                                     d_cand, min_percent, min_overlap, d_out);
+    ov_align_kernel<<<(unsigned)n_all, OV_THREADS, 0, ctx->stream>>>(
+        ov->arena, ov->off, ov->len, d_up, d_up + a_pad, (uint32_t)n_cand, (int)a_len,
+        reinterpret_cast<const uint32_t*>(d_up + 2 * a_pad), min_percent, min_overlap, d_out);
   }
-  RG_CUDA_OK(cudaMemcpyAsync(out_host, d_out, n_cand * sizeof(rg_align_result), cudaMemcpyDeviceToHost, ctx->stream));
+  RG_CUDA_OK(cudaMemcpyAsync(h_out, d_out, down_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   RG_CUDA_OK(cudaGetLastError());
+  if (n_cand) memcpy(out_host, h_out, n_cand * sizeof(rg_align_result));
+  if (n_cand_rev) memcpy(out_rev_host, h_out + n_cand, n_cand_rev * sizeof(rg_align_result));
   return 0;
+}
+
+int rg_overlap_align(rg_overlap* ov, const char* a, uint64_t a_len, const uint32_t* cand, uint64_t n_cand,
+                     float min_percent, int min_overlap, rg_align_result* out_host) {
+  return rg_overlap_align_both(ov, a, nullptr, a_len, cand, n_cand, nullptr, 0, min_percent, min_overlap, out_host,
+                               nullptr);
 }
 
 }  // extern "C"

@@ -215,15 +215,13 @@ int main(int argc, char** argv) {
     }
   };
 
-  // O4 over a candidate list, with the PerfectMatch short-circuit in candidate order (:203-345):
+  // O4 results of one candidate list, with the PerfectMatch short-circuit in candidate order (:203-345):
   // once a candidate has a perfect "inside" placement, the suffix/prefix searches are skipped for it
   // and for every later candidate
-  std::vector<rg_align_result> res;
-  auto align = [&](const std::string& a, const std::vector<uint32_t>& cand, bool& perfect, int& best_index, int& offset) {
+  std::vector<rg_align_result> res_f, res_r;
+  auto resolve = [&](const std::vector<rg_align_result>& res, const std::vector<uint32_t>& cand, bool& perfect,
+                     int& best_index, int& offset) {
     int best = 0;
-    if (cand.empty()) return best;
-    res.resize(cand.size());
-    check(rg_overlap_align(ov, a.data(), a.size(), cand.data(), cand.size(), min_percent, min_overlap, res.data()), "align");
     for (size_t c = 0; c < cand.size(); ++c) {
       const rg_align_result& r = res[c];
       const bool only_inside = perfect || r.perfect1;
@@ -255,17 +253,31 @@ int main(int argc, char** argv) {
     candidates(q, ai, lists);
     for (size_t i = b0; i < hi; ++i) {
       Read A = reads[i];
+      // both strands in one launch (the reference only searches the reverse strand when the forward
+      // search found no perfect match, :973-1001; computing it anyway changes nothing: it is ignored then)
+      Read R;
+      R.seq = revcomp(A.seq);
+      const std::vector<uint32_t>& cf = lists[i - b0];
+      const std::vector<uint32_t>& cr = lists[(hi - b0) + (i - b0)];
+      const bool same_len = R.seq.size() == A.seq.size();   // (RevComp drops characters other than ACGTN)
+      res_f.resize(cf.size());
+      res_r.resize(cr.size());
+      if (same_len) {
+        check(rg_overlap_align_both(ov, A.seq.data(), R.seq.data(), A.seq.size(), cf.data(), cf.size(), cr.data(), cr.size(),
+                                    min_percent, min_overlap, res_f.data(), res_r.data()), "align");
+      } else {
+        check(rg_overlap_align(ov, A.seq.data(), A.seq.size(), cf.data(), cf.size(), min_percent, min_overlap, res_f.data()), "align");
+        check(rg_overlap_align(ov, R.seq.data(), R.seq.size(), cr.data(), cr.size(), min_percent, min_overlap, res_r.data()), "align");
+      }
       bool perfect = false;
       int best_index = -1, k = 0;
-      int score = align(A.seq, lists[i - b0], perfect, best_index, k);
+      int score = resolve(res_f, cf, perfect, best_index, k);
       if (!perfect) {
-        Read R;
-        R.seq = revcomp(A.seq);
         R.qual = rev_drop_nul(A.qual);
         R.depth = rev_drop_nul(A.depth);
         R.strand = flip_strands(A.strand);
         int rbest = -1, rk = -1;
-        const int rscore = align(R.seq, lists[(hi - b0) + (i - b0)], perfect, rbest, rk);
+        const int rscore = resolve(res_r, cr, perfect, rbest, rk);
         if (rscore > score) {
           A = R;
           score = rscore;
