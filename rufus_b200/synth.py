@@ -89,6 +89,46 @@ def make_trio(seed: int, genome_len: int, n_pairs: int, read_len: int = 150, sli
     return trio, dn
 
 
+PAIR_SAMPLES = ("Tumor", "Normal")
+QUAD_SAMPLES = ("Proband", "Mother", "Father", "Sibling")
+
+
+def make_pair(seed: int, genome_len: int, n_pairs_normal: int, read_len: int = 150, tumor_factor: int = 2,
+              n_somatic: int | None = None, **kw):
+    """Tumor/normal pair (BASELINE configs[3]): the normal is a diploid genome (two
+    haplotypes with private SNVs), the tumor is the same individual plus `n_somatic` somatic SNVs,
+    sequenced `tumor_factor` times deeper. dict sample -> (seq1, qual1, seq2, qual2), subject first."""
+    rng = np.random.default_rng([seed, 77])
+    genome = rng.integers(0, 4, size=genome_len, dtype=np.uint8)
+    normal = []
+    for _ in range(2):
+        h = genome.copy()
+        _mutate(h, rng.choice(genome_len, size=max(1, genome_len // 1000), replace=False), rng)
+        normal.append(h)
+    if n_somatic is None:
+        n_somatic = max(20, genome_len // 100000)
+    som = np.sort(rng.choice(np.arange(500, genome_len - 500), size=n_somatic, replace=False))
+    tumor = [normal[0].copy(), normal[1].copy()]
+    _mutate(tumor[0], som[::2], rng)
+    _mutate(tumor[1], som[1::2], rng)
+    out = {}
+    for i, (name, haps, n) in enumerate((("Tumor", tumor, tumor_factor * n_pairs_normal), ("Normal", normal, n_pairs_normal))):
+        out[name] = sample_pairs(tuple(haps), n, np.random.default_rng([seed, 2000 + i]), read_len, **kw)
+    return out, som
+
+
+def make_quad(seed: int, genome_len: int, n_pairs: int, read_len: int = 150, **kw):
+    """Proband + 3 controls (BASELINE configs[4]): the trio of make_haplotypes plus an
+    unaffected sibling carrying the two parental haplotypes the proband did not inherit."""
+    haps, dn = make_haplotypes(seed, genome_len, kw.pop("n_denovo", None))
+    people = {"Proband": haps["Child"], "Mother": haps["Mother"], "Father": haps["Father"],
+              "Sibling": (haps["Mother"][1], haps["Father"][0])}
+    out = {}
+    for i, s in enumerate(QUAD_SAMPLES):
+        out[s] = sample_pairs(people[s], n_pairs, np.random.default_rng([seed, 3000 + i]), read_len, **kw)
+    return out, dn
+
+
 def fastq_bytes(seq: np.ndarray, qual: np.ndarray, prefix: str = "r", suffix: str = "") -> bytes:
     """Vectorised fixed-width 4-line FASTQ of a [n, L] read matrix."""
     n, L = seq.shape

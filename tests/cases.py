@@ -28,8 +28,9 @@ def load_case(case):
     else:
         import hashlib
         sy = g["synth"]
-        trio, _ = synth.make_trio(sy["seed"], sy["genome_len"], sy["n_pairs"])
-        for s in synth.SAMPLES:
+        make = {"trio": synth.make_trio, "pair": synth.make_pair, "quad": synth.make_quad}[sy.get("kind", "trio")]
+        trio, _ = make(sy["seed"], sy["genome_len"], sy["n_pairs"])
+        for s in trio:
             s1, q1, s2, q2 = trio[s]
             md5 = hashlib.md5(s1.tobytes() + q1.tobytes() + s2.tobytes() + q2.tobytes()).hexdigest()
             assert md5 == sy["input_md5"][s], "synthetic generator drifted from the committed golden inputs"

@@ -37,7 +37,7 @@ def md5(b: bytes) -> str:
     return hashlib.md5(b).hexdigest()
 
 
-def run_case(work, fq, k, min_cov, max_cov, minq=15, thresh=1, L=2, ctlL=2, size="16M"):
+def run_case(work, fq, k, min_cov, max_cov, minq=15, thresh=1, L=2, ctlL=2, size="16M", sweep=()):
     """fq: dict sample -> (mate1.fastq path, mate2.fastq path); first sample = subject."""
     res = {"k": k, "min_cov": min_cov, "max_cov": max_cov, "minq": minq, "thresh": thresh,
            "L": L, "ctlL": ctlL, "samples": {}}
@@ -80,6 +80,21 @@ def run_case(work, fq, k, min_cov, max_cov, minq=15, thresh=1, L=2, ctlL=2, size
     sh(f"{REFBIN}/RUFUS.Filter.single HashList {m1} {work}/se {k} {minq} {thresh} 4 > /dev/null", cwd=work)
     se = open(os.path.join(work, "se.Mutations.fastq")).read().splitlines()
     res["single_names_sorted"] = sorted(se[0::4])
+    # min-count sweep (BASELINE configs[4]): the same merge output cut at other MutantMinCov values
+    # (CheckJellyHashList.sh:12 awk filters), each HashList pulled through RUFUS.Filter
+    if sweep:
+        res["sweep"] = {}
+    for mc in sweep:
+        hl = subprocess.run(
+            ["bash", "-c", f"{JF} query -s <(cat merge.out | awk '{{print \">\"$1\"\\n\"$1}}') {jh(subj)}"
+             f" | awk -v var={mc} ' $2 >= var ' | awk -v var={max_cov} ' $2 <= var '"],
+            check=True, capture_output=True, cwd=work).stdout
+        open(os.path.join(work, f"HashList.{mc}"), "wb").write(hl)
+        sh(f"{REFBIN}/RUFUS.Filter HashList.{mc} {m1} {m2} {work}/sw{mc} {k} {minq} {thresh} 4 > /dev/null", cwd=work)
+        o1 = open(os.path.join(work, f"sw{mc}.Mutations.Mate1.fastq")).read().splitlines()
+        res["sweep"][str(mc)] = {"hashlist_md5": md5(("\n".join(sorted(hl.decode().splitlines())) + "\n").encode()),
+                                 "hashlist_lines": len(hl.decode().splitlines()),
+                                 "pulled_mate1_names_sorted": sorted(o1[0::4])}
     return res
 
 
@@ -111,12 +126,13 @@ def bundled(work):
           "hashlist", len(res["hashlist_sorted"]), "pulled", len(res["pulled_mate1_names_sorted"]))
 
 
-def synth_case(work, name, seed, G, n_pairs, k, min_cov, max_cov, **kw):
+def synth_case(work, name, seed, G, n_pairs, k, min_cov, max_cov, kind="trio", **kw):
     out = os.path.join(HERE, name)
     os.makedirs(out, exist_ok=True)
-    trio, _ = synth.make_trio(seed, G, n_pairs)
+    make = {"trio": synth.make_trio, "pair": synth.make_pair, "quad": synth.make_quad}[kind]
+    trio, _ = make(seed, G, n_pairs)
     fq, insum = {}, {}
-    for s in synth.SAMPLES:
+    for s in trio:
         s1, q1, s2, q2 = trio[s]
         p1, p2 = os.path.join(work, f"{s}.m1.fq"), os.path.join(work, f"{s}.m2.fq")
         open(p1, "wb").write(synth.fastq_bytes(s1, q1, prefix=s[0]))
@@ -125,6 +141,8 @@ def synth_case(work, name, seed, G, n_pairs, k, min_cov, max_cov, **kw):
         insum[s] = md5(s1.tobytes() + q1.tobytes() + s2.tobytes() + q2.tobytes())
     res = run_case(work, fq, k, min_cov, max_cov, **kw)
     res["synth"] = {"seed": seed, "genome_len": G, "n_pairs": n_pairs, "input_md5": insum}
+    if kind != "trio":
+        res["synth"]["kind"] = kind
     strip_dumps(res, out, keep=False)
     json.dump(res, open(os.path.join(out, "golden.json"), "w"), indent=0, sort_keys=True)
     print(name, "distinct", {s: d["n_distinct"] for s, d in res["samples"].items()},
@@ -195,11 +213,18 @@ def edge_case(work):
 
 
 if __name__ == "__main__":
-    for fn, args in ((bundled, ()), (edge_case, ()),
-                     (synth_case, ("synth_k25", 7, 50000, 5000, 25, 5, 150)),
-                     (synth_case, ("synth_k31", 11, 40000, 4000, 31, 5, 150))):
+    only = set(sys.argv[1:])
+    for fn, args, kw in ((bundled, (), {}), (edge_case, (), {}),
+                         (synth_case, ("synth_k25", 7, 50000, 5000, 25, 5, 150), {}),
+                         (synth_case, ("synth_k31", 11, 40000, 4000, 31, 5, 150), {}),
+                         # scaled-down BASELINE configs[3] (60x tumor vs 30x normal, one control) and
+                         # configs[4] (proband + 3 controls, k = 31, min-count sweep)
+                         (synth_case, ("pair_k25", 21, 40000, 4000, 25, 5, 300), {"kind": "pair"}),
+                         (synth_case, ("quad_k31", 31, 40000, 4000, 31, 5, 150), {"kind": "quad", "sweep": (2, 3, 8, 12)})):
+        if only and (args[0] if args else fn.__name__) not in only:
+            continue
         work = tempfile.mkdtemp(prefix="rg_golden_")
         try:
-            fn(work, *args)
+            fn(work, *args, **kw)
         finally:
             shutil.rmtree(work, ignore_errors=True)

@@ -15,7 +15,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-CASES = ["testRun", "edge", "synth_k25", "synth_k31"]
+# pair_k25 / quad_k31: scaled-down BASELINE configs[3] (tumor/normal, one control) and configs[4]
+# (proband + 3 controls, k = 31, min-count sweep)
+CASES = ["testRun", "edge", "synth_k25", "synth_k31", "pair_k25", "quad_k31"]
 MODES = [api.MODE_DIRECT, api.MODE_TILED]
 
 
@@ -73,6 +75,17 @@ def test_pipeline_matches_reference_goldens(ctx, case, mode):
         hits = mset.filter_single(m1.seq, m1.qual, m1.offs, g["minq"])
         got = sorted(f"{m1.names[i].decode()}:MH{hits[i]}" for i in np.flatnonzero(hits >= g["thresh"]))
         assert got == g["single_names_sorted"]
+        mset.free()
+    import hashlib
+    for mc, sw in g.get("sweep", {}).items():
+        hk, hc = api.subtract(tabs[subj], [tabs[s] for s in names[1:]], subj_min=mins[0], other_min=mins[1:],
+                              min_cov=int(mc), max_cov=g["max_cov"])
+        lines = sorted(kmer.dump_text(hk, hc, k))
+        assert len(lines) == sw["hashlist_lines"]
+        assert hashlib.md5(("\n".join(lines) + "\n").encode()).hexdigest() == sw["hashlist_md5"]
+        mset = api.MutantSet.from_jf_keys(ctx, hk, k)
+        keep = mset.filter_pairs(m1.seq, m1.qual, m1.offs, m2.seq, m2.qual, m2.offs, g["minq"], g["thresh"])
+        assert sorted(m1.names[i].decode() for i in np.flatnonzero(keep)) == sw["pulled_mate1_names_sorted"]
         mset.free()
     for t in tabs.values():
         t.free()

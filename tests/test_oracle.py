@@ -15,7 +15,9 @@ import sys
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import oracle  # noqa: E402
 
-CASES = ["testRun", "edge", "synth_k25", "synth_k31"]
+# pair_k25 / quad_k31: scaled-down BASELINE configs[3] (tumor/normal, one control) and configs[4]
+# (proband + 3 controls, k = 31, min-count sweep)
+CASES = ["testRun", "edge", "synth_k25", "synth_k31", "pair_k25", "quad_k31"]
 
 
 def _dump_bytes(keys, counts, k):
@@ -59,6 +61,14 @@ def test_count_histo_subtract_filter_match_reference(case):
     hits = oracle.filter_single(m1.seq, m1.qual, m1.offs, k, g["minq"], rset)
     got = sorted(f"{m1.names[i].decode()}:MH{hits[i]}" for i in np.flatnonzero(hits >= g["thresh"]))
     assert got == g["single_names_sorted"]
+    for mc, sw in g.get("sweep", {}).items():
+        hk, hc = oracle.hashlist(tabs[subj], [tabs[s] for s in names[1:]], int(mc), g["max_cov"])
+        lines = sorted(kmer.dump_text(hk, hc, k))
+        assert len(lines) == sw["hashlist_lines"]
+        assert hashlib.md5(("\n".join(lines) + "\n").encode()).hexdigest() == sw["hashlist_md5"]
+        rset = oracle.rufus_set_from_kmers(kmer.keys_to_text(hk, k))
+        keep = oracle.filter_pairs(m1.seq, m1.qual, m1.offs, m2.seq, m2.qual, m2.offs, k, g["minq"], g["thresh"], rset)
+        assert sorted(m1.names[i].decode() for i in np.flatnonzero(keep)) == sw["pulled_mate1_names_sorted"]
 
 
 def test_rufus_pack_known_answers():
