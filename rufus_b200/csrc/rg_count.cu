@@ -137,22 +137,12 @@ int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads,
 #define TILE_THREADS_N 1024
 #endif
 constexpr int TILE_THREADS = TILE_THREADS_N;
-// per-warp staging ring of the bucket stream: 32 KiB in all (what is left beside the 192 KiB tile)
-constexpr uint32_t TILE_RING_KEYS = 4096 / (TILE_THREADS / 32);
-constexpr uint32_t TILE_QUARTER = TILE_RING_KEYS / 4;          // keys per cp.async group: 32 (8 B/lane) or 64 (16 B/lane)
-static_assert(TILE_QUARTER == 32 || TILE_QUARTER == 64, "ring quarter must be 32 or 64 keys");
-constexpr size_t TILE_SMEM = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (TILE_THREADS / 32) * TILE_RING_KEYS * 8;
-
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gmem_src)
-               : "memory");
-}
+#ifndef TILE_AHEAD
+#define TILE_AHEAD 4                 // steps of 32 keys a warp keeps in flight in registers (one block)
+#endif
+// retry queue of a warp: 64 x 16 bytes (key, slot | probes << RG_TILE_BITS, -)
+constexpr uint32_t TILE_Q = 64;
+constexpr size_t TILE_SMEM = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (TILE_THREADS / 32) * TILE_Q * 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -204,6 +194,18 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
   uint32_t* gcounts = counts + ((uint64_t)tile << RG_TILE_BITS);
   if (n == 0 && load_existing) return;   // nothing to apply, tile in HBM is already right
 
+  // the first block of every warp is loaded while the tile is being initialised
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr uint32_t NWARPS = TILE_THREADS / 32, BLOCK_KEYS = 32 * TILE_AHEAD;
+  const uint64_t* bucket = part_keys + (uint64_t)tile * bucket_cap;
+  auto load = [&](uint32_t blk, int u) -> uint64_t {       // key of this lane in step u of block blk
+    const uint32_t pos = blk * BLOCK_KEYS + u * 32 + lane;
+    return pos < n ? __ldg(bucket + pos) : RG_EMPTY;
+  };
+  uint64_t kreg[TILE_AHEAD];
+#pragma unroll
+  for (int u = 0; u < TILE_AHEAD; ++u) kreg[u] = load(warp, u);
+
   if (load_existing) {
     if (threadIdx.x == 0) {
       mbar_init(bar, 1);
@@ -230,84 +232,69 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
     __syncthreads();
   }
 
-  // Stream the bucket. Warp w consumes the w-th 1/32 of the bucket through a private 128-key ring
-  // in shared memory that is kept full with cp.async (4 quarters of 32 keys, 3 in flight ahead of
-  // the reader). Lanes REFILL themselves from the ring: each iteration the lanes whose key has
-  // found its slot claim the next keys of the warp's stream (ballot + popc), so the probe loop
-  // runs ~(mean probes) iterations per key instead of (max over the 32 lanes), and it stays
-  // convergent: every lane executes every iteration until the whole warp is done.
+  // Stream the bucket in blocks of 32 * TILE_AHEAD keys, dealt round-robin to the warps (the first
+  // block of a warp is loaded during the tile initialisation). A step = 32 consecutive keys, one
+  // coalesced 256-byte load issued one block ahead. Every step makes ONE probe per lane; the lanes that hit a slot occupied by another key
+  // push (key, next slot) onto the warp's retry queue (ballot + popc) and the warp moves on, so no
+  // lane ever waits for another lane's probe sequence. Whenever the queue holds 32 entries the
+  // warp spends a step on those instead of the stream (warp-uniform choice), and drains what is
+  // left at the end.
   {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* q = reinterpret_cast<uint4*>(smem_raw + RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64) + warp * TILE_Q;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64) +
-                     warp * TILE_RING_KEYS;
-    constexpr uint32_t NWARPS = TILE_THREADS / 32, PER_LANE = TILE_QUARTER / 32;
-    const uint32_t chunk = (((n + NWARPS - 1) / NWARPS) + 1u) & ~1u;            // even: 16-byte aligned stream starts
-    const uint32_t begin = min(n, warp * chunk);
-    const uint32_t n_rel = min(n, begin + chunk) - begin;       // keys of this warp's stream
-    // this lane's next key(s) to stage
-    const uint64_t* gsrc = part_keys + (uint64_t)tile * bucket_cap + begin + lane * PER_LANE;
-    uint32_t issued = 0;              // cp.async issued for stream positions [0, issued)
-    auto issue_quarter = [&]() {
-      uint64_t* dst = ring + (issued & (TILE_RING_KEYS - TILE_QUARTER)) + lane * PER_LANE;
-      if (PER_LANE == 1) {
-        if (issued + lane < n_rel) cp_async_8(dst, gsrc);
-      } else {
-        // 16 bytes = 2 keys; the second may lie past the stream's end (still inside the bucket slab: never claimed)
-        if (issued + lane * 2 < n_rel) cp_async_16(dst, gsrc);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      gsrc += TILE_QUARTER;
-      issued += TILE_QUARTER;
-    };
-#pragma unroll
-    for (int q = 0; q < 4; ++q) issue_quarter();
-    asm volatile("cp.async.wait_group 2;" ::: "memory");
-    __syncwarp();
-    uint32_t head = 0;                // next unclaimed position of the warp's stream
-    uint32_t slot = 0, probes = 0;
-    uint64_t key = RG_EMPTY;
-    bool have = false;
-    for (;;) {
-      // ---- claim: lanes without a key take the next ones of the stream
-      const uint32_t want = __ballot_sync(0xFFFFFFFFu, !have);
-      if (head >= n_rel && want == 0xFFFFFFFFu) break;          // warp-uniform
-      const uint32_t my = head + __popc(want & lt_mask);
-      if (!have && my < n_rel) {
-        key = ring[my & (TILE_RING_KEYS - 1)];
-        uint32_t tile_unused;
-        rg_locate_in_group(key, geo, tile_unused, slot);
-        probes = 0;
-        have = key != RG_EMPTY;       // (pad slots of the partition runs are skipped)
-      }
-      const uint32_t new_head = min(n_rel, head + (uint32_t)__popc(want));
-      // ---- the reader left a quarter of the ring: refill it with the quarter 4 ahead
-      if ((new_head ^ head) / TILE_QUARTER) {
-        __syncwarp();                 // every lane has read its claim before the slot is overwritten
-        issue_quarter();
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
-        __syncwarp();                 // the two quarters the next claims can touch are complete for all lanes
-      }
-      head = new_head;
-      // ---- one probe for every lane that holds a key
-      if (have) {
-        unsigned long long seen = *(volatile unsigned long long*)(skeys + slot);
-        if (seen == RG_EMPTY)
-          seen = atomicCAS((unsigned long long*)(skeys + slot), (unsigned long long)RG_EMPTY, (unsigned long long)key);
-        const bool hit = (seen == RG_EMPTY) | (seen == key);
-        if (hit) atomicAdd(scounts + slot, 1u);
-        have = !hit;
-        slot = (slot + (hit ? 0u : 1u)) & (RG_TILE_SLOTS - 1);
-        probes += hit ? 0u : 1u;
-        if (probes == RG_TILE_SLOTS) {                 // tile full
-          const uint64_t sp = atomicAdd((unsigned long long*)&status[0], 1ull);
-          if (sp < spill_cap) spill[sp] = key;
-          have = false;
-          probes = 0;
+    uint32_t qhead = 0, qlen = 0;     // warp-uniform
+
+    // one probe of `key` at slot (sp & mask) for the lanes with `have`; failures are queued
+    auto step = [&](uint64_t key, uint32_t sp, bool have) {
+      const uint32_t slot = sp & (RG_TILE_SLOTS - 1);
+      unsigned long long seen = 0;                          // lanes without a key never see an empty slot
+      if (have) seen = *(volatile unsigned long long*)(skeys + slot);
+      if (seen == RG_EMPTY)
+        seen = atomicCAS((unsigned long long*)(skeys + slot), (unsigned long long)RG_EMPTY, (unsigned long long)key);
+      const bool hit = (seen == RG_EMPTY) | (seen == key);
+      if (hit && have) atomicAdd(scounts + slot, 1u);
+      const bool fail = have && !hit;
+      const uint32_t fm = __ballot_sync(0xFFFFFFFFu, fail);
+      if (fm) {                                             // warp-uniform
+        if (fail) {
+          // next slot, one more probe counted in the bits above the slot
+          const uint32_t nsp = ((sp + 1u) & (RG_TILE_SLOTS - 1)) | ((sp + RG_TILE_SLOTS) & ~(RG_TILE_SLOTS - 1));
+          q[(qhead + qlen + __popc(fm & lt_mask)) & (TILE_Q - 1)] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), nsp, 0u);
         }
+        qlen += __popc(fm);
+      }
+    };
+    // a step on (up to) 32 queued keys
+    auto drain = [&]() {
+      __syncwarp();                                         // the queue writes of the previous step are visible
+      const uint32_t take = min(32u, qlen);
+      const uint4 e = q[(qhead + lane) & (TILE_Q - 1)];
+      bool have = lane < take;
+      const uint64_t key = ((uint64_t)e.y << 32) | e.x;
+      qhead = (qhead + take) & (TILE_Q - 1);
+      qlen -= take;
+      if (have && (e.z >> RG_TILE_BITS) >= RG_TILE_SLOTS) {  // every slot of the tile probed: tile full
+        const uint64_t spi = atomicAdd((unsigned long long*)&status[0], 1ull);
+        if (spi < spill_cap) spill[spi] = key;
+        have = false;
+      }
+      step(key, e.z, have);
+    };
+    // blocks are dealt round-robin to the warps. (A shared ticket counter balanced the warps no
+    // better: the compiler emits its warp-aggregated atomic, whose shuffle waits for the shared
+    // atomic's round trip once per block: 0.58 ms against 0.49.)
+    for (uint32_t cur = warp; cur * BLOCK_KEYS < n; cur += NWARPS) {
+#pragma unroll
+      for (int u = 0; u < TILE_AHEAD; ++u) {
+        const uint64_t key = kreg[u];
+        kreg[u] = load(cur + NWARPS, u);
+        uint32_t tile_unused, slot;
+        rg_locate_in_group(key, geo, tile_unused, slot);
+        step(key, slot, key != RG_EMPTY);                   // (neutralised slots and the bucket's end are skipped)
+        while (qlen >= 32) drain();
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    while (qlen) drain();
   }
   __syncthreads();
   // generic-proxy writes -> visible to the async proxy, then bulk store the tile

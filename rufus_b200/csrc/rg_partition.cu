@@ -45,7 +45,7 @@ struct PartStage {
   uint32_t brk[BIT_WORDS + 2];
 };
 
-constexpr size_t part_static_smem() { return sizeof(PartStage) + 33 * sizeof(uint32_t) + 256; }
+constexpr size_t part_static_smem() { return sizeof(PartStage) + 65 * sizeof(uint32_t) + 256; }
 // ukeys (8 B) + sorted (tile,index) entries (4 B) per key; count->gdelta and loff per tile; overflow bitmap
 static size_t part_dynamic_smem(uint32_t n_tiles, uint32_t n_groups = 0) {
   return (size_t)PART_K * 12 + (size_t)n_tiles * 8 + (size_t)((n_tiles + 31) / 32) * 4 + (size_t)(n_groups + 1) * 4;
@@ -280,6 +280,7 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_a
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t scan_total;
   __shared__ uint32_t any_overflow;
+  __shared__ uint32_t dummy_hist[32];    // where the windows without a k-mer "count" (never read)
   // MULTI: the owners' base pointers, indexed per bucket / per key (a dynamically indexed kernel
   // parameter array would be copied to local memory)
   __shared__ uint64_t* s_owner_keys[PART_MAX_OWNERS];
@@ -373,9 +374,11 @@ partition_sorted_kernel(ExtractParams ep, const uint64_t* __restrict__ in_keys_a
           ok = ok && mine;
         }
       }
-      uint32_t m = 0xFFFFFFFFu;
-      if (ok) m = b * 65536u + atomicAdd(&hist[b], 1u);
-      meta[w] = m;
+      // the shared atomic is UNCONDITIONAL (no branch around it): windows without a k-mer count
+      // into a per-lane dummy word instead of a bucket
+      uint32_t* cell = ok ? hist + b : dummy_hist + (threadIdx.x & 31);
+      const uint32_t rank = atomicAdd(cell, 1u);
+      meta[w] = ok ? b * 65536u + rank : 0xFFFFFFFFu;
       ukeys[w * PART_THREADS + threadIdx.x] = key;
     };
     if (SRC != 0) {
