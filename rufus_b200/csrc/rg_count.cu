@@ -269,6 +269,7 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
       __syncwarp();                                         // the queue writes of the previous step are visible
       const uint32_t take = min(32u, qlen);
       const uint4 e = q[(qhead + lane) & (TILE_Q - 1)];
+      __syncwarp();                                         // every lane has its entry before the step overwrites the ring
       bool have = lane < take;
       const uint64_t key = ((uint64_t)e.y << 32) | e.x;
       qhead = (qhead + take) & (TILE_Q - 1);
