@@ -205,6 +205,24 @@ def edge_case(work):
                     f2.write(f"@m2only.{r}/2\n{m2seq}\n+\n{'J' * len(m2seq)}\n")
         fq[s] = (p1, p2)
     res = run_case(work, fq, 25, 5, 1200)
+    # an `-e` exclude file (runRufus.sh:925: extra merge inputs): ANY record excludes, whatever its
+    # count. Here: two subject-only reads seen ONCE, counted without -L (count-1 records are kept)
+    excl_reads = [EDGE_READS[10][1], EDGE_READS[1][1]]
+    with open(os.path.join(work, "excl.fa"), "w") as f:
+        for i, r in enumerate(excl_reads):
+            f.write(f">x{i}\n{r}\n")
+    sh(f"{JF} count -m 25 -s 16M -t 2 -C -o excl.Jhash excl.fa", cwd=work)
+    jh = lambda s: os.path.join(work, s + ".generator.Jhash")
+    merged = subprocess.run(f"{JF} merge " + " ".join(jh(s) for s in fq) + " excl.Jhash", shell=True, check=True,
+                            capture_output=True, cwd=work).stdout
+    open(os.path.join(work, "merge_e.out"), "wb").write(merged)
+    hl = subprocess.run(
+        ["bash", "-c", f"{JF} query -s <(cat merge_e.out | awk '{{print \">\"$1\"\\n\"$1}}') {jh('Subj')}"
+         f" | awk -v var=5 ' $2 >= var ' | awk -v var=1200 ' $2 <= var '"],
+        check=True, capture_output=True, cwd=work).stdout
+    res["exclude"] = {"reads": excl_reads, "merge_sorted": sorted(merged.decode().splitlines()),
+                      "hashlist_sorted": sorted(hl.decode().splitlines())}
+    assert len(res["exclude"]["hashlist_sorted"]) < len(res["hashlist_sorted"])
     strip_dumps(res, out, keep=True)
     json.dump(res, open(os.path.join(out, "golden.json"), "w"), indent=0, sort_keys=True)
     print("edge: distinct", {s: d["n_distinct"] for s, d in res["samples"].items()},

@@ -81,6 +81,28 @@ def test_merge_query_hashlist_match_goldens(run):
     open(os.path.join(work, "HashList"), "w").write("\n".join(hl) + "\n")
 
 
+def test_exclude_file_in_merge(run):
+    """`-e` exclude files are extra `jellyfish merge` inputs (runRufus.sh:925); a record seen once excludes"""
+    case, g, work, fq = run
+    if "exclude" not in g:
+        pytest.skip("no exclude golden for this case")
+    names = SAMPLES[case]
+    with open(os.path.join(work, "excl.fa"), "w") as f:
+        for i, r in enumerate(g["exclude"]["reads"]):
+            f.write(f">x{i}\n{r}\n")
+    sh(f"{JF} count -m {g['k']} -s 16M -t 2 -C -o excl.Jhash excl.fa", work)
+    merged = sh(f"{JF} merge " + " ".join(s + ".Jhash" for s in names) + " excl.Jhash > merge_e.out; cat merge_e.out", work).stdout
+    assert sorted(merged.decode().splitlines()) == g["exclude"]["merge_sorted"]
+    q = sh(f"{JF} query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge_e.out) {names[0]}.Jhash", work).stdout.decode()
+    hl = [l for l in q.splitlines() if g["min_cov"] <= int(l.split()[1]) <= g["max_cov"]]
+    assert sorted(hl) == g["exclude"]["hashlist_sorted"]
+    if os.path.exists(REFJF):
+        # an exclude file written by the REAL jellyfish is read the same way
+        sh(f"{REFJF} count -m {g['k']} -s 16M -t 2 -C -o excl_ref.Jhash excl.fa", work)
+        merged2 = sh(f"{JF} merge " + " ".join(s + ".Jhash" for s in names) + " excl_ref.Jhash", work).stdout
+        assert sorted(merged2.decode().splitlines()) == g["exclude"]["merge_sorted"]
+
+
 def test_read_pull_matches_goldens(run):
     case, g, work, fq = run
     if not os.path.exists(os.path.join(work, "HashList")):

@@ -91,6 +91,24 @@ def test_pipeline_matches_reference_goldens(ctx, case, mode):
         t.free()
 
 
+def test_exclude_table_records_exclude_whatever_their_count(ctx):
+    """SURVEY Appendix B.5 (`-e` exclude files, runRufus.sh:925): one more table in the subtraction,
+    kept from count 1, against the golden made with the reference's merge + query."""
+    g, reads = load_case("edge")
+    k, names = g["k"], list(reads)
+    tabs = [_count_all(ctx, reads, k, api.MODE_TILED)[s] for s in names]
+    seq = np.frombuffer("".join(g["exclude"]["reads"]).encode(), np.uint8)
+    offs = np.cumsum([0] + [len(r) for r in g["exclude"]["reads"]]).astype(np.uint64)
+    tabs.append(api.KmerTable.count(ctx, seq, offs, k, True, mode=api.MODE_DIRECT))
+    mins = [g["L"], g["ctlL"], g["ctlL"], 1]
+    mk, mc, _ = api.merge_unique(tabs, mins)
+    assert sorted(kmer.dump_text(mk, mc, k, "\t")) == g["exclude"]["merge_sorted"]
+    hk, hc = api.subtract(tabs[0], tabs[1:], subj_min=mins[0], other_min=mins[1:], min_cov=g["min_cov"], max_cov=g["max_cov"])
+    assert sorted(kmer.dump_text(hk, hc, k)) == g["exclude"]["hashlist_sorted"]
+    for t in tabs:
+        t.free()
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_medium_synthetic_vs_oracle(ctx, mode):
     """60k pairs/sample (18 Mbases/sample), two pushes per sample, stream and offsets inputs."""

@@ -71,6 +71,25 @@ def test_count_histo_subtract_filter_match_reference(case):
         assert sorted(m1.names[i].decode() for i in np.flatnonzero(keep)) == sw["pulled_mate1_names_sorted"]
 
 
+def test_exclude_file_records_exclude_whatever_their_count():
+    """an `-e` exclude .Jhash is one more merge input; a record seen ONCE excludes
+    (the file is counted without -L), while a control k-mer seen once (-L 2) does not."""
+    g, reads = load_case("edge")
+    k, names = g["k"], list(reads)
+    tabs = []
+    for i, s in enumerate(names):
+        r = both_mates(reads[s])
+        tabs.append(oracle.count(r.seq, r.offs, k, True, g["L"] if i == 0 else g["ctlL"]))
+    seq = np.frombuffer("".join(g["exclude"]["reads"]).encode(), np.uint8)
+    offs = np.cumsum([0] + [len(r) for r in g["exclude"]["reads"]]).astype(np.uint64)
+    tabs.append(oracle.count(seq, offs, k, True, 1))
+    mk, mc = oracle.merge_unique(tabs)
+    assert sorted(kmer.dump_text(mk, mc, k, "\t")) == g["exclude"]["merge_sorted"]
+    hk, hc = oracle.hashlist(tabs[0], tabs[1:], g["min_cov"], g["max_cov"])
+    assert sorted(kmer.dump_text(hk, hc, k)) == g["exclude"]["hashlist_sorted"]
+    assert len(g["exclude"]["hashlist_sorted"]) < len(g["hashlist_sorted"])
+
+
 def test_rufus_pack_known_answers():
     # Util.cpp:51-84: base i at bits (2i, 2i+1): A 00, C bit(2i+1), G bit(2i), T both.
     L = oracle.lib()
