@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Fixtures for the BAM ingest (tools/bin/rg_bamview, oracle/bam_oracle.py). Run in the build container.
 
-  tests/golden/bam/Father.bam        the smallest bundled BAM of the reference's testRun/ (data, 277 KB)
+  (the bundled BAM files themselves are committed under tests/golden/testRun_bam/ by make_golden.py)
   tests/golden/bam/golden.json       per bundled BAM: record counts and md5 of the SAM text of
                                      oracle/bam_oracle.py with -F 3328 (runRufus.sh:599) and without a
                                      filter; md5 of the re-paired reads, which must equal the
@@ -50,8 +50,6 @@ def bgzf(data, block):
 def main():
     os.makedirs(out, exist_ok=True)
     g = {"generator": "tests/golden/make_bam_golden.py", "bundled": {}}
-    shutil.copyfile(os.path.join(REF, "Father.bam"), os.path.join(out, "Father.bam"))
-    os.chmod(os.path.join(out, "Father.bam"), 0o644)
     for s in ("Child", "Mother", "Father"):
         e = {"bam_md5": md5(open(os.path.join(REF, s + ".bam"), "rb").read())}
         for tag, excl in (("F3328", 3328), ("all", 0)):

@@ -37,16 +37,21 @@ def md5(b: bytes) -> str:
     return hashlib.md5(b).hexdigest()
 
 
-def run_case(work, fq, k, min_cov, max_cov, minq=15, thresh=1, L=2, ctlL=2, size="16M", sweep=()):
-    """fq: dict sample -> (mate1.fastq path, mate2.fastq path); first sample = subject."""
+def run_case(work, fq, k, min_cov, max_cov, minq=15, thresh=1, L=2, ctlL=2, size="16M", sweep=(), generators=None):
+    """fq: dict sample -> (mate1.fastq path, mate2.fastq path); first sample = subject.
+    generators: dict sample -> text of the .generator script (BAM mode); the subject's mate files for
+    the read pull are then made from its generator by PassThroughSamCheck.stranded (runRufus.sh:966)."""
     res = {"k": k, "min_cov": min_cov, "max_cov": max_cov, "minq": minq, "thresh": thresh,
            "L": L, "ctlL": ctlL, "samples": {}}
     names = list(fq)
     for i, s in enumerate(names):
         gen = os.path.join(work, s + ".generator")
         with open(gen, "w") as f:
-            for p in fq[s]:
-                f.write(f"perl {REF}/scripts/FastqToSam.pl <(cat {p})\n")
+            if generators:
+                f.write(generators[s])
+            else:
+                for p in fq[s]:
+                    f.write(f"perl {REF}/scripts/FastqToSam.pl <(cat {p})\n")
         lo = L if i == 0 else ctlL
         sh(f"bash {gen} | {REFBIN}/PassThroughSamCheck {gen}.Jelly.chr > {gen}.fq", cwd=work)
         sh(f"{JF} count --disk -m {k} -L {lo} -s {size} -t 4 -o {gen}.Jhash -C {gen}.fq", cwd=work)
@@ -71,7 +76,14 @@ def run_case(work, fq, k, min_cov, max_cov, minq=15, thresh=1, L=2, ctlL=2, size
     open(os.path.join(work, "HashList"), "wb").write(hl)
     res["merge_sorted"] = sorted(merged.decode().splitlines())
     res["hashlist_sorted"] = sorted(hl.decode().splitlines())
-    m1, m2 = fq[subj]
+    if generators:
+        gen = os.path.join(work, subj + ".generator")
+        sh(f"bash {gen} | {REFBIN}/PassThroughSamCheck.stranded {gen}.filter.chr {gen}.temp > {gen}.temp", cwd=work)
+        m1, m2 = gen + ".temp.mate1.fastq", gen + ".temp.mate2.fastq"
+        res["repaired_pairs"] = open(m1).read().count("\n") // 4
+        res["repaired_mate_md5"] = [md5(open(m1, "rb").read()), md5(open(m2, "rb").read())]
+    else:
+        m1, m2 = fq[subj]
     sh(f"{REFBIN}/RUFUS.Filter HashList {m1} {m2} {work}/out {k} {minq} {thresh} 4 > /dev/null", cwd=work)
     o1 = open(os.path.join(work, "out.Mutations.Mate1.fastq")).read().splitlines()
     o2 = open(os.path.join(work, "out.Mutations.Mate2.fastq")).read().splitlines()
@@ -124,6 +136,28 @@ def bundled(work):
     json.dump(res, open(os.path.join(out, "golden.json"), "w"), indent=0, sort_keys=True)
     print("bundled: distinct", {s: d["n_distinct"] for s, d in res["samples"].items()},
           "hashlist", len(res["hashlist_sorted"]), "pulled", len(res["pulled_mate1_names_sorted"]))
+
+
+def bam_case(work):
+    """BASELINE configs[0] as literally written: the bundled testRun/*.bam in BAM mode (runRufus.sh:599
+    generator `samtools view -F 3328 X.bam`, RunJellyForRUFUS.sh:28-29, runRufus.sh:966-967). samtools is
+    not installed here, so the view step is tools/bin/rg_bamview (pinned separately: tests/golden/bam);
+    EVERYTHING downstream of it is the reference's own binaries."""
+    out = os.path.join(HERE, "testRun_bam")
+    os.makedirs(out, exist_ok=True)
+    view = os.path.join(ROOT, "tools", "bin", "rg_bamview")
+    gens = {}
+    for s in ("Child", "Mother", "Father"):
+        dst = os.path.join(out, s + ".bam")
+        shutil.copyfile(f"{REF}/testRun/{s}.bam", dst)
+        os.chmod(dst, 0o644)
+        gens[s] = f"{view} view -F 3328 {dst}\n"
+    res = run_case(work, {s: None for s in gens}, 25, 5, 140, generators=gens)
+    strip_dumps(res, out, keep=False)
+    json.dump(res, open(os.path.join(out, "golden.json"), "w"), indent=0, sort_keys=True)
+    print("testRun_bam: distinct", {s: d["n_distinct"] for s, d in res["samples"].items()},
+          "hashlist", len(res["hashlist_sorted"]), "re-paired", res["repaired_pairs"],
+          "pulled", len(res["pulled_mate1_names_sorted"]), "single", len(res["single_names_sorted"]))
 
 
 def synth_case(work, name, seed, G, n_pairs, k, min_cov, max_cov, kind="trio", **kw):
@@ -232,7 +266,7 @@ def edge_case(work):
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])
-    for fn, args, kw in ((bundled, (), {}), (edge_case, (), {}),
+    for fn, args, kw in ((bundled, (), {}), (bam_case, (), {}), (edge_case, (), {}),
                          (synth_case, ("synth_k25", 7, 50000, 5000, 25, 5, 150), {}),
                          (synth_case, ("synth_k31", 11, 40000, 4000, 31, 5, 150), {}),
                          # scaled-down BASELINE configs[3] (60x tumor vs 30x normal, one control) and

@@ -228,3 +228,41 @@ def test_overlap_fuzz_matches_oracle(tmp_path, seed):
         shutil.copy(tmp_path / "in.fastqd", tmp_path / "ref")
         sh(f"{ref} in.fastqd " + " ".join(args), str(tmp_path / "ref"))
         assert open(tmp_path / "ref" / "o.fastqd").read() == fqd
+
+
+def test_bam_mode_chain_matches_reference(tmp_path):
+    """BASELINE configs[0] in BAM mode, with the stage commands of RunJellyForRUFUS.sh:22-37 and
+    runRufus.sh:925,966-967 (FIFOs included) and OUR executables end to end: rg_bamview ->
+    PassThroughSamCheck -> jellyfish count/histo/merge/query -> PassThroughSamCheck.stranded ->
+    RUFUS.Filter. Golden = the reference's binaries downstream of the same view step
+    (tests/golden/make_golden.py bam_case)."""
+    g = golden("testRun_bam")
+    work = str(tmp_path)
+    k, names = g["k"], ("Child", "Mother", "Father")
+    gen = {s: f"{BIN}/rg_bamview view -F 3328 {GOLDEN}/testRun_bam/{s}.bam" for s in names}
+    for i, s in enumerate(names):
+        lo = g["L"] if i == 0 else g["ctlL"]
+        sh(f"mkfifo {s}.fq; {gen[s]} | {BIN}/PassThroughSamCheck {s}.Jelly.chr > {s}.fq & "
+           f"timeout 200 {JF} count --disk -m {k} -L {lo} -s 16M -t 4 -o {s}.Jhash -C {s}.fq; rm {s}.fq; wait", work)
+        sh(f"{JF} histo -f -o {s}.histo {s}.Jhash", work)
+        gs = g["samples"][s]
+        assert md5(open(os.path.join(work, s + ".histo"), "rb").read()) == gs["histo_md5"]
+        dump = sh(f"{JF} dump -c {s}.Jhash | LC_ALL=C sort", work).stdout
+        assert dump.count(b"\n") == gs["n_distinct"] and md5(dump) == gs["dump_sorted_md5"]
+    merged = sh(f"{JF} merge " + " ".join(s + ".Jhash" for s in names) + " > merge.out; cat merge.out", work).stdout
+    assert sorted(merged.decode().splitlines()) == g["merge_sorted"]
+    q = sh(f"{JF} query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) Child.Jhash", work).stdout.decode()
+    hl = [l for l in q.splitlines() if g["min_cov"] <= int(l.split()[1]) <= g["max_cov"]]
+    assert sorted(hl) == g["hashlist_sorted"]
+    open(os.path.join(work, "HashList"), "w").write("\n".join(hl) + "\n")
+    # the read pull reads the re-paired mates through two FIFOs while the re-pairing is still running
+    sh(f"mkfifo t.mate1.fastq t.mate2.fastq; {gen['Child']} | {BIN}/PassThroughSamCheck.stranded Child.filter.chr t > t.log & "
+       f"timeout 200 {BIN}/RUFUS.Filter HashList t.mate1.fastq t.mate2.fastq Child {k} {g['minq']} {g['thresh']} 4; wait", work)
+    o1 = open(os.path.join(work, "Child.Mutations.Mate1.fastq")).read().splitlines()
+    o2 = open(os.path.join(work, "Child.Mutations.Mate2.fastq")).read().splitlines()
+    assert sorted(o1[0::4]) == g["pulled_mate1_names_sorted"]
+    assert sorted(o2[0::4]) == g["pulled_mate2_names_sorted"]
+    # and the re-paired files themselves are the reference's, byte for byte
+    sh(f"{gen['Child']} | {BIN}/PassThroughSamCheck.stranded c.chr r > r.log", work)
+    assert [md5(open(os.path.join(work, f"r.mate{m}.fastq"), "rb").read()) for m in (1, 2)] == g["repaired_mate_md5"]
+    assert open(os.path.join(work, "r.mate1.fastq")).read().count("\n") // 4 == g["repaired_pairs"]

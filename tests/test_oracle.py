@@ -1,6 +1,7 @@
 """Pin the CPU oracle (oracle/rufus_oracle.c) to outputs of the reference's own
 binaries (tests/golden/*/golden.json, made by tests/golden/make_golden.py)."""
 import gzip
+import json
 import hashlib
 import os
 
@@ -192,3 +193,51 @@ def test_overlap_oracle_differential_vs_reference_binary(seed, tmp_path):
     assert fqd == open(tmp_path / "o.fastqd").read()
     assert fq == open(tmp_path / "o.fastq").read()
     assert bad == open(tmp_path / "o.fastqbad.fastq").read()
+
+
+def _reads_from_lists(names, seqs, quals):
+    from rufus_b200 import fastq
+    offs = np.cumsum([0] + [len(x) for x in seqs]).astype(np.uint64)
+    return fastq.Reads([("@" + n).encode() for n in names], np.frombuffer("".join(seqs).encode(), np.uint8),
+                       np.frombuffer("".join(quals).encode(), np.uint8), offs)
+
+
+def test_bam_mode_matches_reference_chain():
+    """BASELINE configs[0] in BAM mode (tests/golden/testRun_bam): the k-mers of EVERY record the
+    generator prints (-F 3328, sequences as stored) are counted; the read pull runs on the re-paired,
+    strand-restored mates (PassThroughSamCheck.stranded.cpp:197-279: the second-seen record of a name
+    is mate 1, flag 0x10 => reverse complement + reversed quality, leftovers dropped)."""
+    import bam_oracle
+    g = json.load(open(os.path.join(GOLDEN, "testRun_bam", "golden.json")))
+    k, names = g["k"], ("Child", "Mother", "Father")
+    tabs, child = [], None
+    for i, s in enumerate(names):
+        _, lines = bam_oracle.view(os.path.join(GOLDEN, "testRun_bam", s + ".bam"), 3328)
+        f = [l.split("\t") for l in lines]
+        r = _reads_from_lists([x[0] for x in f], [x[9] for x in f], [x[10] for x in f])
+        tabs.append(oracle.count(r.seq, r.offs, k, True, g["L"] if i == 0 else g["ctlL"]))
+        gs = g["samples"][s]
+        assert tabs[-1][0].size == gs["n_distinct"]
+        assert hashlib.md5(_dump_bytes(*tabs[-1], k)).hexdigest() == gs["dump_sorted_md5"]
+        if i == 0:
+            child = f
+    mk, mc = oracle.merge_unique(tabs)
+    assert sorted(kmer.dump_text(mk, mc, k, "\t")) == g["merge_sorted"]
+    hk, hc = oracle.hashlist(tabs[0], tabs[1:], g["min_cov"], g["max_cov"])
+    assert sorted(kmer.dump_text(hk, hc, k)) == g["hashlist_sorted"]
+    comp = str.maketrans("ACGTN", "TGCAN")
+    parked, m1, m2 = {}, [], []
+    for x in child:
+        seq, qual = x[9], x[10]
+        if int(x[1]) & 16:
+            seq, qual = "".join(c for c in seq[::-1] if c in "ACGTN").translate(comp), qual[::-1]
+        if x[0] in parked:
+            m1.append((x[0], seq, qual))
+            m2.append(parked.pop(x[0]))
+        else:
+            parked[x[0]] = (x[0], seq, qual)
+    assert len(m1) == g["repaired_pairs"]
+    r1, r2 = (_reads_from_lists(*zip(*m)) for m in (m1, m2))
+    rset = oracle.rufus_set_from_kmers(kmer.keys_to_text(hk, k))
+    keep = oracle.filter_pairs(r1.seq, r1.qual, r1.offs, r2.seq, r2.qual, r2.offs, k, g["minq"], g["thresh"], rset)
+    assert sorted(r1.names[i].decode() for i in np.flatnonzero(keep)) == g["pulled_mate1_names_sorted"]

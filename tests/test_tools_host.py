@@ -116,14 +116,10 @@ def _pairs_md5(m1, m2):
 def test_bam_ingest_chain_reproduces_bundled_fastq(sample, tmp_path):
     """BAM -> rg_bamview -> PassThroughSamCheck.stranded gives exactly the reads of the bundled
     testRun/X.mate{1,2}.fastq (names, original-strand sequences, qualities); the SAM text equals the
-    restatement's. Father.bam is committed; the other two are read from the reference tree when present."""
+    restatement's."""
     import bam_oracle
     g = json.load(open(os.path.join(BAMG, "golden.json")))["bundled"][sample]
-    bam = os.path.join(BAMG, sample + ".bam")
-    if not os.path.exists(bam):
-        bam = os.path.join(REF_TESTRUN, sample + ".bam")
-        if not os.path.exists(bam):
-            pytest.skip("only Father.bam is committed; the reference tree is not present")
+    bam = os.path.join(GOLDEN, "testRun_bam", sample + ".bam")     # the reference's bundled BAM files (data fixtures)
     assert md5(open(bam, "rb").read()) == g["bam_md5"]
     for tag, excl in (("F3328", 3328), ("all", 0)):
         r = _bamview("view", "-F", str(excl), bam)
