@@ -243,7 +243,7 @@ def test_bam_mode_chain_matches_reference(tmp_path):
     for i, s in enumerate(names):
         lo = g["L"] if i == 0 else g["ctlL"]
         sh(f"mkfifo {s}.fq; {gen[s]} | {BIN}/PassThroughSamCheck {s}.Jelly.chr > {s}.fq & "
-           f"timeout 200 {JF} count --disk -m {k} -L {lo} -s 16M -t 4 -o {s}.Jhash -C {s}.fq; rm {s}.fq; wait", work)
+           f"timeout 60 {JF} count --disk -m {k} -L {lo} -s 16M -t 4 -o {s}.Jhash -C {s}.fq; rm {s}.fq; wait", work)
         sh(f"{JF} histo -f -o {s}.histo {s}.Jhash", work)
         gs = g["samples"][s]
         assert md5(open(os.path.join(work, s + ".histo"), "rb").read()) == gs["histo_md5"]
@@ -257,7 +257,7 @@ def test_bam_mode_chain_matches_reference(tmp_path):
     open(os.path.join(work, "HashList"), "w").write("\n".join(hl) + "\n")
     # the read pull reads the re-paired mates through two FIFOs while the re-pairing is still running
     sh(f"mkfifo t.mate1.fastq t.mate2.fastq; {gen['Child']} | {BIN}/PassThroughSamCheck.stranded Child.filter.chr t > t.log & "
-       f"timeout 200 {BIN}/RUFUS.Filter HashList t.mate1.fastq t.mate2.fastq Child {k} {g['minq']} {g['thresh']} 4; wait", work)
+       f"timeout 60 {BIN}/RUFUS.Filter HashList t.mate1.fastq t.mate2.fastq Child {k} {g['minq']} {g['thresh']} 4; wait", work)
     o1 = open(os.path.join(work, "Child.Mutations.Mate1.fastq")).read().splitlines()
     o2 = open(os.path.join(work, "Child.Mutations.Mate2.fastq")).read().splitlines()
     assert sorted(o1[0::4]) == g["pulled_mate1_names_sorted"]

@@ -133,3 +133,48 @@ def test_bam_ingest_chain_reproduces_bundled_fastq(sample, tmp_path):
                    input=sam, capture_output=True, check=True)
     got = _pairs_md5(tmp_path / "o.mate1.fastq", tmp_path / "o.mate2.fastq")
     assert got == (g["fastq_pairs_md5"], g["fastq_pairs"])
+
+
+# ---- FIFO pipelines of runRufus.sh:963-967: one producer writes both mate files in lock-step, the
+# consumer reads them in lock-step; neither side may wait for a whole block of ONE file
+def _fifo_pipeline(tmp_path, writer, reader_cmd):
+    sam = _bamview("view", "-F", "3328", os.path.join(GOLDEN, "testRun_bam", "Child.bam")).stdout
+    (tmp_path / "in.sam").write_bytes(sam)
+    cmd = (f"mkfifo t.mate1.fastq t.mate2.fastq; {writer} c.chr t < in.sam > t.log & "
+           f"timeout 60 {reader_cmd}; rc=$?; wait; exit $rc")
+    return subprocess.run(cmd, shell=True, cwd=tmp_path, capture_output=True, executable="/bin/bash")
+
+
+def _expected_pairs(tmp_path):
+    subprocess.run(f"{BIN}/PassThroughSamCheck.stranded c2.chr plain < in.sam > plain.log", shell=True, cwd=tmp_path, check=True)
+    n1 = open(tmp_path / "plain.mate1.fastq").read().splitlines()[0::4]
+    n2 = open(tmp_path / "plain.mate2.fastq").read().splitlines()[0::4]
+    assert len(n1) == json.load(open(os.path.join(GOLDEN, "testRun_bam", "golden.json")))["repaired_pairs"]
+    return "".join(f"{a}\t{b}\n" for a, b in zip(n1, n2)).encode()
+
+
+@pytest.mark.parametrize("batch", ["7", "100000"])
+def test_fifo_lockstep_our_writer_our_reader(tmp_path, batch):
+    r = _fifo_pipeline(tmp_path, f"{BIN}/PassThroughSamCheck.stranded",
+                       f"{BIN}/rg_lockstep_check t.mate1.fastq t.mate2.fastq {batch}")
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout == _expected_pairs(tmp_path)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFBIN, "PassThroughSamCheck.stranded")),
+                    reason="reference binaries (oracle/_ref) not present")
+def test_fifo_lockstep_with_reference_tools(tmp_path):
+    # the reference's line-flushing writer feeding our reader ...
+    r = _fifo_pipeline(tmp_path, f"{REFBIN}/PassThroughSamCheck.stranded",
+                       f"{BIN}/rg_lockstep_check t.mate1.fastq t.mate2.fastq 1000")
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout == _expected_pairs(tmp_path)
+    # ... and our block-buffering writer feeding the reference's RUFUS.Filter (a CPU program)
+    g = json.load(open(os.path.join(GOLDEN, "testRun_bam", "golden.json")))
+    (tmp_path / "HashList").write_text("\n".join(g["hashlist_sorted"]) + "\n")
+    subprocess.run("rm -f t.mate1.fastq t.mate2.fastq", shell=True, cwd=tmp_path)
+    r = _fifo_pipeline(tmp_path, f"{BIN}/PassThroughSamCheck.stranded",
+                       f"{REFBIN}/RUFUS.Filter HashList t.mate1.fastq t.mate2.fastq out {g['k']} {g['minq']} {g['thresh']} 2 > f.log")
+    assert r.returncode == 0, r.stderr[-500:]
+    o1 = open(tmp_path / "out.Mutations.Mate1.fastq").read().splitlines()
+    assert sorted(o1[0::4]) == g["pulled_mate1_names_sorted"]

@@ -77,6 +77,7 @@ struct Out {
   void put(char c) { buf.push_back(c); }
   void flush() {
     if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
+    fflush(f);
     buf.clear();
   }
   void record(const char* name, size_t nl, const char* seq, size_t sl, const char* qual, size_t ql) {
@@ -134,6 +135,13 @@ int main(int argc, char** argv) {
       m2.record(f.name, f.name_len, it->second.first.data(), it->second.first.size(), it->second.second.data(),
                 it->second.second.size());
       parked.erase(it);
+      // the two outputs are usually FIFOs read in lock-step by RUFUS.Filter (runRufus.sh:963-967):
+      // both are flushed together and in pieces well below the 64 KiB of a pipe, so that the writer
+      // can never sit on a full mate-1 pipe while the reader waits for mate 2
+      if (m1.buf.size() >= (1u << 14) || m2.buf.size() >= (1u << 14)) {
+        m1.flush();
+        m2.flush();
+      }
     } else {
       parked.emplace(std::move(name), std::make_pair(seq, qual));
     }

@@ -7,6 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <errno.h>
+#include <unistd.h>
+
 #include <string>
 #include <utility>
 #include <vector>
@@ -92,9 +95,13 @@ struct LineReader {
     len -= pos;
     pos = 0;
     if (len == buf.size()) buf.resize(buf.size() * 2);
-    const size_t got = fread(buf.data() + len, 1, buf.size() - len, f);
-    if (got == 0) { eof = true; return false; }
-    len += got;
+    // read(2), not fread: on a FIFO it returns what is there instead of waiting for the whole block,
+    // which is what lets two inputs written in lock-step by one producer (PassThroughSamCheck.stranded
+    // -> RUFUS.Filter, runRufus.sh:966-967) be read in lock-step without a deadlock
+    ssize_t got;
+    do got = read(fileno(f), buf.data() + len, buf.size() - len); while (got < 0 && errno == EINTR);
+    if (got <= 0) { eof = true; return false; }
+    len += (size_t)got;
     return true;
   }
   // next line without its '\n'; false at end of input. The pointer is valid until the next call.

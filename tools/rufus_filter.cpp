@@ -13,47 +13,7 @@
 // for the cases the reference returns 0 for (runRufus.sh only looks at the outputs).
 #include "rg_cli.hpp"
 
-struct Batch {
-  std::vector<char> seq, qual, text;       // text: the four lines of every record, '\n'-terminated
-  std::vector<uint64_t> offs, text_offs;   // per read
-  std::vector<uint32_t> name_len;          // length of line 1 (single-end: where ":MH" goes)
-  void clear() {
-    seq.clear(); qual.clear(); text.clear();
-    offs.assign(1, 0); text_offs.assign(1, 0); name_len.clear();
-  }
-  uint64_t n() const { return offs.size() - 1; }
-};
-
-// one 4-line record; false at end of input (a truncated record counts as the end, as getline would
-// leave empty strings the reference then scores as an empty read)
-static bool read_record(LineReader& lr, Batch& b) {
-  const char* l;
-  size_t n;
-  if (!lr.next(&l, &n)) return false;
-  b.name_len.push_back((uint32_t)n);
-  b.text.insert(b.text.end(), l, l + n);
-  b.text.push_back('\n');
-  size_t seq_len = 0;
-  if (lr.next(&l, &n)) {
-    b.seq.insert(b.seq.end(), l, l + n);
-    seq_len = n;
-    b.text.insert(b.text.end(), l, l + n);
-  }
-  b.text.push_back('\n');
-  if (lr.next(&l, &n)) b.text.insert(b.text.end(), l, l + n);
-  b.text.push_back('\n');
-  size_t qn = 0;
-  if (lr.next(&l, &n)) {
-    qn = n < seq_len ? n : seq_len;
-    b.qual.insert(b.qual.end(), l, l + qn);
-    b.text.insert(b.text.end(), l, l + n);
-  }
-  b.qual.insert(b.qual.end(), seq_len - qn, '\0');   // missing quality = below any MinQ
-  b.text.push_back('\n');
-  b.offs.push_back(b.seq.size());
-  b.text_offs.push_back(b.text.size());
-  return true;
-}
+#include "rg_fastq_batch.hpp"
 
 static std::string slurp(const char* path) {
   FILE* f = fopen(path, "rb");
@@ -161,15 +121,7 @@ int main(int argc, char** argv) {
       }
 #else
     b2.clear();
-    while (b1.n() < batch_reads) {        // lock-step: one record from each file
-      if (!read_record(r1, b1)) { more = false; break; }
-      if (!read_record(r2, b2)) {
-        more = false;                     // mate 2 ended first: drop the unpaired mate-1 record
-        b1.offs.pop_back(); b1.text_offs.pop_back(); b1.name_len.pop_back();
-        b1.seq.resize(b1.offs.back()); b1.qual.resize(b1.offs.back()); b1.text.resize(b1.text_offs.back());
-        break;
-      }
-    }
+    more = read_pair_batch(r1, r2, b1, b2, batch_reads);
     if (b1.n() == 0) break;
     std::vector<uint8_t> keep(b1.n());
     check(rg_filter_pairs(set, b1.seq.data(), b1.qual.data(), b1.offs.data(), b2.seq.data(), b2.qual.data(),
