@@ -135,8 +135,8 @@ struct LineReader {
 // record (what mer_overlap_sequence_parser.hpp:179-207 puts between reads: k-mers never span two
 // records, and the lines of a multi-line record are joined). Format sniffed from the first byte
 // (:124-153). flush(out) is called whenever `out` holds at least `chunk` bytes.
-template <typename Flush>
-static inline void read_sequences(FILE* f, const char* path, ByteBuf& out, size_t chunk, Flush&& flush) {
+template <typename Buf, typename Flush>
+static inline void read_sequences(FILE* f, const char* path, Buf& out, size_t chunk, Flush&& flush) {
   LineReader lr(f);
   const int c0 = lr.peek();
   if (c0 == EOF) return;
