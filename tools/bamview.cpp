@@ -126,6 +126,17 @@ static size_t put_scalar(std::string& o, char t, const unsigned char* p) {
   }
 }
 
+struct SeqPairs {
+  char t[256][2];
+  SeqPairs() {
+    for (int b = 0; b < 256; ++b) {
+      t[b][0] = "=ACMGRSVTWYHKDBN"[b >> 4];
+      t[b][1] = "=ACMGRSVTWYHKDBN"[b & 15];
+    }
+  }
+};
+static const SeqPairs kSeqPairs;
+
 struct Header {
   std::string text;
   std::vector<std::string> refs;
@@ -180,14 +191,22 @@ static void format_record(const unsigned char* r, uint32_t bs, const Header& hd,
   if (l_seq == 0) {
     o.push_back('*');
   } else {
-    for (uint32_t i = 0; i < l_seq; ++i) o.push_back("=ACMGRSVTWYHKDBN"[(p[i >> 1] >> (4 * (1 - (i & 1)))) & 15]);
+    // two bases per packed byte through a 256 x 2 table
+    const size_t at = o.size();
+    o.resize(at + l_seq + 1);
+    char* w = &o[at];
+    for (uint32_t i = 0; i < (l_seq + 1) / 2; ++i) memcpy(w + 2 * i, kSeqPairs.t[p[i]], 2);
+    o.resize(at + l_seq);
   }
   p += (l_seq + 1) / 2;
   o.push_back('\t');
   if (l_seq == 0 || p[0] == 0xFF) {
     o.push_back('*');
   } else {
-    for (uint32_t i = 0; i < l_seq; ++i) o.push_back((char)(p[i] + 33));
+    const size_t at = o.size();
+    o.resize(at + l_seq);
+    char* w = &o[at];
+    for (uint32_t i = 0; i < l_seq; ++i) w[i] = (char)(p[i] + 33);
   }
   p += l_seq;
   const unsigned char* end = r + bs;
@@ -273,20 +292,21 @@ int main(int argc, char** argv) {
   Header hd;
   bool header_done = false;
   const size_t batch_blocks = 64 * (size_t)threads;
-  std::vector<Block> blocks;
+  std::vector<Block> blocks(batch_blocks);                 // reused: the payload buffers keep their capacity
+  std::vector<std::string> text(threads);
+  std::vector<std::pair<size_t, uint32_t>> recs;
   bool eof = false;
   while (!eof) {
-    blocks.clear();
-    while (blocks.size() < batch_blocks) {
-      Block b;
-      if (!read_block(f, b)) { eof = true; break; }
-      blocks.push_back(std::move(b));
+    size_t n_blocks = 0;
+    while (n_blocks < batch_blocks) {
+      if (!read_block(f, blocks[n_blocks])) { eof = true; break; }
+      ++n_blocks;
     }
     // inflate the batch behind what is pending
-    std::vector<size_t> at(blocks.size() + 1, pending.size());
-    for (size_t i = 0; i < blocks.size(); ++i) at[i + 1] = at[i] + blocks[i].isize;
-    pending.resize(at[blocks.size()]);
-    parallel_for(blocks.size(), threads, [&](size_t i) { inflate_block(blocks[i], pending.data() + at[i]); });
+    std::vector<size_t> at(n_blocks + 1, pending.size());
+    for (size_t i = 0; i < n_blocks; ++i) at[i + 1] = at[i] + blocks[i].isize;
+    pending.resize(at[n_blocks]);
+    parallel_for(n_blocks, threads, [&](size_t i) { inflate_block(blocks[i], pending.data() + at[i]); });
 
     size_t p = 0;
     const size_t n = pending.size();
@@ -328,7 +348,7 @@ int main(int argc, char** argv) {
       }
     }
     // record boundaries of the complete records in `pending`
-    std::vector<std::pair<size_t, uint32_t>> recs;
+    recs.clear();
     while (p + 4 <= n) {
       const uint32_t bs = le32(pending.data() + p);
       if (p + 4 + (size_t)bs > n) break;
@@ -338,15 +358,16 @@ int main(int argc, char** argv) {
     }
     if (eof && p != n) die("truncated BAM record at the end of the file");
     const size_t parts = std::min<size_t>(threads, (recs.size() + 255) / 256);
-    std::vector<std::string> text(parts);
+    // (the text buffers live across batches: fresh allocations would fault their pages in again
+    // every batch, which serialises the threads in the kernel)
     parallel_for(parts, threads, [&](size_t t) {
       const size_t lo = recs.size() * t / parts, hi = recs.size() * (t + 1) / parts;
       std::string& o = text[t];
-      o.reserve((hi - lo) * 400);
+      o.clear();
       for (size_t i = lo; i < hi; ++i) format_record(pending.data() + recs[i].first, recs[i].second, hd, o);
     });
-    for (const std::string& t : text)
-      if (fwrite(t.data(), 1, t.size(), stdout) != t.size()) die("write error (stdout)");
+    for (size_t t = 0; t < parts; ++t)
+      if (fwrite(text[t].data(), 1, text[t].size(), stdout) != text[t].size()) die("write error (stdout)");
     pending.erase(pending.begin(), pending.begin() + (ptrdiff_t)p);
   }
   if (!header_done) die("empty input");
