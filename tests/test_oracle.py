@@ -4,6 +4,7 @@ import gzip
 import json
 import hashlib
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -241,3 +242,53 @@ def test_bam_mode_matches_reference_chain():
     rset = oracle.rufus_set_from_kmers(kmer.keys_to_text(hk, k))
     keep = oracle.filter_pairs(r1.seq, r1.qual, r1.offs, r2.seq, r2.qual, r2.offs, k, g["minq"], g["thresh"], rset)
     assert sorted(r1.names[i].decode() for i in np.flatnonzero(keep)) == g["pulled_mate1_names_sorted"]
+
+
+GENSEQ = os.path.join(ROOT, "oracle", "_ref", "generate_sequence")
+
+
+def _fasta_records(path):
+    seqs, cur = [], []
+    for line in open(path, "rb").read().split(b"\n"):
+        if line.startswith(b">"):
+            if cur:
+                seqs.append(b"".join(cur))
+            cur = []
+        else:
+            cur.append(line)
+    if cur:
+        seqs.append(b"".join(cur))
+    return seqs
+
+
+def _histo_text(counts, lower=1, upper=None):
+    """`jellyfish histo` without -f (histo_main.cc:64-84): the non-empty buckets only, low = 1,
+    high = 10000, every count above 10000 in bucket 10001"""
+    c = counts[counts >= lower]
+    if upper is not None:
+        c = c[c <= upper]
+    h = np.bincount(np.minimum(c, 10001).astype(np.int64), minlength=10002)
+    return "".join(f"{i} {v}\n" for i, v in enumerate(h) if v and i >= 1).encode()
+
+
+@pytest.mark.skipif(not os.path.exists(GENSEQ), reason="oracle/_ref/generate_sequence not built (needs /root/reference)")
+def test_jellyfish_known_answers(tmp_path):
+    """The reference's OWN known-answer vectors for this path: the md5 sums in the test scripts of the
+    vendored Jellyfish 2.2.5 tarball (tests/parallel_hashing.sh:6-19, tests/multi_file.sh:6-9) on the
+    inputs of tests/generate_sequence.sh:6-7 (fixed seeds). k = 15, canonical; the m = 40 vectors are
+    outside this path (k <= 32)."""
+    subprocess.run([GENSEQ, "-o", "seq10m", "-m", "10", "-m", "22", "-s", "3141592653", "10000000"], cwd=tmp_path, check=True,
+                   capture_output=True)
+    subprocess.run([GENSEQ, "-o", "seq1m", "-s", "1040104553"] + ["1000000"] * 5, cwd=tmp_path, check=True, capture_output=True)
+
+    def count(files):
+        seqs = [s for f in files for s in _fasta_records(os.path.join(tmp_path, f))]
+        seq = np.frombuffer(b"".join(seqs), np.uint8)
+        offs = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint64)
+        return oracle.count(seq, offs, 15, True, 1)[1]
+
+    c = count(["seq10m.fa"])
+    assert hashlib.md5(_histo_text(c)).hexdigest() == "864c0b0826854bdc72a85d170549b64b"          # ..._m15_s2M.histo
+    assert hashlib.md5(_histo_text(c, 2, 3)).hexdigest() == "94625cd2d59e278f08421a673eb0926a"    # ..._m15_s2M_L2_U3.histo
+    c = count(["seq1m_0.fa", "seq1m_1.fa", "seq1m_2.fa", "seq10m.fa", "seq1m_3.fa", "seq1m_4.fa"])
+    assert hashlib.md5(_histo_text(c)).hexdigest() == "d93b7678037814c256d1d9120a0e6422"          # multi_file_m15_s2M.histo
