@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -53,17 +54,27 @@ static bool split_sam(const char* l, size_t n, Fields& f) {
   return true;
 }
 
-static void revcomp_into(std::string& out, const char* s, size_t n) {
-  for (size_t j = n; j-- > 0;) {
-    switch (s[j]) {
-      case 'A': out.push_back('T'); break;
-      case 'C': out.push_back('G'); break;
-      case 'G': out.push_back('C'); break;
-      case 'T': out.push_back('A'); break;
-      case 'N': out.push_back('N'); break;
-      default: break;                      // dropped, like the reference's switch without default
-    }
+// reverse complement of A/C/G/T/N; every other character is dropped, like the reference's switch
+// without a default (PassThroughSamCheck.stranded.cpp:209-215)
+struct CompTable {
+  char t[256];
+  CompTable() {
+    memset(t, 0, sizeof(t));
+    t[(unsigned char)'A'] = 'T'; t[(unsigned char)'C'] = 'G'; t[(unsigned char)'G'] = 'C';
+    t[(unsigned char)'T'] = 'A'; t[(unsigned char)'N'] = 'N';
   }
+};
+static const CompTable kComp;
+static void revcomp_into(std::string& out, const char* s, size_t n) {
+  const size_t at = out.size();
+  out.resize(at + n);
+  char* w = &out[at];
+  for (size_t j = n; j-- > 0;) {
+    const char c = kComp.t[(unsigned char)s[j]];
+    *w = c;
+    w += c != 0;
+  }
+  out.resize((size_t)(w - out.data()));
 }
 
 struct Out {
@@ -100,7 +111,10 @@ int main(int argc, char** argv) {
   FILE* f2 = fopen((std::string(argv[2]) + ".mate2.fastq").c_str(), "w");
   if (!f1 || !f2) { printf("ERROR, Output file could not be opened -%s\n", argv[1]); return 0; }
   Out m1(f1), m2(f2);
-  std::unordered_map<std::string, std::pair<std::string, std::string>> parked;
+  // a parked record = one allocation holding name, sequence and quality (as they will be written);
+  // the map key is a view of the name inside it
+  struct Parked { char* blob; uint32_t name_len, seq_len, qual_len; };
+  std::unordered_map<std::string_view, Parked> parked;
   std::string seq, qual;
 #else
   Out out(stdout);
@@ -117,24 +131,33 @@ int main(int argc, char** argv) {
       current.assign(f.chr, f.chr_len);
     }
 #ifdef RG_STRANDED
-    const bool reverse = (atoi(std::string(f.flag, f.flag_len).c_str()) & 16) != 0;
-    seq.clear();
-    qual.clear();
-    if (reverse) {
+    char flag_text[16];
+    int flag;
+    if (f.flag_len < sizeof(flag_text)) {
+      memcpy(flag_text, f.flag, f.flag_len);
+      flag_text[f.flag_len] = 0;
+      flag = atoi(flag_text);
+    } else {
+      flag = atoi(std::string(f.flag, f.flag_len).c_str());
+    }
+    const char* sq = f.seq;
+    const char* ql = f.qual;
+    size_t sq_len = f.seq_len, ql_len = f.qual_len;
+    if (flag & 16) {
+      seq.clear();
       revcomp_into(seq, f.seq, f.seq_len);
       qual.assign(f.qual, f.qual_len);
       for (size_t a = 0, b = qual.size(); a + 1 < b; ++a, --b) std::swap(qual[a], qual[b - 1]);
-    } else {
-      seq.assign(f.seq, f.seq_len);
-      qual.assign(f.qual, f.qual_len);
+      sq = seq.data(); sq_len = seq.size();
+      ql = qual.data(); ql_len = qual.size();
     }
-    std::string name(f.name, f.name_len);
-    auto it = parked.find(name);
+    auto it = parked.find(std::string_view(f.name, f.name_len));
     if (it != parked.end()) {
-      m1.record(f.name, f.name_len, seq.data(), seq.size(), qual.data(), qual.size());
-      m2.record(f.name, f.name_len, it->second.first.data(), it->second.first.size(), it->second.second.data(),
-                it->second.second.size());
+      const Parked pk = it->second;
+      m1.record(f.name, f.name_len, sq, sq_len, ql, ql_len);
+      m2.record(f.name, f.name_len, pk.blob + pk.name_len, pk.seq_len, pk.blob + pk.name_len + pk.seq_len, pk.qual_len);
       parked.erase(it);
+      free(pk.blob);
       // the two outputs are usually FIFOs read in lock-step by RUFUS.Filter (runRufus.sh:963-967):
       // both are flushed together and in pieces well below the 64 KiB of a pipe, so that the writer
       // can never sit on a full mate-1 pipe while the reader waits for mate 2
@@ -143,7 +166,14 @@ int main(int argc, char** argv) {
         m2.flush();
       }
     } else {
-      parked.emplace(std::move(name), std::make_pair(seq, qual));
+      Parked pk;
+      pk.name_len = (uint32_t)f.name_len; pk.seq_len = (uint32_t)sq_len; pk.qual_len = (uint32_t)ql_len;
+      pk.blob = (char*)malloc(f.name_len + sq_len + ql_len + 1);
+      if (!pk.blob) die("out of memory");
+      memcpy(pk.blob, f.name, f.name_len);
+      memcpy(pk.blob + f.name_len, sq, sq_len);
+      memcpy(pk.blob + f.name_len + sq_len, ql, ql_len);
+      parked.emplace(std::string_view(pk.blob, f.name_len), pk);
     }
 #else
     out.record(f.name, f.name_len, f.seq, f.seq_len, f.qual, f.qual_len);
