@@ -1,0 +1,70 @@
+"""Structural guarantees the task contract asks for, checked statically (CPU):
+ * the oracle is test infrastructure: nothing under rufus_b200/ or tools/ imports, links or executes
+   anything under oracle/; bench.py touches it only in its CPU-baseline / reference-arm code;
+ * the product fails loudly without its CUDA library or without a CUDA device (no CPU fallback)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def _sources(*dirs, exts):
+    for d in dirs:
+        for base, _, files in os.walk(os.path.join(ROOT, d)):
+            if "bin" in base.split(os.sep) or "__pycache__" in base:
+                continue
+            for f in files:
+                if f.endswith(exts):
+                    yield os.path.join(base, f)
+
+
+def test_product_code_never_touches_the_oracle():
+    pat = re.compile(r"import\s+oracle|from\s+oracle|liboracle|bam_oracle|overlap_oracle|[\"'/]oracle[\"'/]")
+    bad = []
+    for path in _sources("rufus_b200", "tools", "include", exts=(".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+        if os.path.basename(path) in ("overlap_bench.py", "multigpu_check.py", "debug_n2.py"):
+            continue                                   # measurement / parity drivers, not product code
+        for i, line in enumerate(open(path, errors="replace"), 1):
+            if pat.search(line):
+                bad.append(f"{os.path.relpath(path, ROOT)}:{i}: {line.strip()}")
+    assert not bad, "\n".join(bad)
+
+
+def test_bench_uses_the_oracle_only_for_the_cpu_baseline():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    # every mention of oracle/ sits inside cpu_reference_pass (the cpu_baseline leg and --impl reference)
+    start = src.index("def cpu_reference_pass")
+    end = src.index("def run_reference_arm")
+    outside = src[:start] + src[end:]
+    assert "import oracle" not in outside and '"oracle"' not in outside
+
+
+def test_library_missing_fails_loudly(tmp_path):
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from rufus_b200 import api\n"
+            "api.LIB_PATH = %r\n"
+            "try:\n    api.lib()\nexcept api.RufusGpuError as e:\n    print('LOUD:', e)\n") % (ROOT, str(tmp_path / "nope.so"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "LOUD:" in r.stdout and "no CPU fallback" in r.stdout
+
+
+def test_no_device_fails_loudly():
+    """rg_init without a usable CUDA device returns NULL with a message (the build container has none;
+    on a GPU box the device is hidden through CUDA_VISIBLE_DEVICES)."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from rufus_b200 import api\n"
+            "try:\n    api.Context(0)\n    print('UNEXPECTED: context created')\n"
+            "except api.RufusGpuError as e:\n    print('LOUD:', e)\n") % ROOT
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert "LOUD:" in r.stdout, r.stdout + r.stderr
+    # the executables do the same: message on stderr, non-zero exit for jellyfish
+    jf = os.path.join(ROOT, "tools", "bin", "jellyfish")
+    if os.path.exists(jf):
+        r = subprocess.run([jf, "count", "-m", "25", "-s", "1M", "-C", "-o", "/dev/null", os.path.join(ROOT, "README.md")],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode != 0 and r.stderr.strip()
