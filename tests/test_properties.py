@@ -100,3 +100,43 @@ def test_hashlist_is_the_set_difference(subj, ctl, k):
     s, c = dict(zip(ts[0].tolist(), ts[1].tolist())), set(tc[0].tolist())
     want = {x: n for x, n in s.items() if n >= 5 and n <= 1000 and x not in c}
     assert dict(zip(hk.tolist(), hc.tolist())) == want
+
+
+# ---- the read pull (src/RUFUS.Filter.cpp:196-262, src/RUFUS.Filter.ss.cpp:164-201) against a
+# string-level statement of the streak rule
+read_q = st.integers(1, 70).flatmap(lambda n: st.tuples(st.text(alphabet="ACGTN", min_size=n, max_size=n),
+                                                        st.text(alphabet="#,5J", min_size=n, max_size=n)))
+
+
+def _naive_hits(seq, qual, k, minq, mutant, last_base_tested):
+    streak = hits = 0
+    for i in range(len(seq) if last_base_tested else len(seq) - 1):
+        if ord(qual[i]) - 33 < minq or seq[i] == "N":
+            streak = 0
+        else:
+            streak += 1
+        if streak >= k and seq[i - k + 1:i + 1] in mutant:
+            hits += 1
+    return hits
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(read_q, read_q), min_size=1, max_size=8), st.integers(3, 12), st.sampled_from([0, 10, 15, 30]),
+       st.integers(1, 3), st.data())
+def test_read_pull_equals_the_streak_rule(pairs, k, minq, thresh, data):
+    # mutant k-mers: some windows of the reads themselves (either strand), so that there are hits
+    windows = [s[i:i + k] for (s, _), (t, _) in pairs for s in (s, t) for i in range(len(s) - k + 1) if "N" not in s[i:i + k]]
+    chosen = data.draw(st.lists(st.sampled_from(windows), max_size=6)) if windows else []
+    chosen = [w if data.draw(st.booleans()) else w[::-1].translate(COMP) for w in chosen]
+    mutant = set(chosen) | {w[::-1].translate(COMP) for w in chosen}
+    rset = oracle.rufus_set_from_kmers(chosen) if chosen else np.zeros(0, np.uint64)
+    m1 = [p[0] for p in pairs]
+    m2 = [p[1] for p in pairs]
+    s1, o1 = _pack([s for s, _ in m1]); q1, _ = _pack([q for _, q in m1])
+    s2, o2 = _pack([s for s, _ in m2]); q2, _ = _pack([q for _, q in m2])
+    keep = oracle.filter_pairs(s1, q1, o1, s2, q2, o2, k, minq, thresh, rset)
+    want = [int(_naive_hits(a[0], a[1], k, minq, mutant, False) >= thresh or
+                _naive_hits(b[0], b[1], k, minq, mutant, False) >= thresh) for a, b in pairs]
+    assert keep.tolist() == want
+    hits = oracle.filter_single(s1, q1, o1, k, minq, rset)
+    assert hits.tolist() == [_naive_hits(a[0], a[1], k, minq, mutant, True) for a in m1]
