@@ -151,9 +151,11 @@ def build_select(subj, controls, min_subject: int, max_subject: int, max_control
     keys, counts = sk[sel], sc[sel]
     total = np.zeros(keys.size, np.int64)
     for ck, cc in controls:
+        if ck.size == 0:
+            continue                      # an empty control contributes nothing
         pos = np.searchsorted(ck, keys)
         pos[pos >= ck.size] = 0
-        hit = (ck.size > 0) & (ck[pos] == keys) if ck.size else np.zeros(keys.size, bool)
+        hit = ck[pos] == keys
         total += np.where(hit, cc[pos].astype(np.int64), 0)
     keep = total <= max_control_sum
     return keys[keep], counts[keep], total[keep].astype(np.uint32)

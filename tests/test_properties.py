@@ -140,3 +140,42 @@ def test_read_pull_equals_the_streak_rule(pairs, k, minq, thresh, data):
     assert keep.tolist() == want
     hits = oracle.filter_single(s1, q1, o1, k, minq, rset)
     assert hits.tolist() == [_naive_hits(a[0], a[1], k, minq, mutant, True) for a in m1]
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.lists(reads_st, min_size=1, max_size=4), st.integers(4, 16))
+def test_merge_emits_keys_of_exactly_one_input(samples, k):
+    """modified merge (merge_files.cc:86-152): a k-mer is printed iff exactly one input file holds it
+    and its count there is >= 5"""
+    tabs = []
+    for r in samples:
+        seq, offs = _pack(r * 5)
+        tabs.append(oracle.count(seq, offs, k, True, 2))
+    mk, mc = oracle.merge_unique(tabs)
+    want = {}
+    for i, (keys, counts) in enumerate(tabs):
+        others = set().union(*[set(t[0].tolist()) for j, t in enumerate(tabs) if j != i]) if len(tabs) > 1 else set()
+        for x, c in zip(keys.tolist(), counts.tolist()):
+            if x not in others and c >= 5:
+                want[x] = c
+    assert dict(zip(mk.tolist(), mc.tolist())) == want
+    assert mk.tolist() == sorted(mk.tolist())
+
+
+@settings(max_examples=80, deadline=None)
+@given(reads_st, st.lists(reads_st, min_size=0, max_size=3), st.integers(4, 16), st.integers(1, 4), st.integers(4, 30),
+       st.integers(0, 6))
+def test_build_select_is_the_threshold_rule(subj, ctls, k, lo, hi, max_ctl):
+    """RUFUS.Build (src/RUFUS.Build.cpp:224-262): subject entries with lo <= count <= hi whose summed
+    control count is <= max_ctl"""
+    seq, offs = _pack(subj * 3)
+    ts = oracle.count(seq, offs, k, True, 1)
+    tcs = []
+    for r in ctls:
+        seq, offs = _pack(r)
+        tcs.append(oracle.count(seq, offs, k, True, 1))
+    keys, sc, cs = oracle.build_select(ts, tcs, lo, hi, max_ctl)
+    lut = [dict(zip(t[0].tolist(), t[1].tolist())) for t in tcs]
+    want = [(x, c, sum(d.get(x, 0) for d in lut)) for x, c in zip(ts[0].tolist(), ts[1].tolist())
+            if lo <= c <= hi and sum(d.get(x, 0) for d in lut) <= max_ctl]
+    assert list(zip(keys.tolist(), sc.tolist(), cs.tolist())) == want
