@@ -178,3 +178,38 @@ def test_fifo_lockstep_with_reference_tools(tmp_path):
     assert r.returncode == 0, r.stderr[-500:]
     o1 = open(tmp_path / "out.Mutations.Mate1.fastq").read().splitlines()
     assert sorted(o1[0::4]) == g["pulled_mate1_names_sorted"]
+
+
+# ---- differential fuzz of the two SAM -> FASTQ drop-ins against the reference binaries (both are CPU
+# programs): random well-formed records with repeated names, reverse flags, IUPAC / lower-case bases,
+# unpaired reads, several chromosomes
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFBIN, "PassThroughSamCheck.stranded")),
+                    reason="reference binaries (oracle/_ref) not present")
+@pytest.mark.parametrize("seed", range(6))
+def test_passthrough_differential_fuzz(seed, tmp_path):
+    import random
+    rnd = random.Random(1000 + seed)
+    lines = []
+    names = [f"read{rnd.randrange(60)}:{rnd.randrange(3)}" for _ in range(300)]
+    for nm in names:
+        L = rnd.choice([0, 1, 5, 36, 100, 151]) if rnd.random() < 0.3 else 100
+        seq = "".join(rnd.choice("ACGTNacgtRYKM" if rnd.random() < 0.05 else "ACGT") for _ in range(L)) or "*"
+        qual = "".join(chr(33 + rnd.randrange(42)) for _ in range(len(seq)))
+        flag = rnd.choice([0, 16, 65, 81, 97, 113, 129, 145, 147, 163, 99, 83, 1024 + 99, 2048 + 16, 4, 77, 141])
+        chrom = rnd.choice(["1", "1", "2", "X", "GL000207.1", "*"])
+        tags = "\t".join(rnd.sample(["NM:i:0", "MD:Z:100", "AS:i:98", "RG:Z:grp", "XS:i:0"], rnd.randrange(1, 4)))
+        lines.append("\t".join([nm, str(flag), chrom, str(rnd.randrange(1, 10 ** 6)), "60", f"{len(seq)}M", "=",
+                                str(rnd.randrange(1, 10 ** 6)), str(rnd.randrange(-500, 500)), seq, qual, tags]))
+    sam = ("\n".join(lines) + "\n").encode()
+    ours = subprocess.run([os.path.join(BIN, "PassThroughSamCheck"), str(tmp_path / "a.chr")], input=sam, capture_output=True)
+    ref = subprocess.run([os.path.join(REFBIN, "PassThroughSamCheck"), str(tmp_path / "b.chr")], input=sam, capture_output=True)
+    assert ref.returncode == 0 and ours.returncode == 0
+    assert ours.stdout == ref.stdout
+    assert open(tmp_path / "a.chr").read() == open(tmp_path / "b.chr").read()
+    subprocess.run([os.path.join(BIN, "PassThroughSamCheck.stranded"), str(tmp_path / "c.chr"), str(tmp_path / "o")], input=sam,
+                   capture_output=True, check=True)
+    subprocess.run([os.path.join(REFBIN, "PassThroughSamCheck.stranded"), str(tmp_path / "d.chr"), str(tmp_path / "r")], input=sam,
+                   capture_output=True, check=True)
+    for m in (1, 2):
+        assert open(tmp_path / f"o.mate{m}.fastq", "rb").read() == open(tmp_path / f"r.mate{m}.fastq", "rb").read()
+    assert open(tmp_path / "c.chr").read() == open(tmp_path / "d.chr").read()
