@@ -15,7 +15,9 @@ import hashlib, json, os, shutil, struct, sys, zlib
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bam_oracle  # noqa: E402
+from bam_build import build_bam, expected_sam  # noqa: E402
 REF = "/root/reference/testRun"
 out = os.path.join(HERE, "bam")
 
@@ -33,18 +35,6 @@ def pairs_md5(m1, m2):
     a, b = load(m1), load(m2)
     rows = sorted(n + "\t" + "\t".join("\t".join(x) for x in sorted((a[n], b[n]))) for n in a)
     return md5("\n".join(rows).encode()), len(rows)
-
-
-def bgzf(data, block):
-    o = b""
-    for p in list(range(0, len(data), block)) + [None]:
-        chunk = b"" if p is None else data[p:p + block]
-        c = zlib.compressobj(6, zlib.DEFLATED, -15)
-        comp = c.compress(chunk) + c.flush()
-        bsize = 12 + 6 + len(comp) + 8
-        o += b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
-        o += comp + struct.pack("<II", zlib.crc32(chunk), len(chunk))
-    return o
 
 
 def main():
@@ -82,35 +72,9 @@ def main():
         seq = "".join("ACGT"[(i * 7 + j * (1 + i % 3)) & 3] for j in range(37 + i % 5))
         recs.append((f"bulk{i:04d}", 1024 if i % 10 == 0 else (16 if i % 3 == 0 else 0), i % 2, i * 3, 30, [(len(seq), "M")], -1, -1, 0,
                      seq, "".join(chr(33 + (i + j) % 40) for j in range(len(seq))), [("NM", "C", i % 4)], f"NM:i:{i % 4}"))
-    body = b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(refs))
-    for n, l in refs:
-        body += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
-    fmt = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I", "f": "<f"}
-    sam = []
-    for name, flag, ref, pos, mapq, cig, nref, npos, tlen, seq, qual, tags, tagtext in recs:
-        r = struct.pack("<iiBBHHHiiii", ref, pos, len(name) + 1, mapq, 4680, len(cig), flag, len(seq), nref, npos, tlen)
-        r += name.encode() + b"\0"
-        r += b"".join(struct.pack("<I", (n << 4) | ops[o]) for n, o in cig)
-        padded = seq + ("=" if len(seq) & 1 else "")
-        r += bytes((codes[padded[i]] << 4) | codes[padded[i + 1]] for i in range(0, len(padded), 2))
-        r += bytes([0xFF] * len(seq)) if qual is None else bytes(ord(c) - 33 for c in qual)
-        for tag, t, v in tags:
-            r += tag.encode() + t.encode()
-            if t == "A":
-                r += v.encode()
-            elif t in "ZH":
-                r += v.encode() + b"\0"
-            elif t == "B":
-                r += v[0].encode() + struct.pack("<I", len(v[1])) + b"".join(struct.pack(fmt[v[0]], x) for x in v[1])
-            else:
-                r += struct.pack(fmt[t], v)
-        body += struct.pack("<i", len(r)) + r
-        refname = lambda i: "*" if i < 0 else refs[i][0]
-        sam.append("\t".join([name, str(flag), refname(ref), str(pos + 1), str(mapq),
-                              "".join(f"{n}{o}" for n, o in cig) or "*",
-                              "*" if nref < 0 else ("=" if nref == ref else refname(nref)), str(npos + 1), str(tlen),
-                              seq or "*", "*" if (qual is None or not seq) else qual, tagtext]))
-    open(os.path.join(out, "synthetic.bam"), "wb").write(bgzf(body, 997))
+    recs = [r[:12] for r in recs]
+    sam = expected_sam(refs, recs)
+    open(os.path.join(out, "synthetic.bam"), "wb").write(build_bam(text, refs, recs, block=997))
     open(os.path.join(out, "synthetic.sam"), "w").write("\n".join(sam) + "\n")
     g["synthetic"] = {"records": len(sam), "header": text}
     json.dump(g, open(os.path.join(out, "golden.json"), "w"), indent=1, sort_keys=True)

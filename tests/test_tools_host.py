@@ -213,3 +213,59 @@ def test_passthrough_differential_fuzz(seed, tmp_path):
     for m in (1, 2):
         assert open(tmp_path / f"o.mate{m}.fastq", "rb").read() == open(tmp_path / f"r.mate{m}.fastq", "rb").read()
     assert open(tmp_path / "c.chr").read() == open(tmp_path / "d.chr").read()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_bamview_fuzz_against_spec_writer_and_restatement(seed, tmp_path):
+    """random records (every tag type, arrays, unmapped, absent SEQ/QUAL/CIGAR, long names) written by
+    tests/bam_build.py with random BGZF block sizes: rg_bamview == the text the writer states ==
+    oracle/bam_oracle.py, with and without flag filters"""
+    import random
+    import bam_oracle
+    from bam_build import build_bam, expected_sam
+    rnd = random.Random(77 + seed)
+    refs = [(f"chr{i}", 1000 * (i + 1)) for i in range(rnd.randrange(1, 5))]
+    text = "@HD\tVN:1.6\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
+
+    def rand_tag(i):
+        t = rnd.choice("AcCsSiIfZHB")
+        tag = "X" + "abcdefghijklmnop"[i]
+        if t == "A":
+            return (tag, t, rnd.choice("QZa!~"))
+        if t == "Z":
+            return (tag, t, "".join(rnd.choice("ab c:,;|-_09") for _ in range(rnd.randrange(0, 20))))
+        if t == "H":
+            return (tag, t, "".join(rnd.choice("0123456789ABCDEF") for _ in range(2 * rnd.randrange(0, 6))))
+        lim = {"c": (-128, 127), "C": (0, 255), "s": (-32768, 32767), "S": (0, 65535), "i": (-2 ** 31, 2 ** 31 - 1),
+               "I": (0, 2 ** 32 - 1)}
+        if t == "f":
+            return (tag, t, rnd.choice([0.0, 1.5, -2.25, 1e-3, 12345.678, 3e10, -1e-7]))
+        if t == "B":
+            sub = rnd.choice("cCsSiIf")
+            n = rnd.randrange(0, 6)
+            vals = [rnd.choice([0.5, -1.0, 2.75, 1e6]) if sub == "f" else rnd.randint(*lim[sub]) for _ in range(n)]
+            return (tag, t, (sub, vals))
+        return (tag, t, rnd.randint(*lim[t]))
+
+    recs = []
+    for r in range(rnd.randrange(1, 120)):
+        L = rnd.choice([0, 1, 2, 7, 50, 151, 400])
+        seq = "".join(rnd.choice("ACGTN" if rnd.random() < 0.9 else "=ACMGRSVTWYHKDBN") for _ in range(L))
+        qual = None if rnd.random() < 0.15 else "".join(chr(33 + rnd.randrange(60)) for _ in range(L))
+        ref = rnd.randrange(-1, len(refs))
+        cig = [] if ref < 0 or rnd.random() < 0.1 else [(rnd.randrange(1, 300), rnd.choice("MIDNSHP=X")) for _ in range(rnd.randrange(1, 6))]
+        name = "".join(rnd.choice("abcXYZ0189:/_.") for _ in range(rnd.randrange(1, 200)))
+        recs.append((name, rnd.choice([0, 4, 16, 65, 77, 83, 99, 141, 147, 163, 256 + 16, 1024 + 99, 2048 + 83, 3328 + 1]),
+                     ref, rnd.randrange(-1, 10 ** 6) if ref >= 0 else -1, rnd.randrange(0, 255), cig,
+                     rnd.randrange(-1, len(refs)), rnd.randrange(-1, 10 ** 6), rnd.randrange(-10 ** 5, 10 ** 5), seq, qual,
+                     [rand_tag(i) for i in range(rnd.randrange(0, 8))]))
+    bam = tmp_path / "f.bam"
+    bam.write_bytes(build_bam(text, refs, recs, block=rnd.choice([61, 300, 997, 4096, 65280])))
+    want = expected_sam(refs, recs)
+    _, lines = bam_oracle.view(str(bam))
+    assert lines == want
+    for excl, req in ((0, 0), (3328, 0), (4, 0), (0, 16), (1024, 1)):
+        keep = [l for l in want if not int(l.split("\t")[1]) & excl and (int(l.split("\t")[1]) & req) == req]
+        r = _bamview("-F", str(excl), "-f", str(req), "-@", str(rnd.choice([1, 2, 5])), str(bam))
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.decode().splitlines() == keep
