@@ -277,7 +277,8 @@ def main():
     for i in range(args.warmup):
         r = pipe.step()
     st0 = pipe.tables[0].stats()
-    log(f"rank {rank}: warm; mutant k-mers {r['n_mutant']}, pulled {r['n_kept']}, subject table {st0}")
+    log(f"rank {rank}: warm; mutant k-mers {r['n_mutant']}, pulled {r['n_kept']}, subject table {st0}, "
+        f"geometry {pipe.tables[0].geometry()}")
     n_occ = [t.stats()["occurrences"] for t in pipe.tables]
 
     sampler = ClockSampler(local_rank)

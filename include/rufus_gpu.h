@@ -97,7 +97,8 @@ int rg_count_push_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uin
 /* Make room for up to extra_distinct more distinct keys (grows and re-hashes the table if the
  * load would pass ~60 %): for streaming callers that learn the input size as they read it. */
 int rg_table_reserve(rg_table* t, uint64_t extra_distinct);
-/* Finish counting: flush staged keys, resolve spills. */
+/* Finish counting: wait for the enqueued pushes, check them (RG_ERR_FULL if k-mers found no slot), grow the
+ * table when its overflow region is filling up. */
 int rg_count_end(rg_table* t);
 void rg_table_free(rg_table* t);
 /* Empty the table for re-use (keeps its allocation and geometry). */
@@ -109,16 +110,23 @@ int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occurrences, u
 int rg_table_k(rg_table* t);
 int rg_table_canonical(rg_table* t);
 
-/* Multi-GPU building blocks (hash-prefix sharding): extract+partition
- * into `n_parts` contiguous buckets by the top bits of the mixing hash, for an
- * all-to-all between ranks, and insert received packed keys. All DEVICE pointers.
- * part_offsets_dev: n_parts+1 uint64 written by the library. keys_out_dev needs
- * room for one uint64 per window (n_bytes). */
-int rg_extract_partition_dev(rg_ctx* ctx, int k, int canonical, const char* dev_stream, uint64_t n_bytes,
-                             uint32_t read_stride, uint32_t n_parts, uint64_t* keys_out_dev,
-                             uint64_t* part_offsets_dev);
-/* which partition (0..n_parts-1) owns a jf key — same function the kernels use */
-uint32_t rg_key_partition(uint64_t jf_key, uint32_t n_parts);
+/* Multi-GPU building blocks (hash-prefix sharding). The hash prefix of a k-mer is the mixed
+ * order value of its MINIMIZER (the smallest, under a strand-symmetric hash, of its k-m+1 m-mers): the
+ * consecutive k-mers of a read that share it travel to their shard and tile as one 16-byte record.
+ * rg_extract_partition_dev: extract + partition the k-mers of a read stream into the table's shard_parts
+ * contiguous buckets (one per owning shard), for an NCCL all-to-all between ranks; the received packed
+ * keys are inserted with rg_count_push_keys_dev. All DEVICE pointers. part_offsets_dev: n_parts+1 uint64
+ * written by the library. keys_out_dev needs room for one uint64 per window (n_bytes). */
+int rg_extract_partition_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
+                             uint64_t* keys_out_dev, uint64_t* part_offsets_dev);
+/* which shard (0..n_parts-1) owns a jf key of a table with `groups` hash-prefix groups over all shards and
+ * minimizer length m — the function the kernels use (host arithmetic, no device needed) */
+uint32_t rg_key_shard(uint64_t jf_key, int k, int m, uint32_t groups, uint32_t n_parts);
+/* minimizer length the library picks for k-mers of length k in a table of n_tiles_global tiles */
+int rg_minimizer_len(int k, uint64_t n_tiles_global);
+/* geometry of a table: tiles of this shard, hash-prefix groups over all shards, minimizer length, slots of
+ * the overflow region (any pointer may be NULL) */
+int rg_table_geometry(rg_table* t, uint32_t* n_tiles, uint32_t* groups_global, int* m, uint64_t* ovf_slots);
 int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_keys);
 /* restrict a table to the keys of shard `part` of `n_parts` (tile numbering is global) */
 int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts);

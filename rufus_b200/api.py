@@ -73,8 +73,10 @@ def lib():
         "rg_table_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "rg_table_k": (i32, [vp]),
         "rg_table_canonical": (i32, [vp]),
-        "rg_extract_partition_dev": (i32, [vp, i32, i32, vp, u64, u32, u32, vp, vp]),
-        "rg_key_partition": (u32, [u64, u32]),
+        "rg_extract_partition_dev": (i32, [vp, vp, u64, u32, vp, vp]),
+        "rg_key_shard": (u32, [u64, i32, i32, u32, u32]),
+        "rg_minimizer_len": (i32, [i32, u64]),
+        "rg_table_geometry": (i32, [vp, vp, vp, vp, vp]),
         "rg_count_push_keys_dev": (i32, [vp, vp, u64]),
         "rg_table_set_shard": (i32, [vp, u32, u32]),
         "rg_table_p2p_prepare": (i32, [vp, u32, u64]),
@@ -286,6 +288,12 @@ class KmerTable:
         if not h:
             raise _err("rg_table_from_pairs")
         return cls(ctx, k, canonical, _handle=h)
+
+    def geometry(self):
+        """tiles of this shard, hash-prefix groups over all shards, minimizer length, overflow slots"""
+        nt, gg, m, ov = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_uint64()
+        _check(lib().rg_table_geometry(self.h, C.byref(nt), C.byref(gg), C.byref(m), C.byref(ov)), "rg_table_geometry")
+        return {"n_tiles": nt.value, "groups": gg.value, "m": m.value, "ovf_slots": ov.value}
 
     # -- reading -------------------------------------------------------------
     def stats(self):

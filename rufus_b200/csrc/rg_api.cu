@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "rg_internal.cuh"
+#include "rg_sk.cuh"
 
 static thread_local std::string g_err;
 void rg_set_error(const std::string& msg) { g_err = msg; }
@@ -271,11 +272,20 @@ static void drop_buckets(rg_table* t) {
   }
 }
 
-static int table_alloc_tiles(rg_table* t, uint32_t wanted) {
+// overflow region of a table with main_slots tile slots: 1/16 of them, at least one tile's worth (power of two)
+static uint64_t ovf_for(uint64_t main_slots) {
+  uint64_t o = RG_TILE_SLOTS;
+  while (o < main_slots / 16) o <<= 1;
+  return o;
+}
+
+static int table_alloc_tiles(rg_table* t, uint32_t wanted, uint64_t ovf_slots = 0) {
   rg_ctx* ctx = t->ctx;
   uint32_t n_tiles, group_tiles;
   choose_geometry(t, wanted, &n_tiles, &group_tiles);
-  const uint64_t slots = (uint64_t)n_tiles << RG_TILE_BITS;
+  const uint64_t main_slots = (uint64_t)n_tiles << RG_TILE_BITS;
+  if (ovf_slots < ovf_for(main_slots)) ovf_slots = ovf_for(main_slots);
+  const uint64_t slots = main_slots + ovf_slots;
   RG_CUDA_OK(cudaMalloc(&t->keys, slots * 8));
   RG_CUDA_OK(cudaMalloc(&t->counts, slots * 4));
   RG_CUDA_OK(cudaMemsetAsync(t->keys, 0xFF, slots * 8, ctx->stream));
@@ -284,6 +294,9 @@ static int table_alloc_tiles(rg_table* t, uint32_t wanted) {
   t->group_tiles = group_tiles;
   t->n_tiles_global = n_tiles * t->shard_parts;
   t->tile_first = n_tiles * t->shard_part;
+  t->ovf_slots = ovf_slots;
+  t->ovf_used = 0;
+  t->m = sk_choose_m(t->k, t->n_tiles_global);
   return 0;
 }
 
@@ -291,75 +304,124 @@ static uint32_t tiles_for(uint64_t est_distinct) {
   // aim for <= 60 % load
   uint64_t n = (est_distinct * 5 / 3 + RG_TILE_SLOTS - 1) >> RG_TILE_BITS;
   if (n < 1) n = 1;
-  if (n > (1u << 18)) n = 1u << 18;   // 2^18 tiles = 4 Gi slots: the slot bits come out of a 32-bit hash
+  if (n > (1u << 22)) n = 1u << 22;
   return (uint32_t)n;
 }
 
-// grow to new_tiles tiles and re-insert every (key,count)
-static int table_grow(rg_table* t, uint32_t new_tiles) {
+// rebuild with new_tiles tiles (and at least new_ovf overflow slots) and re-insert every (key,count)
+static int table_grow(rg_table* t, uint32_t new_tiles, uint64_t new_ovf = 0) {
   rg_ctx* ctx = t->ctx;
   uint64_t* old_keys = t->keys;
   uint32_t* old_counts = t->counts;
-  const uint64_t old_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
-  t->keys = nullptr;
-  t->counts = nullptr;
+  const uint64_t old_slots = rg_table_slots(t);
   if (t->p2p_block) {
     rg_set_error("count: a peer-to-peer table cannot grow (its slabs are exported); raise est_distinct");
-    t->keys = old_keys;
-    t->counts = old_counts;
     return RG_ERR_FULL;
   }
-  int rc = table_alloc_tiles(t, new_tiles);
+  t->keys = nullptr;
+  t->counts = nullptr;
+  int rc = table_alloc_tiles(t, new_tiles, new_ovf);
   if (rc) return rc;
   // bucket staging is sized per tile count: drop it, it is rebuilt on the next push
   drop_buckets(t);
+  RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, RG_ST_WORDS * sizeof(uint64_t), ctx->stream));
   rc = rg_launch_rehash(t, old_keys, old_counts, old_slots);
   if (rc) return rc;
-  RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  uint64_t st[RG_ST_WORDS];
+  rc = read_scalars(ctx, t->d_status, RG_ST_WORDS, st);
   cudaFree(old_keys);
   cudaFree(old_counts);
+  if (rc) return rc;
+  if (st[RG_ST_LOST]) {      // (cannot happen: the new table is larger than what it has to hold)
+    rg_set_error("count: rehash overflow");
+    return RG_ERR_FULL;
+  }
+  t->ovf_used = st[RG_ST_OVF_NEW];
+  RG_CUDA_OK(cudaMemsetAsync(t->d_status + RG_ST_OVF_NEW, 0, sizeof(uint64_t), ctx->stream));
+  t->tiles_dirty = true;
   return 0;
 }
 
-// after a push: resolve keys that found their tile (or bucket) full
-static int table_resolve_spill(rg_table* t) {
+// the spill list (last resort of a push that found tiles AND overflow region full) holds at least
+// min(n_keys / 4, 2^27) pairs, 4 Mi at the least
+static int ensure_spill(rg_table* t, uint64_t n_keys) {
+  uint64_t want = std::max<uint64_t>(1ull << 22, std::min<uint64_t>(n_keys / 4, 1ull << 27));
+  if (t->spill_cap >= want) return 0;
   rg_ctx* ctx = t->ctx;
-  for (int round = 0; round < 8; ++round) {
-    uint64_t st[3];
-    int rc = read_scalars(ctx, t->d_status, 3, st);
+  if (t->spill_keys) {
+    int rc = rg_table_finish(t);          // (entries of earlier pushes are resolved first)
     if (rc) return rc;
-    if (st[1] != 0) {
-      rg_set_error("count: " + std::to_string(st[1]) + " keys do not belong to this table's shard");
+    RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(t->spill_keys);
+    cudaFree(t->spill_counts);
+    t->spill_keys = nullptr;
+    t->spill_counts = nullptr;
+    t->spill_cap = 0;
+  }
+  RG_CUDA_OK(cudaMalloc(&t->spill_keys, want * 8));
+  RG_CUDA_OK(cudaMalloc(&t->spill_counts, want * 4));
+  t->spill_cap = want;
+  return 0;
+}
+
+// after a push: read the status words; re-insert what found no slot after growing the table; keep the
+// overflow region at most half full
+static int table_check_status(rg_table* t) {
+  rg_ctx* ctx = t->ctx;
+  for (int round = 0; round < 10; ++round) {
+    uint64_t st[RG_ST_WORDS];
+    int rc = read_scalars(ctx, t->d_status, RG_ST_WORDS, st);
+    if (rc) return rc;
+    if (st[RG_ST_FOREIGN] != 0) {
+      rg_set_error("count: " + std::to_string(st[RG_ST_FOREIGN]) + " keys do not belong to this table's shard");
       return RG_ERR_ARG;
     }
-    if (st[2] != 0) {
-      rg_set_error("count: rehash overflow");
+    if (st[RG_ST_LOST] > t->spill_cap) {
+      rg_set_error("count: table full, " + std::to_string(st[RG_ST_LOST]) +
+                   " k-mer occurrences found no slot and the spill list overflowed; raise est_distinct or "
+                   "call rg_table_reserve before the push");
       return RG_ERR_FULL;
     }
-    if (st[0] == 0) return 0;
-    if (st[0] > t->spill_cap) {
-      rg_set_error("count: table full and spill list overflowed (" + std::to_string(st[0]) +
-                   " keys); raise est_distinct");
+    if (st[RG_ST_OVF_NEW]) {
+      t->ovf_used += st[RG_ST_OVF_NEW];
+      RG_CUDA_OK(cudaMemsetAsync(t->d_status + RG_ST_OVF_NEW, 0, sizeof(uint64_t), ctx->stream));
+    }
+    const uint64_t n_spill = st[RG_ST_LOST];
+    if (n_spill == 0 && t->ovf_used * 2 <= t->ovf_slots) return 0;
+    if (t->p2p_block) {
+      if (n_spill == 0) return 0;      // (fixed geometry: it runs until the overflow region is really full)
+      rg_set_error("count: a peer-to-peer table is full (its geometry is fixed); raise est_distinct");
       return RG_ERR_FULL;
     }
-    // move the spill aside, clear the counter, then make room when the tiles themselves were full
-    uint64_t* tmp = nullptr;
-    RG_CUDA_OK(cudaMalloc(&tmp, st[0] * 8));
-    RG_CUDA_OK(cudaMemcpyAsync(tmp, t->spill, st[0] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, 3 * sizeof(uint64_t), ctx->stream));
-    if (round > 0) {
-      // worst case every spilled key is new and every current slot is taken: size for <= 50 % load
-      const uint64_t cur_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
-      const uint32_t want = std::max<uint32_t>(t->n_tiles * 2, tiles_for(cur_slots + st[0]));
-      rc = table_grow(t, want);
-      if (rc) { cudaFree(tmp); return rc; }
+    // Either the tiles are too loaded (more tiles), or a few minimizers own more k-mers than a tile holds
+    // (a larger overflow region). The spilled pairs are moved aside and re-inserted into the rebuilt table.
+    uint64_t* tmp_k = nullptr;
+    uint32_t* tmp_c = nullptr;
+    if (n_spill) {
+      RG_CUDA_OK(cudaMalloc(&tmp_k, n_spill * 8));
+      RG_CUDA_OK(cudaMalloc(&tmp_c, n_spill * 4));
+      RG_CUDA_OK(cudaMemcpyAsync(tmp_k, t->spill_keys, n_spill * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      RG_CUDA_OK(cudaMemcpyAsync(tmp_c, t->spill_counts, n_spill * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      RG_CUDA_OK(cudaMemsetAsync(t->d_status + RG_ST_LOST, 0, sizeof(uint64_t), ctx->stream));
     }
-    rc = rg_launch_insert_keys(t, tmp, st[0], nullptr);
-    RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
+    uint64_t distinct = 0;
+    rc = rg_launch_stats(t, ctx->d_scratch);
+    if (rc == 0) rc = read_scalars(ctx, ctx->d_scratch, 1, &distinct);
+    if (rc == 0) {
+      const uint64_t main_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+      uint32_t want_tiles = t->n_tiles;
+      // (every spilled pair may be a new key)
+      if ((distinct + n_spill) * 2 > main_slots)
+        want_tiles = std::max<uint32_t>(t->n_tiles * 2, tiles_for((distinct + n_spill) * 2));
+      rc = table_grow(t, want_tiles, t->ovf_slots * 2);
+    }
+    if (rc == 0 && n_spill) rc = rg_launch_insert_keys(t, tmp_k, n_spill, tmp_c);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp_k);
+    cudaFree(tmp_c);
     if (rc) return rc;
   }
-  rg_set_error("count: could not resolve spill after growing 7 times");
+  rg_set_error("count: could not make room after growing 10 times");
   return RG_ERR_FULL;
 }
 
@@ -376,13 +438,16 @@ static int ensure_stage(rg_table* t, uint64_t bytes) {
   return 0;
 }
 
-// (re)size the per-tile bucket slabs for a push of at most n_keys keys and zero the cursors
-static int prepare_buckets(rg_table* t, uint64_t n_keys) {
+// (re)size the per-tile bucket slabs (super-k-mer records) for a push of n_bytes stream bytes and zero the
+// cursors. Records that find their slab full are inserted straight into the table by the partition pass, so
+// the sizing is a speed matter only.
+static int prepare_buckets(rg_table* t, uint64_t n_bytes) {
   rg_ctx* ctx = t->ctx;
-  // bucket capacity: mean keys per tile + 25 % + slack; overflow goes to the spill list
-  const uint64_t mean = n_keys / t->n_tiles + 1;
-  uint64_t cap = mean + mean / 4 + 1024 + rg_partition_pad_keys(t->n_tiles, n_keys);
-  cap = (cap + 3) & ~3ull;  // slabs start on a 32-byte sector boundary
+  const uint64_t n_rec = (uint64_t)((double)n_bytes * rg_partition_record_density(t->k, t->m)) + 1;
+  // bucket capacity: mean records per tile + 30 % + slack
+  const uint64_t mean = n_rec / t->n_tiles + 1;
+  uint64_t cap = mean + mean * 3 / 10 + 128;
+  cap = (cap + 1) & ~1ull;  // slabs start on a 32-byte sector boundary
   if (!t->part_cursor) RG_CUDA_OK(cudaMalloc(&t->part_cursor, (uint64_t)t->n_tiles * sizeof(uint32_t)));
   if (t->part_cap < cap * t->n_tiles) {
     if (t->part_keys) {
@@ -390,7 +455,7 @@ static int prepare_buckets(rg_table* t, uint64_t n_keys) {
       cudaFree(t->part_keys);
       t->part_keys = nullptr;
     }
-    RG_CUDA_OK(cudaMalloc(&t->part_keys, cap * t->n_tiles * 8 + 64));   // + slack: 16-byte staging reads may touch one key past a slab
+    RG_CUDA_OK(cudaMalloc(&t->part_keys, cap * t->n_tiles * 16 + 64));
     t->part_cap = cap * t->n_tiles;
   }
   t->bucket_cap = (uint32_t)(t->part_cap / t->n_tiles);
@@ -398,9 +463,9 @@ static int prepare_buckets(rg_table* t, uint64_t n_keys) {
   // two-level partition: the slabs of the groups (a peer-to-peer table owns fixed ones)
   if (t->group_tiles > 1 && !t->p2p_block) {
     const uint32_t n_groups = t->n_tiles / t->group_tiles;
-    const uint64_t gmean = n_keys / n_groups + 1;
-    uint64_t gcap = gmean + gmean / 4 + 4096;
-    gcap = (gcap + 3) & ~3ull;
+    const uint64_t gmean = n_rec / n_groups + 1;
+    uint64_t gcap = gmean + gmean / 4 + 1024;
+    gcap = (gcap + 1) & ~1ull;
     if (!t->grp_cursor) RG_CUDA_OK(cudaMalloc(&t->grp_cursor, (uint64_t)n_groups * sizeof(uint32_t)));
     if (t->grp_alloc_keys < gcap * n_groups) {
       if (t->grp_keys) {
@@ -408,7 +473,7 @@ static int prepare_buckets(rg_table* t, uint64_t n_keys) {
         cudaFree(t->grp_keys);
         t->grp_keys = nullptr;
       }
-      RG_CUDA_OK(cudaMalloc(&t->grp_keys, gcap * n_groups * 8 + 64));
+      RG_CUDA_OK(cudaMalloc(&t->grp_keys, gcap * n_groups * 16 + 64));
       t->grp_alloc_keys = gcap * n_groups;
     }
     t->grp_cap = (uint32_t)(t->grp_alloc_keys / n_groups);
@@ -435,7 +500,8 @@ static int push_dev_piece(rg_table* t, const char* dev_stream, uint64_t n_bytes,
   ep.k = t->k;
   ep.canonical = t->canonical;
   ep.skip = skip;
-  int rc;
+  int rc = ensure_spill(t, n_bytes);
+  if (rc) return rc;
   if (t->mode == RG_MODE_TILED) {
     rc = prepare_buckets(t, n_bytes);
     if (rc) return rc;
@@ -500,7 +566,7 @@ static int p2p_collect_spill(rg_table* t) {
     rg_set_error("count: peer-to-peer spill list overflowed; raise max_keys_per_push");
     return RG_ERR_FULL;
   }
-  if (n_spill) return rg_launch_insert_keys(t, t->p2p_spill, n_spill, nullptr);
+  if (n_spill) return rg_launch_insert_records(t, t->p2p_spill, n_spill);
   return 0;
 }
 
@@ -510,7 +576,7 @@ int rg_table_finish(rg_table* t) {
     const int prc = p2p_collect_spill(t);
     if (prc) return prc;
   }
-  const int rc = table_resolve_spill(t);
+  const int rc = table_check_status(t);
   if (rc == 0) t->unchecked = false;
   return rc;
 }
@@ -550,13 +616,12 @@ rg_table* rg_count_begin(rg_ctx* ctx, int k, int canonical, uint64_t est_distinc
     delete t;
     return nullptr;
   }
-  t->spill_cap = 1ull << 22;
-  if (cudaMalloc(&t->spill, t->spill_cap * 8) != cudaSuccess || cudaMalloc(&t->d_status, 8 * sizeof(uint64_t)) != cudaSuccess) {
+  if (cudaMalloc(&t->d_status, RG_ST_WORDS * sizeof(uint64_t)) != cudaSuccess || ensure_spill(t, 0) != 0) {
     rg_set_error("rg_count_begin: out of device memory");
     rg_table_free(t);
     return nullptr;
   }
-  cudaMemsetAsync(t->d_status, 0, 8 * sizeof(uint64_t), ctx->stream);
+  cudaMemsetAsync(t->d_status, 0, RG_ST_WORDS * sizeof(uint64_t), ctx->stream);
   return t;
 }
 
@@ -569,6 +634,7 @@ int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts) {
   t->shard_parts = n_parts;
   t->n_tiles_global = t->n_tiles * n_parts;
   t->tile_first = t->n_tiles * part;
+  t->m = sk_choose_m(t->k, t->n_tiles_global);     // (the same on every shard: it depends on the global tile count)
   return 0;
 }
 
@@ -591,9 +657,9 @@ static void p2p_layout(const rg_table* t, uint64_t* off_status, uint64_t* off_sp
   *off_status = o;
   o += 256;
   *off_spill = o;
-  o += ((t->p2p_spill_cap * 8 + 255) / 256) * 256;
+  o += ((t->p2p_spill_cap * 16 + 255) / 256) * 256;
   *off_slabs = o;
-  o += n_groups * (uint64_t)t->grp_cap * 8 + 256;
+  o += n_groups * (uint64_t)t->grp_cap * 16 + 256;
   *total = o;
 }
 static void p2p_pointers(const rg_table* t, void* base, uint32_t r, rg_table* into) {
@@ -602,8 +668,8 @@ static void p2p_pointers(const rg_table* t, void* base, uint32_t r, rg_table* in
   char* b = static_cast<char*>(base);
   into->peer_cursor[r] = reinterpret_cast<uint32_t*>(b);
   into->peer_status[r] = reinterpret_cast<uint64_t*>(b + os);
-  into->peer_spill[r] = reinterpret_cast<uint64_t*>(b + osp);
-  into->peer_keys[r] = reinterpret_cast<uint64_t*>(b + osl);
+  into->peer_spill[r] = reinterpret_cast<uint4*>(b + osp);
+  into->peer_keys[r] = reinterpret_cast<uint4*>(b + osl);
 }
 
 int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_keys_per_push) {
@@ -631,8 +697,9 @@ int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_ke
   int rc = table_alloc_tiles(t, std::max<uint32_t>(wanted, 2));
   if (rc) return rc;
   const uint64_t n_groups = (uint64_t)(t->n_tiles / t->group_tiles) * t->shard_parts;      // sub-slabs I own
-  const uint64_t gmean = max_keys_per_push / n_groups + 1;
-  t->grp_cap = (uint32_t)((gmean + gmean / 2 + 2048 + 3) & ~3ull);
+  const uint64_t n_rec = (uint64_t)((double)max_keys_per_push * rg_partition_record_density(t->k, t->m)) + 1;
+  const uint64_t gmean = n_rec / n_groups + 1;
+  t->grp_cap = (uint32_t)((gmean + gmean / 2 + 1024 + 3) & ~3ull);
   t->p2p_spill_cap = 1ull << 20;
   t->p2p_max_keys = max_keys_per_push;
   uint64_t os, osp, osl, tot;
@@ -741,6 +808,7 @@ int rg_count_push(rg_table* t, const char* host_stream, uint64_t n_bytes) {
   if (n_bytes == 0) return 0;
   rg_ctx* ctx = t->ctx;
   int rc = slots_ensure(ctx);
+  if (rc == 0) rc = ensure_spill(t, n_bytes);
   if (rc) return rc;
   if (t->mode == RG_MODE_TILED) {
     rc = prepare_buckets(t, n_bytes);
@@ -811,14 +879,9 @@ int rg_count_push_reads(rg_table* t, const char* host_seq, const uint64_t* host_
 
 int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_keys) {
   if (!t) return RG_ERR_ARG;
-  int rc;
-  if (t->mode == RG_MODE_TILED && n_keys >= (uint64_t)t->n_tiles * 64) {
-    rc = prepare_buckets(t, n_keys);
-    if (rc == 0) rc = rg_launch_partition_keys(t, dev_keys, n_keys);
-    if (rc == 0) rc = finish_tiled_push(t);
-  } else {
-    rc = rg_launch_insert_keys(t, dev_keys, n_keys, nullptr);
-  }
+  // packed keys carry no read context: every key finds its tile through its own minimizer (global atomics)
+  int rc = ensure_spill(t, n_keys);
+  if (rc == 0) rc = rg_launch_insert_keys(t, dev_keys, n_keys, nullptr);
   if (rc) return rc;
   t->tiles_dirty = true;
   t->unchecked = true;
@@ -832,7 +895,9 @@ int rg_count_end(rg_table* t) {
 }
 
 // make room for up to extra_distinct new keys before a push (streaming callers do not know the
-// number of distinct k-mers up front): grows (re-hashes) when the load would exceed ~60 %
+// number of distinct k-mers up front): grows (re-hashes) when the load would exceed ~60 %, and keeps
+// the overflow region large enough to take all of them (whatever their minimizers, the push cannot
+// lose a key)
 int rg_table_reserve(rg_table* t, uint64_t extra_distinct) {
   if (!t) return RG_ERR_ARG;
   int rc = rg_table_finish(t);
@@ -840,9 +905,13 @@ int rg_table_reserve(rg_table* t, uint64_t extra_distinct) {
   uint64_t distinct = 0;
   rc = rg_table_stats(t, &distinct, nullptr, nullptr);
   if (rc) return rc;
-  const uint32_t want = tiles_for(distinct + extra_distinct);
-  if (want <= t->n_tiles) return 0;
-  return table_grow(t, std::max<uint32_t>(want, t->n_tiles + t->n_tiles / 2));
+  uint32_t want = tiles_for(distinct + extra_distinct);
+  uint64_t want_ovf = t->ovf_slots;
+  while (want_ovf < 2 * (t->ovf_used + extra_distinct)) want_ovf <<= 1;
+  if (want <= t->n_tiles && want_ovf == t->ovf_slots) return 0;
+  if (want > t->n_tiles) want = std::max<uint32_t>(want, t->n_tiles + t->n_tiles / 2);
+  else want = t->n_tiles;
+  return table_grow(t, want, want_ovf);
 }
 
 int rg_table_trim(rg_table* t) {
@@ -859,14 +928,12 @@ int rg_table_trim(rg_table* t) {
 int rg_table_clear(rg_table* t) {
   if (!t) return RG_ERR_ARG;
   rg_ctx* ctx = t->ctx;
-  const uint64_t slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
-  // the tiled insert rewrites every tile of an empty table, so only the direct path needs the memset
-  if (t->mode != RG_MODE_TILED) {
-    RG_CUDA_OK(cudaMemsetAsync(t->keys, 0xFF, slots * 8, ctx->stream));
-    RG_CUDA_OK(cudaMemsetAsync(t->counts, 0, slots * 4, ctx->stream));
-  }
-  RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, 8 * sizeof(uint64_t), ctx->stream));
+  const uint64_t slots = rg_table_slots(t);
+  RG_CUDA_OK(cudaMemsetAsync(t->keys, 0xFF, slots * 8, ctx->stream));
+  RG_CUDA_OK(cudaMemsetAsync(t->counts, 0, slots * 4, ctx->stream));
+  RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, RG_ST_WORDS * sizeof(uint64_t), ctx->stream));
   t->tiles_dirty = false;
+  t->ovf_used = 0;
   return 0;
 }
 
@@ -877,7 +944,8 @@ void rg_table_free(rg_table* t) {
   cudaFree(t->keys);
   cudaFree(t->counts);
   cudaFree(t->d_status);
-  cudaFree(t->spill);
+  cudaFree(t->spill_keys);
+  cudaFree(t->spill_counts);
   cudaFree(t->part_keys);
   cudaFree(t->part_cursor);
   if (t->p2p_block) {
@@ -906,27 +974,40 @@ int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occ, uint64_t*
   if (rc) return rc;
   if (n_distinct) *n_distinct = v[0];
   if (n_occ) *n_occ = v[1];
-  if (n_slots) *n_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  if (n_slots) *n_slots = rg_table_slots(t);
   return 0;
 }
 
 int rg_table_k(rg_table* t) { return t ? t->k : 0; }
 int rg_table_canonical(rg_table* t) { return t ? t->canonical : 0; }
 
-uint32_t rg_key_partition(uint64_t jf_key, uint32_t n_parts) { return rg_tile_of_key(jf_key, n_parts); }
+uint32_t rg_key_shard(uint64_t jf_key, int k, int m, uint32_t groups, uint32_t n_parts) {
+  if (k < 1 || k > 32 || m < 1 || m > 16 || m > k || n_parts == 0 || groups < n_parts) return 0;
+  return rg_group_of_mh(rg_min_hash(jf_key, (uint32_t)k, (uint32_t)m), groups) / (groups / n_parts);
+}
+int rg_minimizer_len(int k, uint64_t n_tiles_global) { return sk_choose_m(k, n_tiles_global); }
+int rg_table_geometry(rg_table* t, uint32_t* n_tiles, uint32_t* groups_global, int* m, uint64_t* ovf_slots) {
+  if (!t) return RG_ERR_ARG;
+  if (n_tiles) *n_tiles = t->n_tiles;
+  if (groups_global) *groups_global = t->n_tiles_global / t->group_tiles;
+  if (m) *m = t->m;
+  if (ovf_slots) *ovf_slots = t->ovf_slots;
+  return 0;
+}
 
-int rg_extract_partition_dev(rg_ctx* ctx, int k, int canonical, const char* dev_stream, uint64_t n_bytes,
-                             uint32_t read_stride, uint32_t n_parts, uint64_t* keys_out_dev,
-                             uint64_t* part_offsets_dev) {
-  if (!ctx || k < 1 || k > 32) return RG_ERR_ARG;
+int rg_extract_partition_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
+                             uint64_t* keys_out_dev, uint64_t* part_offsets_dev) {
+  if (!t) return RG_ERR_ARG;
+  rg_ctx* ctx = t->ctx;
   ExtractParams ep;
   ep.stream = dev_stream;
   ep.n_bytes = n_bytes;
   ep.brk = nullptr;
   ep.read_stride = read_stride;
-  ep.k = k;
-  ep.canonical = canonical;
-  return rg_launch_extract_partition(ctx, ep, n_parts, keys_out_dev, part_offsets_dev, ctx->d_scratch + 64);
+  ep.k = t->k;
+  ep.canonical = t->canonical;
+  return rg_launch_extract_partition(ctx, ep, rg_view(t).geo, t->shard_parts, keys_out_dev, part_offsets_dev,
+                                     ctx->d_scratch + 64);
 }
 
 // ---- histo ----------------------------------------------------------------
@@ -1043,12 +1124,14 @@ int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_co
 }
 
 // ---- subtraction ------------------------------------------------------------
-static int fill_others(OtherTables& ot, rg_table* const* others, const uint64_t* other_min, int n_others, int k) {
+static int fill_others(OtherTables& ot, rg_table* const* others, const uint64_t* other_min, int n_others, int k,
+                       const rg_table* subj) {
   if (n_others < 0 || n_others > 16) {
     rg_set_error("subtract: at most 16 control/exclude tables");
     return RG_ERR_ARG;
   }
   ot.n = n_others;
+  ot.same_geo = 0;
   for (int i = 0; i < n_others; ++i) {
     if (!others[i] || others[i]->k != k) {
       rg_set_error("subtract: tables must share k");
@@ -1057,6 +1140,10 @@ static int fill_others(OtherTables& ot, rg_table* const* others, const uint64_t*
     const int frc = rg_table_finish(others[i]);
     if (frc) return frc;
     ot.tv[i] = rg_view(others[i]);
+    if (subj && others[i]->n_tiles == subj->n_tiles && others[i]->group_tiles == subj->group_tiles &&
+        others[i]->n_tiles_global == subj->n_tiles_global && others[i]->tile_first == subj->tile_first &&
+        others[i]->m == subj->m)
+      ot.same_geo |= 1u << i;
     uint64_t m = other_min ? other_min[i] : 1;
     ot.min_count[i] = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(m, 1), 0xFFFFFFFFull);
   }
@@ -1071,7 +1158,7 @@ int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* othe
   OtherTables ot;
   int rc = rg_table_finish(subj);
   if (rc) return rc;
-  rc = fill_others(ot, others, other_min, n_others, subj->k);
+  rc = fill_others(ot, others, other_min, n_others, subj->k, subj);
   if (rc) return rc;
   // candidates: c >= subj_min (in the subject .Jhash), c >= floor (merge_files.cc:149), min_cov <= c <= max_cov
   uint64_t lo = std::max<uint64_t>(std::max<uint64_t>(subj_min, floor), 1);
@@ -1122,7 +1209,7 @@ int64_t rg_build_select(rg_table* subj, int64_t min_subject, int64_t max_subject
   OtherTables ot;
   int rc = rg_table_finish(subj);
   if (rc) return rc;
-  rc = fill_others(ot, controls, nullptr, n_controls, subj->k);
+  rc = fill_others(ot, controls, nullptr, n_controls, subj->k, subj);
   if (rc) return rc;
   if (needed) *needed = 0;
   if (max_subject < 0 || max_control_sum < 0) return 0;     // nothing can pass

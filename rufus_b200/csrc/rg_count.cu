@@ -7,9 +7,12 @@
 #include "rg_internal.cuh"
 
 #include "rg_extract.cuh"
+#include "rg_sk.cuh"
 
 // ---------------------------------------------------------------------------
-// Path 1 (RG_MODE_DIRECT): extraction fused with global-memory CAS/atomic insert.
+// Path 1 (RG_MODE_DIRECT): extraction fused with global-memory CAS/atomic insert. The tile of every
+// k-mer comes from its minimizer, recomputed per key (rg_min_hash): the slow, simple path for small
+// inputs and for the callers that bring packed keys.
 // ---------------------------------------------------------------------------
 constexpr int COUNT_THREADS = 256;
 constexpr int COUNT_R = 16;                       // windows per thread
@@ -17,22 +20,17 @@ constexpr int CHUNK = COUNT_THREADS * COUNT_R;    // window starts per CTA chunk
 using CountStage = StageT<COUNT_THREADS, COUNT_R>;
 
 __global__ void __launch_bounds__(COUNT_THREADS)
-count_direct_kernel(ExtractParams ep, TableView tv, uint64_t* status, uint64_t* spill, uint64_t spill_cap) {
+count_direct_kernel(ExtractParams ep, TableView tv) {
   __shared__ CountStage sm;
   const uint64_t n_chunks = (ep.n_bytes + CHUNK - 1) / CHUNK;
+  if (blockIdx.x == 0 && threadIdx.x == 0) tv.status[RG_ST_DIRECT] = 1;
   for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     __syncthreads();
     stage_super(sm, ep, c * CHUNK);
     __syncthreads();
     roll_windows(sm, threadIdx.x, ep.k, ep.canonical, [&](int, uint64_t key) {
       if (key == RG_EMPTY) return;
-      const int rc = rg_table_add(tv, key, 1);
-      if (rc == 1) {
-        const uint64_t at = atomicAdd((unsigned long long*)&status[0], 1ull);
-        if (at < spill_cap) spill[at] = key;
-      } else if (rc == 2) {
-        atomicAdd((unsigned long long*)&status[1], 1ull);
-      }
+      rg_table_add(tv, key, 1);
     }, c == 0 ? ep.skip : 0u);
   }
 }
@@ -45,27 +43,21 @@ int rg_launch_count_direct(rg_table* t, const ExtractParams& ep) {
   if (n_chunks < grid) grid = (unsigned)n_chunks;
   {
     rg_launch_scope _ls(ctx, "count_direct_kernel");
-    count_direct_kernel<<<grid, COUNT_THREADS, 0, ctx->stream>>>(ep, rg_view(t), t->d_status, t->spill, t->spill_cap);
+    count_direct_kernel<<<grid, COUNT_THREADS, 0, ctx->stream>>>(ep, rg_view(t));
   }
   RG_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-// insert a list of packed keys (spill resolution, received all-to-all buffers, .Jhash loads)
+// insert a list of packed keys, each `counts[i]` (or 1) times (received all-to-all buffers, .Jhash loads)
 __global__ void __launch_bounds__(256)
-insert_keys_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n, TableView tv,
-                   uint64_t* status, uint64_t* spill, uint64_t spill_cap) {
+insert_keys_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n, TableView tv) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) tv.status[RG_ST_DIRECT] = 1;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t key = __ldg(keys + i);
     const uint32_t add = counts ? __ldg(counts + i) : 1u;
     if (add == 0) continue;
-    const int rc = rg_table_add(tv, key, add);
-    if (rc == 1) {
-      const uint64_t at = atomicAdd((unsigned long long*)&status[0], 1ull);
-      if (at < spill_cap) spill[at] = key;   // (count lost for counted inserts: caller sizes tables to avoid it)
-    } else if (rc == 2) {
-      atomicAdd((unsigned long long*)&status[1], 1ull);
-    }
+    rg_table_add(tv, key, add);
   }
 }
 
@@ -77,21 +69,50 @@ int rg_launch_insert_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n, con
   if (need < grid) grid = (unsigned)need;
   {
     rg_launch_scope _ls(ctx, "insert_keys_kernel");
-    insert_keys_kernel<<<grid, 256, 0, ctx->stream>>>(dev_keys, dev_counts, n, rg_view(t), t->d_status, t->spill,
-                                                      t->spill_cap);
+    insert_keys_kernel<<<grid, 256, 0, ctx->stream>>>(dev_keys, dev_counts, n, rg_view(t));
+  }
+  RG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// the k-mers of spilled super-k-mer records (peer-to-peer counting: what other GPUs could not place in a slab)
+__global__ void __launch_bounds__(256)
+insert_records_kernel(const uint4* __restrict__ recs, uint64_t n, TableView tv, int canonical) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) tv.status[RG_ST_DIRECT] = 1;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 rec = __ldg(recs + i);
+    const uint32_t tile = rg_tile_of_mh(rec.w & ~15u, tv.geo) - tv.tile_first;
+    if (tile >= tv.n_tiles) {
+      atomicAdd((unsigned long long*)&tv.status[RG_ST_FOREIGN], 1ull);
+      continue;
+    }
+    const uint32_t len = (rec.w & 15u) + 1;
+    for (uint32_t o = 0; o < len; ++o) rg_table_add_at(tv, tile, sk_key(rec, o, tv.geo.k, canonical), 1u);
+  }
+}
+
+int rg_launch_insert_records(rg_table* t, const uint4* dev_recs, uint64_t n) {
+  if (n == 0) return 0;
+  rg_ctx* ctx = t->ctx;
+  unsigned grid = rg_grid(ctx, 8);
+  const uint64_t need = (n + 255) / 256;
+  if (need < grid) grid = (unsigned)need;
+  {
+    rg_launch_scope _ls(ctx, "insert_records_kernel");
+    insert_records_kernel<<<grid, 256, 0, ctx->stream>>>(dev_recs, n, rg_view(t), t->canonical);
   }
   RG_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 __global__ void rehash_kernel(const uint64_t* __restrict__ old_keys, const uint32_t* __restrict__ old_counts,
-                              uint64_t n_slots, TableView tv, uint64_t* status) {
+                              uint64_t n_slots, TableView tv) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) tv.status[RG_ST_DIRECT] = 1;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_slots;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t key = old_keys[i];
     if (key == RG_EMPTY) continue;
-    const uint32_t c = old_counts[i];
-    if (rg_table_add(tv, key, c) != 0) atomicAdd((unsigned long long*)&status[2], 1ull);
+    rg_table_add(tv, key, old_counts[i]);
   }
 }
 
@@ -99,7 +120,7 @@ int rg_launch_rehash(rg_table* dst, const uint64_t* old_keys, const uint32_t* ol
   rg_ctx* ctx = dst->ctx;
   {
     rg_launch_scope _ls(ctx, "rehash_kernel");
-    rehash_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(old_keys, old_counts, n_slots, rg_view(dst), dst->d_status);
+    rehash_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(old_keys, old_counts, n_slots, rg_view(dst));
   }
   RG_CUDA_OK(cudaGetLastError());
   return 0;
@@ -125,24 +146,23 @@ int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads,
 }
 
 // ---------------------------------------------------------------------------
-// Path 2, step 2: one CTA per tile. The tile (128 KiB keys + 64 KiB counts) is
-// brought into shared memory with TMA bulk copies (or initialised empty), the
-// bucket's keys are streamed with coalesced 16-byte loads and applied with
-// shared-memory CAS/atomics, and the tile is written back with TMA bulk stores.
-// HBM traffic per tile: bucket read once + tile written once (+ read once when
-// the table already holds data) — two streaming passes instead of one random
-// DRAM round trip per k-mer.
+// Path 2, step 2: one CTA per tile. The tile (128 KiB keys + 64 KiB counts) is brought into shared
+// memory with TMA bulk copies (or initialised empty), the bucket's super-k-mer RECORDS are streamed with
+// coalesced 16-byte loads, their k-mers are re-extracted, canonicalised and applied with shared-memory
+// CAS/atomics, and the tile is written back with TMA bulk stores. HBM traffic per tile: bucket read once
+// (~3 bytes per k-mer) + tile written once (+ read once when the table already holds data).
 // ---------------------------------------------------------------------------
-#ifndef TILE_THREADS_N
-#define TILE_THREADS_N 1024
+#ifndef TILE_WARPS_N
+#define TILE_WARPS_N 24
 #endif
-constexpr int TILE_THREADS = TILE_THREADS_N;
-#ifndef TILE_AHEAD
-#define TILE_AHEAD 4                 // steps of 32 keys a warp keeps in flight in registers (one block)
-#endif
-// retry queue of a warp: 64 x 16 bytes (key, slot | probes << RG_TILE_BITS, -)
+constexpr int TILE_WARPS = TILE_WARPS_N;
+constexpr int TILE_THREADS = TILE_WARPS * 32;
+// per warp: retry queue of 64 x (8-byte key, 4-byte slot | probes << RG_TILE_BITS), the 32 records of the
+// current batch, and the 512-bit map of the k-mer positions where a record starts
 constexpr uint32_t TILE_Q = 64;
-constexpr size_t TILE_SMEM = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (TILE_THREADS / 32) * TILE_Q * 16;
+constexpr uint32_t TILE_WARP_SMEM = TILE_Q * 12 + 32 * 16 + 16 * 4;
+constexpr size_t TILE_SMEM = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (size_t)TILE_WARPS * TILE_WARP_SMEM;
+static_assert(TILE_SMEM <= 232448, "tile insert: shared memory");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -179,9 +199,8 @@ __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_sr
 }
 
 __global__ void __launch_bounds__(TILE_THREADS, 1)
-tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, const uint64_t* __restrict__ part_keys,
-                   const uint32_t* __restrict__ cursor, uint32_t bucket_cap, RgGeo geo,
-                   int load_existing, uint64_t* status, uint64_t* spill, uint64_t spill_cap) {
+tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint32_t* __restrict__ cursor,
+                   uint32_t bucket_cap, int canonical, int host_dirty) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* scounts = reinterpret_cast<uint32_t*>(smem_raw + RG_TILE_KEY_BYTES);
@@ -190,21 +209,18 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
   const uint32_t tile = blockIdx.x;
   uint32_t n = cursor[tile];
   if (n > bucket_cap) n = bucket_cap;
-  uint64_t* gkeys = keys + ((uint64_t)tile << RG_TILE_BITS);
-  uint32_t* gcounts = counts + ((uint64_t)tile << RG_TILE_BITS);
+  uint64_t* gkeys = tv.keys + ((uint64_t)tile << RG_TILE_BITS);
+  uint32_t* gcounts = tv.counts + ((uint64_t)tile << RG_TILE_BITS);
+  // the tile in HBM holds data when an earlier push filled it, or when global-memory inserts ran since the
+  // table was last empty (records that found their slab full, direct pushes): load it, else start empty
+  const bool load_existing = host_dirty || tv.status[RG_ST_DIRECT] != 0;
   if (n == 0 && load_existing) return;   // nothing to apply, tile in HBM is already right
 
-  // the first block of every warp is loaded while the tile is being initialised
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr uint32_t NWARPS = TILE_THREADS / 32, BLOCK_KEYS = 32 * TILE_AHEAD;
-  const uint64_t* bucket = part_keys + (uint64_t)tile * bucket_cap;
-  auto load = [&](uint32_t blk, int u) -> uint64_t {       // key of this lane in step u of block blk
-    const uint32_t pos = blk * BLOCK_KEYS + u * 32 + lane;
-    return pos < n ? __ldg(bucket + pos) : RG_EMPTY;
-  };
-  uint64_t kreg[TILE_AHEAD];
-#pragma unroll
-  for (int u = 0; u < TILE_AHEAD; ++u) kreg[u] = load(warp, u);
+  const uint4* bucket = part_recs + (uint64_t)tile * bucket_cap;
+  const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+  // the first batch of every warp is loaded while the tile is being initialised
+  uint4 rec_next = warp * 32 + lane < n ? __ldg(bucket + warp * 32 + lane) : none;
 
   if (load_existing) {
     if (threadIdx.x == 0) {
@@ -232,17 +248,23 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
     __syncthreads();
   }
 
-  // Stream the bucket in blocks of 32 * TILE_AHEAD keys, dealt round-robin to the warps (the first
-  // block of a warp is loaded during the tile initialisation). A step = 32 consecutive keys, one
-  // coalesced 256-byte load issued one block ahead. Every step makes ONE probe per lane; the lanes that hit a slot occupied by another key
-  // push (key, next slot) onto the warp's retry queue (ballot + popc) and the warp moves on, so no
-  // lane ever waits for another lane's probe sequence. Whenever the queue holds 32 entries the
-  // warp spends a step on those instead of the stream (warp-uniform choice), and drains what is
-  // left at the end.
+  // The bucket is streamed in batches of 32 records, dealt round-robin to the warps (one coalesced 512-byte
+  // load, issued one batch ahead). A batch holds T <= 512 k-mers; lane l takes k-mers l, l+32, ... of the
+  // batch, whatever record they belong to (a 512-bit map of the record starts + popc finds the record), so
+  // the lanes stay busy although records hold 1..16 k-mers. Every step makes ONE probe per lane (LDS.64,
+  // CAS if empty, shared atomic on the count); the lanes that met another key push (key, next slot) onto the
+  // warp's retry queue (ballot + popc) and the warp moves on: no lane waits for another lane's probe
+  // sequence. Whenever the queue holds 32 entries the warp spends a step on those, and drains what is left
+  // at the end. A key that has probed RG_PROBE_MAX slots goes to the table's overflow region.
   {
-    uint4* q = reinterpret_cast<uint4*>(smem_raw + RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64) + warp * TILE_Q;
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned char* wbase = smem_raw + RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (size_t)warp * TILE_WARP_SMEM;
+    uint64_t* qkey = reinterpret_cast<uint64_t*>(wbase);                       // [TILE_Q]
+    uint4* rq = reinterpret_cast<uint4*>(wbase + TILE_Q * 8);                  // [32]
+    uint32_t* qsp = reinterpret_cast<uint32_t*>(wbase + TILE_Q * 8 + 512);     // [TILE_Q]
+    uint32_t* bm = qsp + TILE_Q;                                               // [16]
+    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
     uint32_t qhead = 0, qlen = 0;     // warp-uniform
+    const uint32_t k = tv.geo.k;
 
     // one probe of `key` at slot (sp & mask) for the lanes with `have`; failures are queued
     auto step = [&](uint64_t key, uint32_t sp, bool have) {
@@ -259,7 +281,9 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
         if (fail) {
           // next slot, one more probe counted in the bits above the slot
           const uint32_t nsp = ((sp + 1u) & (RG_TILE_SLOTS - 1)) | ((sp + RG_TILE_SLOTS) & ~(RG_TILE_SLOTS - 1));
-          q[(qhead + qlen + __popc(fm & lt_mask)) & (TILE_Q - 1)] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), nsp, 0u);
+          const uint32_t at = (qhead + qlen + __popc(fm & lt_mask)) & (TILE_Q - 1);
+          qkey[at] = key;
+          qsp[at] = nsp;
         }
         qlen += __popc(fm);
       }
@@ -268,30 +292,50 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
     auto drain = [&]() {
       __syncwarp();                                         // the queue writes of the previous step are visible
       const uint32_t take = min(32u, qlen);
-      const uint4 e = q[(qhead + lane) & (TILE_Q - 1)];
+      const uint32_t at = (qhead + lane) & (TILE_Q - 1);
+      const uint64_t key = qkey[at];
+      const uint32_t sp = qsp[at];
       __syncwarp();                                         // every lane has its entry before the step overwrites the ring
       bool have = lane < take;
-      const uint64_t key = ((uint64_t)e.y << 32) | e.x;
       qhead = (qhead + take) & (TILE_Q - 1);
       qlen -= take;
-      if (have && (e.z >> RG_TILE_BITS) >= RG_TILE_SLOTS) {  // every slot of the tile probed: tile full
-        const uint64_t spi = atomicAdd((unsigned long long*)&status[0], 1ull);
-        if (spi < spill_cap) spill[spi] = key;
+      if (have && (sp >> RG_TILE_BITS) >= RG_PROBE_MAX) {   // probe window exhausted: the key lives in the overflow region
+        rg_ovf_add(tv, key, 1u);
         have = false;
       }
-      step(key, e.z, have);
+      step(key, sp, have);
     };
-    // blocks are dealt round-robin to the warps. (A shared ticket counter balanced the warps no
-    // better: the compiler emits its warp-aggregated atomic, whose shuffle waits for the shared
-    // atomic's round trip once per block: 0.58 ms against 0.49.)
-    for (uint32_t cur = warp; cur * BLOCK_KEYS < n; cur += NWARPS) {
+
+    for (uint32_t b0 = warp * 32; b0 < n; b0 += TILE_WARPS * 32) {
+      const uint4 rec = rec_next;
+      const uint32_t nb = b0 + TILE_WARPS * 32 + lane;
+      rec_next = nb < n ? __ldg(bucket + nb) : none;
+      const uint32_t len = b0 + lane < n ? (rec.w & 15u) + 1u : 0u;
+      uint32_t incl = len;
 #pragma unroll
-      for (int u = 0; u < TILE_AHEAD; ++u) {
-        const uint64_t key = kreg[u];
-        kreg[u] = load(cur + NWARPS, u);
-        uint32_t tile_unused, slot;
-        rg_locate_in_group(key, geo, tile_unused, slot);
-        step(key, slot, key != RG_EMPTY);                   // (neutralised slots and the bucket's end are skipped)
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const uint32_t start = incl - len;
+      const uint32_t T = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      __syncwarp();                                         // the previous batch's readers are done with rq / bm
+      rq[lane] = rec;
+      if (lane < 16) bm[lane] = 0;
+      __syncwarp();
+      if (len) atomicOr(&bm[start >> 5], 1u << (start & 31));
+      __syncwarp();
+      uint32_t carry = 0;                                   // records that start before this round (warp-uniform)
+      for (uint32_t j0 = 0; j0 < T; j0 += 32) {
+        const uint32_t word = bm[j0 >> 5];
+        const uint32_t j = j0 + lane;
+        const bool have = j < T;
+        const uint32_t r = have ? carry + __popc(word & le_mask) - 1u : 0u;   // the record k-mer j belongs to
+        carry += __popc(word);
+        const uint32_t o = j - __shfl_sync(0xFFFFFFFFu, start, r);
+        const uint4 rr = rq[r];
+        const uint64_t key = sk_key(rr, have ? o : 0u, k, canonical);
+        step(key, rg_slot_of_key(key), have);
         while (qlen >= 32) drain();
       }
     }
@@ -316,17 +360,13 @@ tile_insert_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, c
 int rg_launch_tile_insert(rg_table* t) {
   rg_ctx* ctx = t->ctx;
   const size_t smem = TILE_SMEM;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RG_CUDA_OK(cudaFuncSetAttribute(tile_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // (the attribute is per device: set on every launch, a process may drive several GPUs)
+  RG_CUDA_OK(cudaFuncSetAttribute(tile_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     rg_launch_scope _ls(ctx, "tile_insert_kernel");
-    tile_insert_kernel<<<t->n_tiles, TILE_THREADS, smem, ctx->stream>>>(t->keys, t->counts, t->part_keys, t->part_cursor,
-                                                                        t->bucket_cap, rg_view(t).geo,
-                                                                        t->tiles_dirty ? 1 : 0, t->d_status, t->spill,
-                                                                        t->spill_cap);
+    tile_insert_kernel<<<t->n_tiles, TILE_THREADS, smem, ctx->stream>>>(rg_view(t), t->part_keys, t->part_cursor,
+                                                                        t->bucket_cap, t->canonical,
+                                                                        t->tiles_dirty ? 1 : 0);
   }
   RG_CUDA_OK(cudaGetLastError());
   return 0;
@@ -339,7 +379,7 @@ int rg_launch_tile_insert(rg_table* t) {
 // ---------------------------------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(COUNT_THREADS)
-extract_parts_kernel(ExtractParams ep, uint32_t n_parts, unsigned long long* __restrict__ counters,
+extract_parts_kernel(ExtractParams ep, RgGeo geo, uint32_t groups_per_part, unsigned long long* __restrict__ counters,
                      uint64_t* __restrict__ keys_out) {
   __shared__ CountStage sm;
   __shared__ unsigned int local_cnt[64];
@@ -357,12 +397,13 @@ extract_parts_kernel(ExtractParams ep, uint32_t n_parts, unsigned long long* __r
       mykeys[w] = key;
       myslot[w] = 0xFFFFFFFFu;
       if (key != RG_EMPTY) {
-        const uint32_t part = rg_tile_of_key(key, n_parts);
+        // owner = shard of the key's hash-prefix group (slow per-key minimizer: this exchange moves packed keys)
+        const uint32_t part = rg_group_of_mh(rg_min_hash(key, geo.k, geo.m), geo.groups) / groups_per_part;
         myslot[w] = (part << 16) | atomicAdd(&local_cnt[part], 1u);
       }
     });
     __syncthreads();
-    if (threadIdx.x < n_parts) {
+    if (threadIdx.x < 64) {
       const unsigned int cnt = local_cnt[threadIdx.x];
       local_base[threadIdx.x] = cnt ? atomicAdd(&counters[threadIdx.x], (unsigned long long)cnt) : 0ull;
     }
@@ -388,12 +429,13 @@ __global__ void parts_scan_kernel(uint32_t n_parts, const unsigned long long* co
   }
 }
 
-int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, uint32_t n_parts, uint64_t* keys_out,
+int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, RgGeo geo, uint32_t n_parts, uint64_t* keys_out,
                                 uint64_t* part_offsets, uint64_t* d_tmp) {
-  if (n_parts == 0 || n_parts > 64) {
-    rg_set_error("rg_extract_partition: n_parts must be 1..64");
+  if (n_parts == 0 || n_parts > 64 || geo.groups % n_parts != 0) {
+    rg_set_error("rg_extract_partition: n_parts must be 1..64 and divide the table's groups");
     return RG_ERR_ARG;
   }
+  const uint32_t gpp = geo.groups / n_parts;
   // d_tmp: [0..63] counts, [64..127] cursors
   RG_CUDA_OK(cudaMemsetAsync(d_tmp, 0, 128 * sizeof(uint64_t), ctx->stream));
   const uint64_t n_chunks = (ep.n_bytes + CHUNK - 1) / CHUNK;
@@ -403,7 +445,7 @@ int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, uint32_t n
   unsigned long long* cur = cnt + 64;
   {
     rg_launch_scope _ls(ctx, "extract_parts_kernel<count>");
-    extract_parts_kernel<false><<<grid, COUNT_THREADS, 0, ctx->stream>>>(ep, n_parts, cnt, nullptr);
+    extract_parts_kernel<false><<<grid, COUNT_THREADS, 0, ctx->stream>>>(ep, geo, gpp, cnt, nullptr);
   }
   {
     rg_launch_scope _ls(ctx, "parts_scan_kernel");
@@ -411,7 +453,7 @@ int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, uint32_t n
   }
   {
     rg_launch_scope _ls(ctx, "extract_parts_kernel<scatter>");
-    extract_parts_kernel<true><<<grid, COUNT_THREADS, 0, ctx->stream>>>(ep, n_parts, cur, keys_out);
+    extract_parts_kernel<true><<<grid, COUNT_THREADS, 0, ctx->stream>>>(ep, geo, gpp, cur, keys_out);
   }
   RG_CUDA_OK(cudaGetLastError());
   return 0;

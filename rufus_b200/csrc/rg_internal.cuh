@@ -10,22 +10,34 @@
 #include "rufus_gpu.h"
 
 // ---------------------------------------------------------------------------
-// Table geometry. A table is an array of TILES; a tile is an independent
-// open-addressed (linear probing, wrap inside the tile) hash table of
-// RG_TILE_SLOTS slots, stored SoA: keys[] (u64, EMPTY = ~0) and counts[] (u32).
-// One tile = 128 KiB of keys + 64 KiB of counts = 192 KiB: exactly what one CTA
-// stages in shared memory (227 KiB/SM on B200) in the tiled insert.
-//   h      = hash32(key)                  (lo * C1 + hi * C2 mod 2^32)
-//   p      = h * groups                   (64-bit product; groups = hash-prefix GROUPS over all shards)
+// Table geometry. A table is an array of TILES plus an OVERFLOW region; a tile is an
+// open-addressed (linear probing, wrap inside the tile) hash table of RG_TILE_SLOTS slots,
+// stored SoA: keys[] (u64, EMPTY = ~0) and counts[] (u32). One tile = 128 KiB of keys +
+// 64 KiB of counts = 192 KiB: what one CTA stages in shared memory in the tiled insert.
+//
+// The tile of a k-mer is chosen by its MINIMIZER, so that the consecutive k-mers of a read that
+// share a minimizer (a "super-k-mer") travel to their tile as ONE 16-byte record (rg_sk.cuh):
+//   y_j    = ((f_j + r_j) * RG_MM_C) << (32 - 2m)    j = 0..k-m; f_j / r_j = the m-mer at base j of the
+//                                                    k-mer and its reverse complement (strand-symmetric)
+//   ymin   = min_j y_j ;  mh = mix32(ymin) & ~15     (the hash prefix every level of the partition uses)
+//   p      = mh * groups                  (64-bit product; groups = hash-prefix GROUPS over all shards)
 //   group  = p >> 32                      (the level-1 partition bucket; group / groups_per_shard = owning GPU)
 //   q      = low32(p) * group_tiles       (64-bit product; group_tiles = tiles per group, 1 for small tables)
 //   tile   = group * group_tiles + (q >> 32)
-//   slot0  = low32(q) >> (32 - RG_TILE_BITS)   (the position of h inside its tile's hash range)
+//   slot0  = hash32(key) >> (32 - RG_TILE_BITS)
+// A key is probed over at most RG_PROBE_MAX consecutive slots of its tile; a key that finds that window
+// full lives in the overflow region (slots [n_tiles << RG_TILE_BITS, ... + ovf_slots), one open-addressed
+// table addressed by a second hash of the key, global-memory atomics only). Minimizer-owned tiles are
+// loaded unevenly (one hot minimizer can exceed a tile whatever the tile count); the overflow region
+// takes what does not fit, and the host grows it (or the tile count) between pushes.
 // With group_tiles == 1 a group IS a tile and one partition pass feeds the tile inserts; larger
 // tables (more tiles than the partition kernel can histogram in shared memory) use two passes:
 // stream -> groups, then group -> tiles.
 // ---------------------------------------------------------------------------
 #define RG_TILE_BITS 14
+#define RG_PROBE_MAX 256u          // probe window inside a tile
+#define RG_OVF_PROBE_MAX 128u      // probe window inside the overflow region (beyond it: the spill list)
+#define RG_MM_C 0x9E3779B1u        // m-mer order hash multiplier (odd)
 #define RG_TILE_SLOTS (1u << RG_TILE_BITS)
 #define RG_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define RG_TILE_KEY_BYTES (RG_TILE_SLOTS * 8u)
@@ -76,23 +88,27 @@ struct rg_table {
   uint32_t shard_part = 0, shard_parts = 1;
   uint64_t* keys = nullptr;     // [n_tiles * RG_TILE_SLOTS]
   uint32_t* counts = nullptr;
-  // device-side status words: [0]=spill count, [1]=foreign-key count (wrong shard)
+  int m = 0;                    // minimizer length (<= min(k, 16)); k - m + 1 = window of the partition kernel
+  uint64_t ovf_slots = 0;       // overflow region (power of two, multiple of RG_TILE_SLOTS), after the tiles
+  uint64_t ovf_used = 0;        // keys placed in the overflow region so far (host copy, updated by rg_table_finish)
+  // device-side status words (RG_ST_*)
   uint64_t* d_status = nullptr;
-  uint64_t* spill = nullptr;    // keys that found their tile full
+  uint64_t* spill_keys = nullptr;   // (key, count) pairs that found tiles and overflow region full (RG_ST_LOST)
+  uint32_t* spill_counts = nullptr;
   uint64_t spill_cap = 0;
   bool tiles_dirty = false;     // table holds data (tiled insert must load tiles, not zero them)
   uint32_t p2p_groups = 0;      // > 0: peer-to-peer multi-GPU counting with this many groups per shard
   bool unchecked = false;       // pushes were enqueued whose status words (spill / foreign) are not read back yet
   // tiled-mode staging
-  uint64_t* part_keys = nullptr;     // bucketed keys
-  uint64_t part_cap = 0;             // total key capacity
+  uint4* part_keys = nullptr;        // bucketed super-k-mer records
+  uint64_t part_cap = 0;             // total record capacity
   uint32_t* part_cursor = nullptr;   // [n_tiles] fill of each bucket
   uint32_t bucket_cap = 0;
   // two-level partition (group_tiles > 1) and peer-to-peer multi-GPU counting: slabs of the groups
-  uint64_t* grp_keys = nullptr;      // [n_groups_local][grp_cap]
+  uint4* grp_keys = nullptr;         // [n_groups_local][grp_cap] records
   uint32_t* grp_cursor = nullptr;    // [n_groups_local]
   uint32_t grp_cap = 0;
-  uint64_t grp_alloc_keys = 0;       // keys allocated behind grp_keys
+  uint64_t grp_alloc_keys = 0;       // records allocated behind grp_keys
   // peer-to-peer: one allocation [cursors | status | spill | slabs], exported with CUDA IPC
   void* p2p_block = nullptr;
   uint64_t p2p_block_bytes = 0;
@@ -101,12 +117,12 @@ struct rg_table {
   uint32_t p2p_ctas = 0;             // CTAs of the scatter kernel (0 = one per SM); fewer leave SMs to a concurrent stream
   uint64_t p2p_max_keys = 0;         // keys one shard may receive per push (sizes the slabs)
   uint32_t* p2p_src_cursor = nullptr;  // LOCAL fill of my sub-slab in every group of every shard [groups_global]
-  uint64_t* p2p_status = nullptr;    // [0] = spill count of keys other GPUs could not place in a slab
-  uint64_t* p2p_spill = nullptr;
-  uint64_t* peer_keys[8] = {};
+  uint64_t* p2p_status = nullptr;    // [0] = number of records other GPUs could not place in a slab (spilled)
+  uint4* p2p_spill = nullptr;
+  uint4* peer_keys[8] = {};
   uint32_t* peer_cursor[8] = {};
   uint64_t* peer_status[8] = {};
-  uint64_t* peer_spill[8] = {};
+  uint4* peer_spill[8] = {};
   void* peer_mapped[8] = {};         // bases returned by cudaIpcOpenMemHandle (to close them)
   uint64_t* stage = nullptr;         // host->device staging for rg_count_push
   uint64_t stage_bytes = 0;
@@ -149,57 +165,88 @@ void rg_set_error(const std::string& msg);
 // ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------
-// table hash: two 32-bit multiply-adds (both on the FMA pipe, nothing on the integer ALU pipe that the
-// extraction saturates). Checked against the previous xor-shift-multiply hash on real k-mer sets: same
-// tile-load variance (Poisson) and the same mean probe length (profiles/README.md).
+// status words of a table (device, uint64 each)
+#define RG_ST_FOREIGN 1   // keys / records that do not belong to this table's shard
+#define RG_ST_LOST 2      // (key, count) pairs that found the overflow region full: appended to the spill list, re-inserted
+                          // by the host after it has grown the table (beyond the list's capacity they are lost: error)
+#define RG_ST_OVF_NEW 3   // keys newly placed in the overflow region
+#define RG_ST_DIRECT 4    // != 0: global-memory inserts happened since the table was last empty (the tiled insert must load tiles)
+#define RG_ST_WORDS 8
+
+// slot hash inside a tile: two 32-bit multiply-adds (FMA pipe)
 __host__ __device__ __forceinline__ uint32_t rg_hash32(uint64_t key) {
   return (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
+}
+// second, independent hash: slot in the overflow region
+__host__ __device__ __forceinline__ uint32_t rg_hash32b(uint64_t key) {
+  uint32_t h = (uint32_t)key * 0xC2B2AE35u + (uint32_t)(key >> 32) * 0x27D4EB2Fu;
+  h ^= h >> 15;
+  return h * 0x2C1B3C6Du;
 }
 
 // table geometry as the kernels see it
 struct RgGeo {
   uint32_t groups;        // hash-prefix groups over ALL shards (= n_tiles_global / group_tiles)
   uint32_t group_tiles;   // tiles per group
+  uint32_t k, m;          // k-mer and minimizer length
 };
-
-// level-1 bucket (hash-prefix group, global numbering) of a key
-__host__ __device__ __forceinline__ uint32_t rg_group_of_key(uint64_t key, uint32_t groups) {
-  return (uint32_t)(((uint64_t)rg_hash32(key) * groups) >> 32);
-}
-// kept for the callers that partition by shard only (n = number of shards)
-__host__ __device__ __forceinline__ uint32_t rg_tile_of_key(uint64_t key, uint32_t n) { return rg_group_of_key(key, n); }
-
-// tile (global numbering) and home slot of a key
-__host__ __device__ __forceinline__ void rg_locate(uint64_t key, RgGeo geo, uint32_t& tile, uint32_t& slot) {
-  const uint64_t p = (uint64_t)rg_hash32(key) * geo.groups;
-  const uint64_t q = (uint64_t)(uint32_t)p * geo.group_tiles;
-  tile = (uint32_t)(p >> 32) * geo.group_tiles + (uint32_t)(q >> 32);
-  slot = (uint32_t)q >> (32 - RG_TILE_BITS);
-}
-// tile inside its group and home slot (level-2 partition, tile insert)
-__host__ __device__ __forceinline__ void rg_locate_in_group(uint64_t key, RgGeo geo, uint32_t& tile_in_group,
-                                                            uint32_t& slot) {
-  const uint32_t r = rg_hash32(key) * geo.groups;            // low word of h * groups
-  const uint64_t q = (uint64_t)r * geo.group_tiles;
-  tile_in_group = (uint32_t)(q >> 32);
-  slot = (uint32_t)q >> (32 - RG_TILE_BITS);
-}
 
 // reverse complement of a jf key (first base in the MSBs of 2k bits)
 __host__ __device__ __forceinline__ uint64_t rg_revcomp_jf(uint64_t x, int k) {
-  // reverse the order of the 2-bit groups of the 64-bit word, complement, shift down
+#ifdef __CUDA_ARCH__
+  // bit-reverse the 64-bit word (two BREV), swap the bits inside every pair, complement, shift down
+  const uint32_t lo = __brev((uint32_t)(x >> 32)), hi = __brev((uint32_t)x);
+  const uint32_t l2 = ((lo >> 1) & 0x55555555u) | ((lo & 0x55555555u) << 1);
+  const uint32_t h2 = ((hi >> 1) & 0x55555555u) | ((hi & 0x55555555u) << 1);
+  x = ((uint64_t)h2 << 32) | l2;
+#else
   x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
   x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
-#ifdef __CUDA_ARCH__
-  uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-  lo = __byte_perm(lo, 0, 0x0123);
-  hi = __byte_perm(hi, 0, 0x0123);
-  x = ((uint64_t)lo << 32) | hi;
-#else
   x = __builtin_bswap64(x);
 #endif
   return (~x) >> (64 - 2 * k);
 }
+
+// final mix of the minimizer order value -> the hash prefix (low 4 bits are free for the record's length)
+__host__ __device__ __forceinline__ uint32_t rg_mix_min(uint32_t ymin) {
+  uint32_t h = ymin * 0x9E3779B1u;
+  h = (h ^ (h >> 15)) * 0x85EBCA77u;
+  h ^= h >> 13;
+  return h & ~15u;
+}
+
+// hash prefix of a k-mer from its packed key (slow path: k-m+1 m-mers; the partition kernel gets the same
+// value incrementally from the read). Strand-symmetric: key and its reverse complement give the same value.
+__host__ __device__ __forceinline__ uint32_t rg_min_hash(uint64_t key, uint32_t k, uint32_t m) {
+  const uint64_t rc = rg_revcomp_jf(key, (int)k);
+  const uint32_t sh = 32u - 2u * m;
+  const uint32_t cm = RG_MM_C << sh;              // (x * cm) == ((x mod 4^m) * RG_MM_C) << sh  (mod 2^32)
+  uint32_t ymin = 0xFFFFFFFFu;
+  for (uint32_t j = 0; j + m <= k; ++j) {
+    const uint32_t f = (uint32_t)(key >> (2u * (k - m - j)));   // m-mer at base j (garbage above 2m bits: multiplied away)
+    const uint32_t r = (uint32_t)(rc >> (2u * j));              // its reverse complement
+    const uint32_t y = (f + r) * cm;
+    ymin = y < ymin ? y : ymin;
+  }
+  return rg_mix_min(ymin);
+}
+
+// level-1 bucket (hash-prefix group, global numbering) of a hash prefix
+__host__ __device__ __forceinline__ uint32_t rg_group_of_mh(uint32_t mh, uint32_t groups) {
+  return (uint32_t)(((uint64_t)mh * groups) >> 32);
+}
+// tile (global numbering) of a hash prefix
+__host__ __device__ __forceinline__ uint32_t rg_tile_of_mh(uint32_t mh, RgGeo geo) {
+  const uint64_t p = (uint64_t)mh * geo.groups;
+  const uint64_t q = (uint64_t)(uint32_t)p * geo.group_tiles;
+  return (uint32_t)(p >> 32) * geo.group_tiles + (uint32_t)(q >> 32);
+}
+// tile inside its group (level-2 partition)
+__host__ __device__ __forceinline__ uint32_t rg_tile_in_group_of_mh(uint32_t mh, RgGeo geo) {
+  const uint32_t r = mh * geo.groups;             // low word of mh * groups
+  return (uint32_t)(((uint64_t)r * geo.group_tiles) >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t rg_slot_of_key(uint64_t key) { return rg_hash32(key) >> (32 - RG_TILE_BITS); }
 
 struct TableView {
   uint64_t* keys;
@@ -207,6 +254,12 @@ struct TableView {
   uint32_t n_tiles;
   uint32_t tile_first;
   RgGeo geo;
+  uint64_t ovf_base;      // first slot of the overflow region (= n_tiles << RG_TILE_BITS)
+  uint64_t ovf_mask;      // ovf_slots - 1
+  uint64_t* status;       // RG_ST_* words of the table
+  uint64_t* spill_keys;   // last resort: what found the overflow region full
+  uint32_t* spill_counts;
+  uint64_t spill_cap;
 };
 
 static inline TableView rg_view(const rg_table* t) {
@@ -217,17 +270,49 @@ static inline TableView rg_view(const rg_table* t) {
   v.tile_first = t->tile_first;
   v.geo.groups = t->n_tiles_global / t->group_tiles;
   v.geo.group_tiles = t->group_tiles;
+  v.geo.k = (uint32_t)t->k;
+  v.geo.m = (uint32_t)t->m;
+  v.ovf_base = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  v.ovf_mask = t->ovf_slots - 1;
+  v.status = t->d_status;
+  v.spill_keys = t->spill_keys;
+  v.spill_counts = t->spill_counts;
+  v.spill_cap = t->spill_cap;
   return v;
 }
+static inline uint64_t rg_table_slots(const rg_table* t) { return ((uint64_t)t->n_tiles << RG_TILE_BITS) + t->ovf_slots; }
 
-// add `add` to key's counter in a global-memory table. Returns 0 ok, 1 tile full, 2 foreign shard.
-__device__ __forceinline__ int rg_table_add(const TableView& tv, uint64_t key, uint32_t add) {
-  uint32_t tile, slot;
-  rg_locate(key, tv.geo, tile, slot);
-  tile -= tv.tile_first;
-  if (tile >= tv.n_tiles) return 2;
+#ifdef __CUDACC__
+// add `add` to key's counter in the overflow region. Returns 0 ok, 1 probe window full (the pair goes to the spill list).
+__device__ __forceinline__ int rg_ovf_add(const TableView& tv, uint64_t key, uint32_t add) {
+  uint64_t slot = rg_hash32b(key) & tv.ovf_mask;
+  for (uint32_t probe = 0; probe < RG_OVF_PROBE_MAX; ++probe) {
+    unsigned long long* kp = (unsigned long long*)(tv.keys + tv.ovf_base + slot);
+    unsigned long long cur = *(volatile unsigned long long*)kp;
+    if (cur == RG_EMPTY) {
+      cur = atomicCAS(kp, (unsigned long long)RG_EMPTY, (unsigned long long)key);
+      if (cur == RG_EMPTY) atomicAdd((unsigned long long*)&tv.status[RG_ST_OVF_NEW], 1ull);
+    }
+    if (cur == RG_EMPTY || cur == key) {
+      atomicAdd(tv.counts + tv.ovf_base + slot, add);
+      return 0;
+    }
+    slot = (slot + 1) & tv.ovf_mask;
+  }
+  const unsigned long long at = atomicAdd((unsigned long long*)&tv.status[RG_ST_LOST], 1ull);
+  if (at < tv.spill_cap) {
+    tv.spill_keys[at] = key;
+    tv.spill_counts[at] = add;
+  }
+  return 1;
+}
+
+// add `add` to key's counter in a global-memory table, tile already known (local numbering).
+// Returns 0 ok, 1 lost (overflow region full).
+__device__ __forceinline__ int rg_table_add_at(const TableView& tv, uint32_t tile, uint64_t key, uint32_t add) {
   const uint64_t base = (uint64_t)tile << RG_TILE_BITS;
-  for (uint32_t probe = 0; probe < RG_TILE_SLOTS; ++probe) {
+  uint32_t slot = rg_slot_of_key(key);
+  for (uint32_t probe = 0; probe < RG_PROBE_MAX; ++probe) {
     unsigned long long* kp = (unsigned long long*)(tv.keys + base + slot);
     unsigned long long cur = *(volatile unsigned long long*)kp;
     if (cur == RG_EMPTY) cur = atomicCAS(kp, (unsigned long long)RG_EMPTY, (unsigned long long)key);
@@ -237,24 +322,44 @@ __device__ __forceinline__ int rg_table_add(const TableView& tv, uint64_t key, u
     }
     slot = (slot + 1) & (RG_TILE_SLOTS - 1);
   }
-  return 1;
+  return rg_ovf_add(tv, key, add);
 }
 
-// count of key (0 if absent)
-__device__ __forceinline__ uint32_t rg_table_get(const TableView& tv, uint64_t key) {
-  uint32_t tile, slot;
-  rg_locate(key, tv.geo, tile, slot);
-  tile -= tv.tile_first;
-  if (tile >= tv.n_tiles) return 0;
+// same, tile from the key's minimizer. Returns 0 ok, 1 lost, 2 foreign shard.
+__device__ __forceinline__ int rg_table_add(const TableView& tv, uint64_t key, uint32_t add) {
+  const uint32_t tile = rg_tile_of_mh(rg_min_hash(key, tv.geo.k, tv.geo.m), tv.geo) - tv.tile_first;
+  if (tile >= tv.n_tiles) {
+    atomicAdd((unsigned long long*)&tv.status[RG_ST_FOREIGN], 1ull);
+    return 2;
+  }
+  return rg_table_add_at(tv, tile, key, add);
+}
+
+// count of key (0 if absent), tile known (local numbering)
+__device__ __forceinline__ uint32_t rg_table_get_at(const TableView& tv, uint32_t tile, uint64_t key) {
   const uint64_t base = (uint64_t)tile << RG_TILE_BITS;
-  for (uint32_t probe = 0; probe < RG_TILE_SLOTS; ++probe) {
+  uint32_t slot = rg_slot_of_key(key);
+  for (uint32_t probe = 0; probe < RG_PROBE_MAX; ++probe) {
     const uint64_t cur = __ldg(tv.keys + base + slot);
     if (cur == key) return __ldg(tv.counts + base + slot);
     if (cur == RG_EMPTY) return 0;
     slot = (slot + 1) & (RG_TILE_SLOTS - 1);
   }
+  uint64_t os = rg_hash32b(key) & tv.ovf_mask;
+  for (uint32_t probe = 0; probe < RG_OVF_PROBE_MAX; ++probe) {
+    const uint64_t cur = __ldg(tv.keys + tv.ovf_base + os);
+    if (cur == key) return __ldg(tv.counts + tv.ovf_base + os);
+    if (cur == RG_EMPTY) return 0;
+    os = (os + 1) & tv.ovf_mask;
+  }
   return 0;
 }
+__device__ __forceinline__ uint32_t rg_table_get(const TableView& tv, uint64_t key) {
+  const uint32_t tile = rg_tile_of_mh(rg_min_hash(key, tv.geo.k, tv.geo.m), tv.geo) - tv.tile_first;
+  if (tile >= tv.n_tiles) return 0;
+  return rg_table_get_at(tv, tile, key);
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // host-side launchers implemented in the .cu files
@@ -269,20 +374,20 @@ struct ExtractParams {
   uint32_t skip = 0;       // windows starting before this position are not emitted (the halo of a split push)
 };
 
-// read back the status words of the enqueued pushes and resolve spills (every reader calls it first)
+// read back the status words of the enqueued pushes, grow the table when its overflow region fills (every reader calls it first)
 int rg_table_finish(rg_table* t);
 
 int rg_launch_count_direct(rg_table* t, const ExtractParams& ep);
-int rg_launch_partition(rg_table* t, const ExtractParams& ep);   // into t->part_keys buckets
-int rg_launch_partition_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n);
+int rg_launch_partition(rg_table* t, const ExtractParams& ep);   // into t->part_keys buckets (or the group slabs)
 int rg_launch_partition_groups(rg_table* t);                      // level 2: group slabs -> tile buckets
 int rg_launch_partition_multi(rg_table* t, const ExtractParams& ep);   // level 1 into every GPU's group slabs
 uint32_t rg_partition_max_buckets();
-int rg_launch_tile_insert(rg_table* t);
-uint64_t rg_partition_pad_keys(uint32_t n_tiles, uint64_t n_units);                           // consume buckets
+double rg_partition_record_density(int k, int m);
+int rg_launch_tile_insert(rg_table* t);                           // consume buckets
 int rg_launch_insert_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n, const uint32_t* dev_counts);
+int rg_launch_insert_records(rg_table* t, const uint4* dev_recs, uint64_t n);
 int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads, uint32_t* brk);
-int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, uint32_t n_parts, uint64_t* keys_out,
+int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, RgGeo geo, uint32_t n_parts, uint64_t* keys_out,
                                 uint64_t* part_offsets, uint64_t* d_tmp_counts);
 
 int rg_launch_histo(rg_table* t, uint64_t min_count, uint64_t base, uint64_t nb, uint64_t* d_out);
@@ -293,6 +398,7 @@ int rg_launch_query(rg_table* t, const uint64_t* d_keys, uint64_t n, uint64_t mi
 struct OtherTables {
   TableView tv[16];
   uint32_t min_count[16];
+  uint32_t same_geo;     // bit o: table o has the subject's tile geometry (a key sits in the same tile in both)
   int n;
 };
 int rg_launch_subtract(rg_table* subj, uint64_t lo, uint64_t hi, const OtherTables& others, uint64_t* d_keys,

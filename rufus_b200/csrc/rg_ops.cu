@@ -41,7 +41,7 @@ histo_kernel(const uint32_t* __restrict__ counts, uint64_t n_slots, uint32_t min
 
 int rg_launch_histo(rg_table* t, uint64_t min_count, uint64_t base, uint64_t nb, uint64_t* d_out) {
   rg_ctx* ctx = t->ctx;
-  const uint64_t n_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  const uint64_t n_slots = rg_table_slots(t);
   RG_CUDA_OK(cudaMemsetAsync(d_out, 0, nb * sizeof(uint64_t), ctx->stream));
   {
     rg_launch_scope _ls(ctx, "histo_kernel");
@@ -74,7 +74,7 @@ stats_kernel(const uint32_t* __restrict__ counts, uint64_t n_slots, unsigned lon
 
 int rg_launch_stats(rg_table* t, uint64_t* d_out2) {
   rg_ctx* ctx = t->ctx;
-  const uint64_t n_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  const uint64_t n_slots = rg_table_slots(t);
   RG_CUDA_OK(cudaMemsetAsync(d_out2, 0, 2 * sizeof(uint64_t), ctx->stream));
   {
     rg_launch_scope _ls(ctx, "stats_kernel");
@@ -124,7 +124,7 @@ dump_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ coun
 int rg_launch_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* d_keys, uint32_t* d_counts,
                    uint64_t cap, uint64_t* d_cursor) {
   rg_ctx* ctx = t->ctx;
-  const uint64_t n_slots = (uint64_t)t->n_tiles << RG_TILE_BITS;
+  const uint64_t n_slots = rg_table_slots(t);
   RG_CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), ctx->stream));
   {
     rg_launch_scope _ls(ctx, "dump_kernel");
@@ -164,10 +164,19 @@ int rg_launch_query(rg_table* t, const uint64_t* d_keys, uint64_t n, uint64_t mi
 // survives if every other table holds the key with count < that table's -L
 // (i.e. the key would be absent from its .Jhash). Survivors are compacted.
 // ---------------------------------------------------------------------------
+// count of `key` (found in slot i of the subject) in another table. A table with the subject's geometry
+// holds the key in the same tile (no minimizer to recompute) unless the subject keeps it in its overflow region.
+__device__ __forceinline__ uint32_t other_count(const OtherTables& others, int o, uint64_t key, uint64_t i,
+                                                uint64_t subj_main_slots) {
+  const TableView& tv = others.tv[o];
+  if (((others.same_geo >> o) & 1u) && i < subj_main_slots) return rg_table_get_at(tv, (uint32_t)(i >> RG_TILE_BITS), key);
+  return rg_table_get(tv, key);
+}
+
 __global__ void __launch_bounds__(256)
-subtract_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n_slots, uint64_t lo,
-                uint64_t hi, OtherTables others, uint64_t* out_keys, uint32_t* out_counts, uint64_t cap,
-                unsigned long long* cursor) {
+subtract_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n_slots,
+                uint64_t main_slots, uint64_t lo, uint64_t hi, OtherTables others, uint64_t* out_keys,
+                uint32_t* out_counts, uint64_t cap, unsigned long long* cursor) {
   const uint64_t n_round = (n_slots + 31) & ~31ull;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round;
        i += (uint64_t)gridDim.x * blockDim.x) {
@@ -178,7 +187,7 @@ subtract_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
     if (sel) {
       key = __ldg(keys + i);
       for (int o = 0; o < others.n && sel; ++o) {
-        const uint32_t oc = rg_table_get(others.tv[o], key);
+        const uint32_t oc = other_count(others, o, key, i, main_slots);
         if (oc != 0 && oc >= others.min_count[o]) sel = false;
       }
     }
@@ -193,7 +202,7 @@ subtract_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 build_select_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n_slots,
-                    uint64_t lo, uint64_t hi, OtherTables others, uint64_t max_ctl_sum, uint64_t* out_keys,
+                    uint64_t main_slots, uint64_t lo, uint64_t hi, OtherTables others, uint64_t max_ctl_sum, uint64_t* out_keys,
                     uint32_t* out_counts, uint32_t* out_sums, uint64_t cap, unsigned long long* cursor) {
   const uint64_t n_round = (n_slots + 31) & ~31ull;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round;
@@ -204,7 +213,7 @@ build_select_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
     bool sel = c != 0 && c >= lo && c <= hi;
     if (sel) {
       key = __ldg(keys + i);
-      for (int o = 0; o < others.n; ++o) sum += rg_table_get(others.tv[o], key);
+      for (int o = 0; o < others.n; ++o) sum += other_count(others, o, key, i, main_slots);
       sel = sum <= max_ctl_sum;
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, sel);
@@ -227,11 +236,12 @@ build_select_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restric
 int rg_launch_build_select(rg_table* subj, uint64_t lo, uint64_t hi, const OtherTables& others, uint64_t max_ctl_sum,
                            uint64_t* d_keys, uint32_t* d_counts, uint32_t* d_sums, uint64_t cap, uint64_t* d_cursor) {
   rg_ctx* ctx = subj->ctx;
-  const uint64_t n_slots = (uint64_t)subj->n_tiles << RG_TILE_BITS;
+  const uint64_t n_slots = rg_table_slots(subj);
   RG_CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), ctx->stream));
   {
     rg_launch_scope _ls(ctx, "build_select_kernel");
-    build_select_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(subj->keys, subj->counts, n_slots, lo, hi, others,
+    build_select_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(subj->keys, subj->counts, n_slots,
+                                                                  (uint64_t)subj->n_tiles << RG_TILE_BITS, lo, hi, others,
                                                                   max_ctl_sum, d_keys, d_counts, d_sums, cap,
                                                                   reinterpret_cast<unsigned long long*>(d_cursor));
   }
@@ -242,11 +252,12 @@ int rg_launch_build_select(rg_table* subj, uint64_t lo, uint64_t hi, const Other
 int rg_launch_subtract(rg_table* subj, uint64_t lo, uint64_t hi, const OtherTables& others, uint64_t* d_keys,
                        uint32_t* d_counts, uint64_t cap, uint64_t* d_cursor) {
   rg_ctx* ctx = subj->ctx;
-  const uint64_t n_slots = (uint64_t)subj->n_tiles << RG_TILE_BITS;
+  const uint64_t n_slots = rg_table_slots(subj);
   RG_CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), ctx->stream));
   {
     rg_launch_scope _ls(ctx, "subtract_kernel");
-    subtract_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(subj->keys, subj->counts, n_slots, lo, hi, others, d_keys,
+    subtract_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(subj->keys, subj->counts, n_slots,
+                                                              (uint64_t)subj->n_tiles << RG_TILE_BITS, lo, hi, others, d_keys,
                                                               d_counts, cap,
                                                               reinterpret_cast<unsigned long long*>(d_cursor));
   }

@@ -140,7 +140,7 @@ class DevicePipeline:
         """world > 1: extract + bucket sample i by owner rank, start its all-to-all (asynchronous)."""
         L = api.lib()
         s = self.streams[i]
-        rc = L.rg_extract_partition_dev(self.ctx.h, self.k, 1, api._ptr(s), s.numel(), self.read_len, self.world,
+        rc = L.rg_extract_partition_dev(self.tables[i].h, api._ptr(s), s.numel(), self.read_len,
                                         api._ptr(self.part_keys[i]), api._ptr(self.part_offs))
         api._check(rc, "rg_extract_partition_dev")
         sizes = split_sizes_from_offsets(self.part_offs.tolist())

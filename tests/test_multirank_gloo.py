@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the multi-GPU host logic (no GPU needed): hash-prefix
-ownership (rg_key_partition, the same function the kernels use), the ragged
+ownership (rg_key_shard, the same function the kernels use), the ragged
 all-to-all of packed k-mers (pipeline.exchange_keys) and the gather of the
 per-shard HashList pieces (pipeline.gather_varlen). K-mers are extracted on the CPU
 by the oracle (allowed in tests/), bucketed per owner like rg_extract_partition_dev
@@ -51,13 +51,14 @@ def _worker(rank, world, port, tmp):
     trio, _ = synth.make_trio(3, 20000, 400, slice_id=rank)
     s1, _, s2, _ = trio["Child"]
     mine = _kmers_cpu(np.concatenate([s1, s2]), k)
-    owner = np.array([L.rg_key_partition(int(x), world) for x in mine.tolist()], dtype=np.int64)
+    m, groups = L.rg_minimizer_len(k, 64), 64
+    owner = np.array([L.rg_key_shard(int(x), k, m, groups, world) for x in mine.tolist()], dtype=np.int64)
     order = np.argsort(owner, kind="stable")
     keys = torch.from_numpy(mine[order].view(np.int64))
     offs = np.searchsorted(owner[order], np.arange(world + 1))
     sizes = pipeline.split_sizes_from_offsets(offs)
     got = pipeline.exchange_keys(keys, sizes).numpy().view(np.uint64)
-    assert all(L.rg_key_partition(int(x), world) == rank for x in got[:2000].tolist())
+    assert all(L.rg_key_shard(int(x), k, m, groups, world) == rank for x in got[:2000].tolist())
     uk, uc = np.unique(got, return_counts=True)
     np.save(os.path.join(tmp, f"k{rank}.npy"), uk)
     np.save(os.path.join(tmp, f"c{rank}.npy"), uc)
