@@ -8,10 +8,15 @@
 One step = one pass of the hot path over one batch: count the three samples
 (1 M reads x 150 bp each, per GPU) -> subject histogram -> subtract -> pull the
 subject's read pairs. `value` = bases of all samples counted / device time with
-inputs resident in HBM; `e2e` = the same pass through the host-buffer C ABI
+inputs resident in HBM; `e2e` = the same pass with inputs in pinned host memory
 (H2D of the reads and D2H of the results inside the timed region).
-N > 1 (torchrun): weak scaling, every rank brings its own 1 M reads/sample; k-mers
-are routed to their hash-prefix shard with one NCCL all-to-all per sample.
+N > 1 (torchrun): weak scaling on a workload that stays a 30x trio: the genome is
+5 Mb x N and every rank brings its own 1 M reads/sample; super-k-mer records are
+routed to the GPU that owns their minimizer's hash prefix (peer-to-peer stores over
+NVLink, or --exchange nccl: one all-to-all of packed keys per sample).
+After the timed loop the run's RESULT (histogram, HashList, pulled read names) is
+checked against digests of the reference's own output on the same workload
+(tests/golden/bench_digests.json); a mismatch makes the exit code 3.
 """
 import argparse
 import json
@@ -29,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "Gbases/sec through k-mer count+filter (k=25, 30x trio)"
-K, READ_LEN, MIN_COV, MINQ, THRESH = 25, 150, 5, 15, 1
+K, READ_LEN, MIN_COV, MAX_COV, MINQ, THRESH = 25, 150, 5, 150, 15, 1
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -105,11 +110,12 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- data
-def make_data(n_pairs, genome_len, seed, slice_id):
-    from rufus_b200 import synth
+def make_data(args, rank, world):
+    """this rank's reads of the benchmark workload (rufus_b200/workload.py: genome = unit x world, slice = rank)"""
+    from rufus_b200 import workload
     t0 = time.time()
-    trio, _ = synth.make_trio(seed, genome_len, n_pairs, slice_id=slice_id)
-    log(f"synthetic trio: {n_pairs} pairs/sample, genome {genome_len}, {time.time() - t0:.1f}s")
+    trio = workload.make_slice(args.seed, args.genome, args.pairs, rank, world)
+    log(f"synthetic trio: {args.pairs} pairs/sample/rank, genome {args.genome * world}, slice {rank}/{world}, {time.time() - t0:.1f}s")
     return trio
 
 
@@ -141,7 +147,7 @@ def cpu_reference_pass(trio, n_pairs, workdir, threads):
         # runRufus.sh:925-926 + CheckJellyHashList.sh:12
         subprocess.run(f"{jf} merge Child.Jhash Mother.Jhash Father.Jhash > merge.out && "
                        f"{jf} query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) Child.Jhash | "
-                       f"awk -v var={MIN_COV} ' $2 >= var ' | awk -v var=150 ' $2 <= var ' > HashList",
+                       f"awk -v var={MIN_COV} ' $2 >= var ' | awk -v var={MAX_COV} ' $2 <= var ' > HashList",
                        shell=True, check=True, cwd=workdir, executable="/bin/bash")
         # runRufus.sh:981
         subprocess.run(f"{refbin}/RUFUS.Filter HashList {fq['Child'][0]} {fq['Child'][1]} out {K} {MINQ} {THRESH} {T} "
@@ -164,7 +170,7 @@ def cpu_reference_pass(trio, n_pairs, workdir, threads):
         tabs.append(oracle.count(both.reshape(-1), offs, K, True, 2))
         oracle.histo(tabs[-1][1])
         bases += both.size
-    hk, hc = oracle.hashlist(tabs[0], tabs[1:], MIN_COV, 150)
+    hk, hc = oracle.hashlist(tabs[0], tabs[1:], MIN_COV, MAX_COV)
     s1, q1, s2, q2 = (a[:n_pairs] for a in trio["Child"])
     offs = np.arange(n_pairs + 1, dtype=np.uint64) * READ_LEN
     keep = oracle.filter_pairs(s1, q1, offs, s2, q2, offs, K, MINQ, THRESH,
@@ -175,8 +181,8 @@ def cpu_reference_pass(trio, n_pairs, workdir, threads):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n_pairs = args.ref_pairs
-    trio = make_data(n_pairs, args.genome, args.seed, None if world == 1 else 0)
+    n_pairs = min(args.ref_pairs, args.pairs)
+    trio = make_data(args, 0, world)
     threads = os.cpu_count() or 1
     times, kind, info, bases = [], None, None, 0
     for i in range(args.warmup + args.steps):
@@ -190,11 +196,12 @@ def run_reference_arm(args, rank, world):
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     val = bases / (ms / 1e3) / 1e9
-    sample = f"first {n_pairs} pairs/sample of the workload ({bases / 1e6:.0f} Mbases), jellyfish -s 256M"
+    sample = (f"first {n_pairs} of the {args.pairs} pairs/sample of rank 0's slice ({bases / 1e6:.0f} Mbases per pass), "
+              f"jellyfish -s 256M -t {info['cores']}, per-base normalised")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gbases/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": workload_config(args, world),
+           "config": dict(workload_config(args, world), reference_sample=sample),
            "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": info["cores"], "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -202,12 +209,14 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(args, world):
-    return {"workload": f"synthetic trio, {2 * args.pairs} x {READ_LEN} bp reads per sample per GPU, k={K}, "
-                        f"genome {args.genome} bp (30x per GPU slice), count 3 samples -> histo -> subtract "
-                        f"(min {MIN_COV}, max {150 * world}) -> pull subject pairs (MinQ {MINQ})",
+    return {"workload": f"synthetic 30x trio (synth-trio v1, seed {args.seed}): genome {args.genome} bp x {world}, "
+                        f"{2 * args.pairs} x {READ_LEN} bp reads per sample per GPU, k={K}, count 3 samples -> histo -> "
+                        f"subtract (min {MIN_COV}, max {MAX_COV}) -> pull subject pairs (MinQ {MINQ})"
+                        + (" = BASELINE configs[1]" if world == 1 and args.pairs == 500_000 and args.genome == 5_000_000 else ""),
             "reads_per_sample_per_gpu": 2 * args.pairs, "read_len": READ_LEN, "k": K, "samples": 3,
-            "partition": f"hash-prefix x{world}" if world > 1 else "single GPU",
-            "l2": "inputs (450 MB reads + GB-scale tables) larger than L2; no flush needed"}
+            "genome_bp": args.genome * world, "coverage": round(2.0 * args.pairs * READ_LEN / args.genome, 1),
+            "partition": f"minimizer hash prefix x{world}" if world > 1 else "single GPU",
+            "l2": "inputs (450 MB reads + GB-scale tables per GPU) larger than L2; no flush needed"}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -218,7 +227,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--pairs", type=int, default=500_000, help="read pairs per sample per GPU")
-    ap.add_argument("--genome", type=int, default=5_000_000)
+    ap.add_argument("--genome", type=int, default=5_000_000, help="genome bases per GPU (the genome is N times that)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs/sample of the CPU baseline sample")
     ap.add_argument("--mode", default="tiled", choices=["tiled", "direct"])
@@ -251,7 +260,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
-    trio = make_data(args.pairs, args.genome, args.seed, None if world == 1 else rank)
+    trio = make_data(args, rank, world)
     ctx = api.Context(local_rank)
     ctx.use_stream(torch.cuda.current_stream().cuda_stream)
     mode = api.MODE_TILED if args.mode == "tiled" else api.MODE_DIRECT
@@ -263,9 +272,10 @@ def main():
         streams.append(torch.from_numpy(np.concatenate([s1, s2]).reshape(-1)).to(dev))
     subj = tuple(torch.from_numpy(a.reshape(-1)).to(dev) for a in trio["Child"])
     bases_per_step = sum(int(s.numel()) for s in streams)
-    # distinct k-mers per shard: genomic (two haplotypes, ~3 % private) / world + ~6.2 error k-mers per read
-    est = int(((1.03 * args.genome) / world + 6.2 * 2 * args.pairs) * args.est_scale)
-    pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, 150 * world, MINQ, THRESH,
+    # distinct k-mers per shard: genomic (two haplotypes, ~3 % private; the genome grows with the GPU count, so a
+    # shard holds one unit's worth) + ~6.2 error k-mers per read
+    est = int((1.03 * args.genome + 6.2 * 2 * args.pairs) * args.est_scale)
+    pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, MAX_COV, MINQ, THRESH,
                                    mode=mode, rank=rank, world=world, exchange=args.exchange,
                                    groups_per_shard=args.p2p_groups, scatter_ctas=args.scatter_ctas)
 
@@ -294,6 +304,12 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.stop()
+    # ---- parity of the benchmarked run (untimed): the job's results against the digests of the REFERENCE's
+    # output on the same workload (tests/golden/bench_digests.json, made by tests/golden/make_bench_golden.py)
+    from rufus_b200 import workload
+    g = pipe.gathered_results()
+    parity = workload.check(world, g["histo"], g["keys"], g["counts"], g["names"], seed=args.seed, pairs=args.pairs,
+                            genome_unit=args.genome, k=K) if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
     prof = ctx.profile_report()
@@ -346,55 +362,77 @@ def main():
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "kernels_ms": kern,
-           "result": {"n_mutant_kmers": r["n_mutant"], "n_pulled_pairs_rank0": r["n_kept"]}}
+           "result": {"n_mutant_kmers": r["n_mutant"], "n_pulled_pairs_rank0": r["n_kept"]}, "parity": parity}
 
-    # ---- e2e: same pass through the host-buffer C ABI (H2D + D2H inside the timed region)
+    # ---- e2e: the same pass with every input starting in pinned HOST memory and every result ending there
+    # (H2D + D2H inside the timed region). N = 1: the host-buffer C ABI (rg_count_push / rg_histo / rg_subtract /
+    # rg_filter_pairs, H2D pipelined against the kernels). N > 1: the sharded pipeline fed from host buffers.
     if not args.no_e2e:
-        pipe.free()
-        del pipe
-        torch.cuda.empty_cache()
-        nl = np.full((2 * args.pairs, 1), 10, np.uint8)
-        host_streams = []
-        for s in synth.SAMPLES:
-            s1, _, s2, _ = trio[s]
-            a = torch.from_numpy(np.concatenate([np.concatenate([s1, s2]), nl], axis=1).reshape(-1)).pin_memory()
-            host_streams.append(a.numpy())
-        pairs_host = tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in trio["Child"])
-        tables = [api.KmerTable(ctx, K, True, est, mode) for _ in host_streams]
-        h2d = sum(a.size for a in host_streams) + sum(a.size for a in pairs_host) + 2 * 8 * (args.pairs + 1)
-        res = None
         e2e_steps = max(3, args.steps // 2)
-        for i in range(2):
-            tm = {}
-            res = pipeline.host_step(ctx, K, host_streams, pairs_host, READ_LEN, est, MIN_COV, 150, MINQ, THRESH,
-                                     mode=mode, tables=tables, timings=tm)
-            log("e2e warm-up pass, host-side phase times (ms):", {k: round(v, 2) for k, v in tm.items()})
-        barrier()
-        e0.record()
-        for i in range(e2e_steps):
-            res = pipeline.host_step(ctx, K, host_streams, pairs_host, READ_LEN, est, MIN_COV, 150, MINQ, THRESH,
-                                     mode=mode, tables=tables)
-        e1.record()
-        barrier()
+        if world == 1:
+            pipe.free()
+            del pipe
+            torch.cuda.empty_cache()
+            nl = np.full((2 * args.pairs, 1), 10, np.uint8)
+            host_streams = []
+            for s in synth.SAMPLES:
+                s1, _, s2, _ = trio[s]
+                a = torch.from_numpy(np.concatenate([np.concatenate([s1, s2]), nl], axis=1).reshape(-1)).pin_memory()
+                host_streams.append(a.numpy())
+            pairs_host = tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in trio["Child"])
+            tables = [api.KmerTable(ctx, K, True, est, mode) for _ in host_streams]
+            h2d = sum(a.size for a in host_streams) + sum(a.size for a in pairs_host) + 2 * 8 * (args.pairs + 1)
+            res = None
+            for i in range(2):
+                tm = {}
+                res = pipeline.host_step(ctx, K, host_streams, pairs_host, READ_LEN, est, MIN_COV, MAX_COV, MINQ, THRESH,
+                                         mode=mode, tables=tables, timings=tm)
+                log("e2e warm-up pass, host-side phase times (ms):", {k: round(v, 2) for k, v in tm.items()})
+            barrier()
+            e0.record()
+            for i in range(e2e_steps):
+                res = pipeline.host_step(ctx, K, host_streams, pairs_host, READ_LEN, est, MIN_COV, MAX_COV, MINQ, THRESH,
+                                         mode=mode, tables=tables)
+            e1.record()
+            barrier()
+            d2h = res["histo"].nbytes + res["hashlist"][0].nbytes + res["hashlist"][1].nbytes + res["keep"].nbytes
+            e2e_ok = workload.check(1, res["histo"], res["hashlist"][0], res["hashlist"][1],
+                                    workload.pulled_names(res["keep"], "Child", 0, 1), seed=args.seed, pairs=args.pairs,
+                                    genome_unit=args.genome, k=K)["ok"]
+            note = "rg_count_push/rg_histo/rg_subtract/rg_filter_pairs on pinned host buffers"
+            for t in tables:
+                t.free()
+        else:
+            host_streams = [s.cpu().pin_memory() for s in streams]
+            pairs_host = tuple(a.cpu().pin_memory() for a in subj)
+            h2d = sum(a.numel() for a in host_streams) + sum(a.numel() for a in pairs_host)
+            for i in range(2):
+                res = pipe.step_from_host(host_streams, pairs_host)
+            barrier()
+            e0.record()
+            for i in range(e2e_steps):
+                res = pipe.step_from_host(host_streams, pairs_host)
+            e1.record()
+            barrier()
+            d2h = res["histo"].nbytes + res["keys"].nbytes + res["counts"].nbytes + res["keep"].nbytes
+            g2 = pipe.gathered_results()
+            e2e_ok = workload.check(world, g2["histo"], g2["keys"], g2["counts"], g2["names"], seed=args.seed,
+                                    pairs=args.pairs, genome_unit=args.genome, k=K)["ok"] if rank == 0 else None
+            note = "sharded pipeline (DevicePipeline.step_from_host): H2D of every rank's reads, peer-to-peer count, D2H of results"
         ms_e2e = e0.elapsed_time(e1) / e2e_steps
         if world > 1:
             t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item())
-        d2h = res["histo"].nbytes + res["hashlist"][0].nbytes + res["hashlist"][1].nbytes + res["keep"].nbytes
         out["e2e"] = {"value": bases_per_step * world / (ms_e2e / 1e3) / 1e9, "unit": "Gbases/s",
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
-                      "steps": e2e_steps,
-                      "note": "rg_count_push/rg_histo/rg_subtract/rg_filter_pairs on pinned host buffers"
-                              + ("; ranks run independent replicas in the e2e leg" if world > 1 else "")}
-        for t in tables:
-            t.free()
+                      "steps": e2e_steps, "parity_ok": e2e_ok, "note": note}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         wd = tempfile.mkdtemp(prefix="rg_cpu_")
         try:
-            dt, b, kind, info = cpu_reference_pass(trio, args.ref_pairs, wd, os.cpu_count() or 1)
+            dt, b, kind, info = cpu_reference_pass(trio, min(args.ref_pairs, args.pairs), wd, os.cpu_count() or 1)
         finally:
             shutil.rmtree(wd, ignore_errors=True)
         out["cpu_baseline"] = {"value": b / dt / 1e9, "unit": "Gbases/s", "cores": info["cores"], "kind": kind,
@@ -406,6 +444,10 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+    # a run whose RESULT differs from the reference's is not a measurement: fail it
+    if rank == 0 and (parity["ok"] is False or out.get("e2e", {}).get("parity_ok") is False):
+        log("PARITY MISMATCH against the reference digests:", parity)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -38,6 +38,9 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("RG_LIB"):           # development: an alternative build of the library (A/B kernel variants)
+        LIB_PATH = os.path.abspath(os.environ["RG_LIB"])
     if not os.path.exists(LIB_PATH):
         raise RufusGpuError(f"{LIB_PATH} is missing: run `make lib` (or __graft_entry__.build()); "
                             "rufus_b200 has no CPU fallback")

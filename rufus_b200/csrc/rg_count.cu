@@ -266,24 +266,41 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
     uint32_t qhead = 0, qlen = 0;     // warp-uniform
     const uint32_t k = tv.geo.k;
 
-    // one probe of `key` at slot (sp & mask) for the lanes with `have`; failures are queued
+    const uint32_t skeys_a = smem_u32(skeys), scounts_a = smem_u32(scounts);
+    // one probe of `key` at slot (sp & mask) for the lanes with `have`; failures are queued. Branch-free up to
+    // the queue push: the CAS (slot seen empty) and the count increment are PREDICATED instructions.
     auto step = [&](uint64_t key, uint32_t sp, bool have) {
       const uint32_t slot = sp & (RG_TILE_SLOTS - 1);
-      unsigned long long seen = 0;                          // lanes without a key never see an empty slot
-      if (have) seen = *(volatile unsigned long long*)(skeys + slot);
-      if (seen == RG_EMPTY)
-        seen = atomicCAS((unsigned long long*)(skeys + slot), (unsigned long long)RG_EMPTY, (unsigned long long)key);
-      const bool hit = (seen == RG_EMPTY) | (seen == key);
-      if (hit && have) atomicAdd(scounts + slot, 1u);
+      const uint32_t ka = skeys_a + slot * 8u;
+      unsigned long long seen;
+      asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(seen) : "r"(ka) : "memory");
+      const uint32_t try_claim = (have && seen == RG_EMPTY) ? 1u : 0u;
+      asm volatile(
+          "{\n"
+          ".reg .pred q;\n"
+          "setp.ne.u32 q, %2, 0;\n"
+          "@q atom.shared.cas.b64 %0, [%1], %3, %4;\n"
+          "}\n"
+          : "+l"(seen)
+          : "r"(ka), "r"(try_claim), "l"((unsigned long long)RG_EMPTY), "l"((unsigned long long)key)
+          : "memory");
+      const bool hit = have && ((seen == RG_EMPTY) | (seen == key));
+      asm volatile(
+          "{\n"
+          ".reg .pred q;\n"
+          "setp.ne.u32 q, %1, 0;\n"
+          "@q red.shared.add.u32 [%0], 1;\n"
+          "}\n" ::"r"(scounts_a + slot * 4u),
+          "r"(hit ? 1u : 0u)
+          : "memory");
       const bool fail = have && !hit;
       const uint32_t fm = __ballot_sync(0xFFFFFFFFu, fail);
       if (fm) {                                             // warp-uniform
         if (fail) {
-          // next slot, one more probe counted in the bits above the slot
-          const uint32_t nsp = ((sp + 1u) & (RG_TILE_SLOTS - 1)) | ((sp + RG_TILE_SLOTS) & ~(RG_TILE_SLOTS - 1));
+          // next slot, one more probe counted in the bits above the slot (a wrap of the slot counts one more: harmless)
           const uint32_t at = (qhead + qlen + __popc(fm & lt_mask)) & (TILE_Q - 1);
           qkey[at] = key;
-          qsp[at] = nsp;
+          qsp[at] = sp + RG_TILE_SLOTS + 1u;
         }
         qlen += __popc(fm);
       }
@@ -325,17 +342,18 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
       __syncwarp();
       if (len) atomicOr(&bm[start >> 5], 1u << (start & 31));
       __syncwarp();
-      uint32_t carry = 0;                                   // records that start before this round (warp-uniform)
+      uint32_t carry = 0xFFFFFFFFu;                         // (records that start before this round) - 1, warp-uniform
       for (uint32_t j0 = 0; j0 < T; j0 += 32) {
         const uint32_t word = bm[j0 >> 5];
         const uint32_t j = j0 + lane;
-        const bool have = j < T;
-        const uint32_t r = have ? carry + __popc(word & le_mask) - 1u : 0u;   // the record k-mer j belongs to
+        // the record k-mer j belongs to = (number of record starts at or before j) - 1; lanes past the batch's
+        // end (last round only) wrap to some valid record and are masked by `have`
+        const uint32_t r = (carry + __popc(word & le_mask)) & 31u;
         carry += __popc(word);
-        const uint32_t o = j - __shfl_sync(0xFFFFFFFFu, start, r);
+        const uint32_t o = (j - __shfl_sync(0xFFFFFFFFu, start, r)) & 15u;
         const uint4 rr = rq[r];
-        const uint64_t key = sk_key(rr, have ? o : 0u, k, canonical);
-        step(key, rg_slot_of_key(key), have);
+        const uint64_t key = sk_key(rr, o, k, canonical);
+        step(key, rg_slot_of_key(key), j < T);
         while (qlen >= 32) drain();
       }
     }

@@ -105,6 +105,26 @@ __device__ __forceinline__ uint64_t and_run(uint64_t x, int n) {
   return x;
 }
 
+// same for a warp-uniform n in 1..64, static shifts behind uniform branches (the partition kernel's validity test)
+__device__ __forceinline__ uint64_t and_run_uniform(uint64_t x, int n) {
+  if (n >= 2) {
+    x &= x >> 1;
+    if (n >= 4) {
+      x &= x >> 2;
+      if (n >= 8) {
+        x &= x >> 4;
+        if (n >= 16) {
+          x &= x >> 8;
+          if (n >= 32) x &= x >> 16;
+        }
+      }
+    }
+  }
+  const int len = 1 << (31 - __clz(n));
+  if (n > len) x &= x >> (n - len);
+  return x;
+}
+
 // reverse the order of the 2-bit groups of a 64-bit word
 __device__ __forceinline__ uint64_t reverse_groups(uint64_t x) {
   x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);

@@ -17,8 +17,10 @@
 //
 // The tile of a k-mer is chosen by its MINIMIZER, so that the consecutive k-mers of a read that
 // share a minimizer (a "super-k-mer") travel to their tile as ONE 16-byte record (rg_sk.cuh):
-//   y_j    = ((f_j + r_j) * RG_MM_C) << (32 - 2m)    j = 0..k-m; f_j / r_j = the m-mer at base j of the
-//                                                    k-mer and its reverse complement (strand-symmetric)
+//   y_j    = (((f_j * C1) ^ (r_j * C1)) + (f_j & r_j) * C2) << (32 - 2m)   j = 0..k-m; f_j / r_j = the m-mer at base j
+//            of the k-mer and its reverse complement: strand-symmetric without a compare. (Not (f + r) * C: f + r only
+//            depends on the differences of mirrored bases, 7^(m/2) classes instead of 4^m / 2; and the xor alone is 0
+//            for every palindromic m-mer, which would all share one tile: the (f & r) term separates them.)
 //   ymin   = min_j y_j ;  mh = mix32(ymin) & ~15     (the hash prefix every level of the partition uses)
 //   p      = mh * groups                  (64-bit product; groups = hash-prefix GROUPS over all shards)
 //   group  = p >> 32                      (the level-1 partition bucket; group / groups_per_shard = owning GPU)
@@ -37,7 +39,8 @@
 #define RG_TILE_BITS 14
 #define RG_PROBE_MAX 256u          // probe window inside a tile
 #define RG_OVF_PROBE_MAX 128u      // probe window inside the overflow region (beyond it: the spill list)
-#define RG_MM_C 0x9E3779B1u        // m-mer order hash multiplier (odd)
+#define RG_MM_C 0x9E3779B1u        // m-mer order hash multipliers (odd)
+#define RG_MM_C2 0x85EBCA77u
 #define RG_TILE_SLOTS (1u << RG_TILE_BITS)
 #define RG_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define RG_TILE_KEY_BYTES (RG_TILE_SLOTS * 8u)
@@ -195,10 +198,12 @@ struct RgGeo {
 __host__ __device__ __forceinline__ uint64_t rg_revcomp_jf(uint64_t x, int k) {
 #ifdef __CUDA_ARCH__
   // bit-reverse the 64-bit word (two BREV), swap the bits inside every pair, complement, shift down
+  // (one LOP3 per word swaps the pair bits AND complements: ~(((r >> 1) & 0x55..) | ((r << 1) & 0xAA..)), LUT 0x1B)
   const uint32_t lo = __brev((uint32_t)(x >> 32)), hi = __brev((uint32_t)x);
-  const uint32_t l2 = ((lo >> 1) & 0x55555555u) | ((lo & 0x55555555u) << 1);
-  const uint32_t h2 = ((hi >> 1) & 0x55555555u) | ((hi & 0x55555555u) << 1);
-  x = ((uint64_t)h2 << 32) | l2;
+  uint32_t l2, h2;
+  asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1B;" : "=r"(l2) : "r"(lo >> 1), "r"(lo << 1));
+  asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1B;" : "=r"(h2) : "r"(hi >> 1), "r"(hi << 1));
+  return (((uint64_t)h2 << 32) | l2) >> (64 - 2 * k);
 #else
   x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
   x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
@@ -220,12 +225,12 @@ __host__ __device__ __forceinline__ uint32_t rg_mix_min(uint32_t ymin) {
 __host__ __device__ __forceinline__ uint32_t rg_min_hash(uint64_t key, uint32_t k, uint32_t m) {
   const uint64_t rc = rg_revcomp_jf(key, (int)k);
   const uint32_t sh = 32u - 2u * m;
-  const uint32_t cm = RG_MM_C << sh;              // (x * cm) == ((x mod 4^m) * RG_MM_C) << sh  (mod 2^32)
+  const uint32_t cm = RG_MM_C << sh, cm2 = RG_MM_C2 << sh;   // (x * cm) == ((x mod 4^m) * RG_MM_C) << sh  (mod 2^32)
   uint32_t ymin = 0xFFFFFFFFu;
   for (uint32_t j = 0; j + m <= k; ++j) {
     const uint32_t f = (uint32_t)(key >> (2u * (k - m - j)));   // m-mer at base j (garbage above 2m bits: multiplied away)
     const uint32_t r = (uint32_t)(rc >> (2u * j));              // its reverse complement
-    const uint32_t y = (f + r) * cm;
+    const uint32_t y = ((f * cm) ^ (r * cm)) + (f & r) * cm2;
     ymin = y < ymin ? y : ymin;
   }
   return rg_mix_min(ymin);

@@ -8,8 +8,8 @@
 // start in the same 16-base block travel as one 16-byte record), so the counting sort, its atomics and
 // the copy-out handle ~5x fewer items and the slabs (and NVLink, multi-GPU) carry ~3 bytes per k-mer:
 //   1. ASCII -> 2-bit streams in shared memory (forward big-endian + complemented little-endian);
-//   2. every thread hashes the 16 m-mers that start in its block: y = (fwd + revcomp) * C, two funnel
-//      shifts, one add, one multiply each (strand-symmetric without a compare); y goes to shared
+//   2. every thread hashes the 16 m-mers that start in its block: y = ((fwd * C1) ^ (rc * C1)) + (fwd & rc) * C2,
+//      two funnel shifts, three multiply-adds, two logic ops each (strand-symmetric without a compare); y goes to shared
 //      memory, transposed (conflict-free);
 //   3. sliding minimum over the W = k-m+1 m-mers of each k-mer (log-step doubling in registers, W is a
 //      template parameter) -> the minimizer value of the thread's 16 k-mers;
@@ -214,8 +214,8 @@ __device__ __forceinline__ void part_stage_store(PartStage& sm, const PartPrefet
 
 // order hash y of the 16 m-mers that start in the 16-base block `t` of the staged super-chunk, stored to
 // column t of the transposed array (row w = position inside the block)
-__device__ __forceinline__ void mmer_hashes(const PartStage& sm, uint32_t t, uint32_t sh, uint32_t cm, uint32_t* Yt,
-                                            uint32_t (&y)[SK_R]) {
+__device__ __forceinline__ void mmer_hashes(const PartStage& sm, uint32_t t, uint32_t sh, uint32_t cm, uint32_t cm2,
+                                            uint32_t* Yt, uint32_t (&y)[SK_R]) {
   const uint32_t W0 = sm.fwd[t], W1 = sm.fwd[t + 1];
   const uint32_t V0 = sm.rcw[t], V1 = sm.rcw[t + 1];
   // (W0:W1) >> sh puts the m-mer of base 0 in the low 2m bits of the high word
@@ -224,7 +224,7 @@ __device__ __forceinline__ void mmer_hashes(const PartStage& sm, uint32_t t, uin
   for (int w = 0; w < SK_R; ++w) {
     const uint32_t f = w ? __funnelshift_l(X1, X0, 2 * w) : X0;      // forward m-mer in the low 2m bits (garbage above)
     const uint32_t r = w ? __funnelshift_r(V0, V1, 2 * w) : V0;      // its reverse complement, same alignment
-    y[w] = (f + r) * cm;                                             // garbage above 2m bits is multiplied away
+    y[w] = ((f * cm) ^ (r * cm)) + (f & r) * cm2;                    // garbage above 2m bits is multiplied away
     Yt[w * SK_YS + t] = y[w];
   }
 }
@@ -300,7 +300,7 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
   if (t == 0) any_overflow = 0;
   for (uint32_t i = t; i < ovf_words; i += SK_THREADS) ovf_bits[i] = 0;
   const uint32_t k = g.geo.k, m = g.geo.m;
-  const uint32_t sh = 32u - 2u * m, cm = RG_MM_C << sh;
+  const uint32_t sh = 32u - 2u * m, cm = RG_MM_C << sh, cm2 = RG_MM_C2 << sh;
 
   // Work items = super-chunks. Level 2: chunks of SK_RMAX records over ALL input slabs, numbered slab after
   // slab (gstart[] = exclusive prefix of the slabs' chunk counts, built here from the slab cursors), so
@@ -332,6 +332,7 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
     // first output slab of this group (peer-to-peer: the input slabs are (group, source GPU) pairs)
     const uint32_t slab0 = SRC == 2 ? (og / g.in_per_group) * g.n_buckets : 0u;
     const uint64_t sc = SRC == 2 ? item - gstart[og] : item;
+#pragma unroll 1
     for (uint32_t i = t; i < g.n_buckets; i += SK_THREADS) hist[i] = 0;
     if (t == 0) rec_total = 0;
     const bool more = item + gridDim.x < total_items;
@@ -349,12 +350,12 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
       uint32_t x[32];
       {
         uint32_t y[SK_R];
-        mmer_hashes(sm, t, sh, cm, Yt, y);
+        mmer_hashes(sm, t, sh, cm, cm2, Yt, y);
 #pragma unroll
         for (int i = 0; i < SK_R; ++i) x[i] = y[i];
         if (t < 2) {                                  // the two blocks of tail after the super-chunk
           uint32_t yt[SK_R];
-          mmer_hashes(sm, SK_THREADS + t, sh, cm, Yt, yt);
+          mmer_hashes(sm, SK_THREADS + t, sh, cm, cm2, Yt, yt);
         }
       }
       // validity of each of the 16 windows: k good bases and no read start strictly inside
@@ -362,8 +363,10 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
         const int p0 = t * SK_R;
         const uint64_t good = ~bits_at(sm.bad, p0);
         const uint64_t nobrk = ~bits_at(sm.brk, p0 + 1);          // bit j: no read starts at base p0+j+1
-        uint64_t valid = and_run(good, (int)k);
-        if (k > 1) valid &= and_run(nobrk, (int)k - 1);
+        // window i holds a k-mer iff bases i..i+k-1 are good and no read starts at bases i+1..i+k-1: one run of
+        // k-1 over (good & nobrk) and the last base's good bit
+        uint64_t valid = good;
+        if (k > 1) valid = and_run_uniform(good & nobrk, (int)k - 1) & (good >> (k - 1));
         valid16 = (uint32_t)valid & 0xFFFFu;
         // first super-chunk of a split push: the windows that start inside the halo belong to the previous piece
         const uint32_t skip_local = sc == 0 ? ep.skip : 0u;
@@ -469,15 +472,18 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
       uint32_t sum = 0;
 #pragma unroll
       for (int j = 0; j < SK_BUCKETS_PER_THREAD; ++j) {
-        cnt[j] = ((uint32_t)j < per_thread && t0 + j < g.n_buckets) ? hist[t0 + j] : 0u;
-        sum += cnt[j];
+        cnt[j] = 0;
+        if ((uint32_t)j < per_thread) {                  // CTA-uniform
+          cnt[j] = t0 + j < g.n_buckets ? hist[t0 + j] : 0u;
+          sum += cnt[j];
+        }
       }
       uint32_t run = block_exclusive_scan(sum, warp_sums, &scan_total);
       const uint32_t run0 = run;
 #pragma unroll
       for (int j = 0; j < SK_BUCKETS_PER_THREAD; ++j) {
         gb[j] = 0;
-        if (cnt[j]) {
+        if ((uint32_t)j < per_thread && cnt[j]) {
           const uint32_t b = t0 + j;
           loff[b] = run;
           // MULTI: every source GPU fills its OWN sub-slab of the owner's group slab: the cursor is local
@@ -499,7 +505,7 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
       run = run0;
 #pragma unroll
       for (int j = 0; j < SK_BUCKETS_PER_THREAD; ++j) {
-        if (cnt[j]) {
+        if ((uint32_t)j < per_thread && cnt[j]) {
           const uint32_t b = t0 + j;
           const uint32_t o = g.multi ? b / g.buckets_per_owner : 0u;
           // slab index inside its owner's array (MULTI: [group of the owner][source GPU])

@@ -31,8 +31,7 @@ __device__ __forceinline__ uint64_t sk_key(const uint4& rec, uint32_t o, uint32_
 // values the partition kernel is specialised for (16, 14, 12, 10, 8), with enough minimizer classes per tile
 // for an even load; otherwise the generic (slower) window with m = min(k, 16). Only the ~2/(W+1) of the 4^m/2
 // classes with the smallest order values ever win a window, and a tile's load is the sum over the classes it
-// owns: 4^m >= 2^13 * n_tiles leaves ~500 winning classes per tile (measured at m = 10, 1184 tiles, 5 Mb
-// genome: ~50 per tile, tile loads 58 % +- 9 %, 8 % of the keys beyond their probe window).
+// owns: 4^m >= 2^13 * n_tiles leaves ~500 winning classes per tile.
 static inline int sk_choose_m(int k, uint64_t n_tiles_global) {
   int lg = 0;
   while ((1ull << lg) < n_tiles_global) ++lg;

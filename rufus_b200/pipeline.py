@@ -207,6 +207,7 @@ class DevicePipeline:
                               self.mut_keys.numel())
         if n < 0:
             raise api._err("rg_subtract_dev")
+        self.n_local = int(n)
         keys = self.mut_keys[:n]
         if self.world > 1:
             keys = gather_varlen(keys)
@@ -224,6 +225,38 @@ class DevicePipeline:
     def mutant_keys_host(self):
         n = self.last["n_mutant"] if self.world == 1 else None
         return self.mut_keys[:n].cpu().numpy().view(np.uint64) if n is not None else None
+
+    def results(self) -> dict:
+        """The last step's results on the host: subject histogram (all shards), this shard's piece of the
+        HashList (keys, counts) and this rank's keep mask. What a caller reads back after a step."""
+        n = self.n_local
+        return {"histo": self.last["histo"], "keys": self.mut_keys[:n].cpu().numpy().view(np.uint64),
+                "counts": self.mut_counts[:n].cpu().numpy().view(np.uint32), "keep": self.keep.cpu().numpy()}
+
+    def gathered_results(self, sample_prefix: str = "C") -> dict:
+        """results of the whole job on every rank (not timed by the bench): the HashList pieces of all
+        shards concatenated, and the names of the pulled pairs of all ranks (workload.name_prefix naming)."""
+        import torch.distributed as dist
+        from . import workload
+        r = self.results()
+        names = workload.pulled_names(r["keep"], "Child", self.rank, self.world)
+        if self.world == 1:
+            return {"histo": r["histo"], "keys": r["keys"], "counts": r["counts"], "names": names}
+        parts = [None] * self.world
+        dist.all_gather_object(parts, (r["keys"], r["counts"], names))
+        return {"histo": r["histo"], "keys": np.concatenate([p[0] for p in parts]),
+                "counts": np.concatenate([p[1] for p in parts]), "names": [x for p in parts for x in p[2]]}
+
+    def step_from_host(self, host_streams, host_pairs) -> dict:
+        """One step with every input starting in (pinned) host memory and every result ending there: the
+        end-to-end call of the sharded pipeline. host_streams: list of uint8 torch tensors (pinned), one per
+        sample; host_pairs: the subject's (seq1, qual1, seq2, qual2) as pinned uint8 tensors."""
+        for d, h in zip(self.streams, host_streams):
+            d.copy_(h, non_blocking=True)
+        for d, h in zip((self.s1, self.q1, self.s2, self.q2), host_pairs):
+            d.copy_(h, non_blocking=True)
+        self.step()
+        return self.results()
 
     def free(self):
         for t in self.tables:

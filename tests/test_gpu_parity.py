@@ -345,3 +345,28 @@ def test_split_device_pushes(ctx, mode, monkeypatch):
     k2, c2 = oracle.count(both.reshape(-1), np.array([0, both.size], np.uint64), 25, True, 1)
     assert np.array_equal(keys, k2) and np.array_equal(counts, c2)
     t.free()
+
+
+def test_bench_workload_matches_reference_digests(ctx):
+    """BASELINE configs[1] / SURVEY §8d C2 at FULL size (seed 42, 5 Mb, 500 k pairs x 3 samples), exactly as bench.py
+    builds it: histogram, HashList and pulled read names against digests of the reference binaries' output
+    (tests/golden/bench_digests.json, tests/golden/make_bench_golden.py). Bit-exact."""
+    import torch
+    from rufus_b200 import pipeline, workload
+    exp = workload.expected(1)
+    assert exp is not None and exp["hashlist_lines"] == 1265 and exp["pulled_pairs"] == 682
+    trio = workload.make_slice(workload.SEED, workload.GENOME_UNIT, workload.PAIRS, 0, 1)
+    dev = torch.device("cuda", 0)
+    ctx.use_stream(torch.cuda.current_stream().cuda_stream)
+    streams = [torch.from_numpy(np.concatenate([trio[s][0], trio[s][2]]).reshape(-1)).to(dev) for s in synth.SAMPLES]
+    subj = tuple(torch.from_numpy(a.reshape(-1)).to(dev) for a in trio["Child"])
+    est = int(1.03 * workload.GENOME_UNIT + 6.2 * 2 * workload.PAIRS)
+    pipe = pipeline.DevicePipeline(ctx, workload.K, streams, subj, workload.READ_LEN, est, workload.MIN_COV,
+                                   workload.MAX_COV, workload.MINQ, workload.THRESH)
+    pipe.step()
+    pipe.step()          # twice: cleared and re-used tables give the same result
+    g = pipe.gathered_results()
+    par = workload.check(1, g["histo"], g["keys"], g["counts"], g["names"])
+    pipe.free()
+    ctx.use_stream(None)
+    assert par["ok"], par
