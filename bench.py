@@ -257,7 +257,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's banner off stdout: one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings stay off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     trio = make_data(args, rank, world)

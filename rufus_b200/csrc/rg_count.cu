@@ -4,6 +4,8 @@
 // (src/modifiedJellyfish/sub_commands/count_main.cc:154-157):
 //   mer_iterator::operator++   mer_iterator.hpp:61-89   -> stage_chunk + window_key
 //   array::add / claim_key     large_hash_array.hpp:298-302,513-601 -> rg_table_add / tile_insert_kernel
+#include <type_traits>
+
 #include "rg_internal.cuh"
 
 #include "rg_extract.cuh"
@@ -267,33 +269,47 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
     const uint32_t k = tv.geo.k;
 
     const uint32_t skeys_a = smem_u32(skeys), scounts_a = smem_u32(scounts);
-    // one probe of `key` at slot (sp & mask) for the lanes with `have`; failures are queued. Branch-free up to
-    // the queue push: the CAS (slot seen empty) and the count increment are PREDICATED instructions.
-    auto step = [&](uint64_t key, uint32_t sp, bool have) {
-      const uint32_t slot = sp & (RG_TILE_SLOTS - 1);
-      const uint32_t ka = skeys_a + slot * 8u;
-      unsigned long long seen;
-      asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(seen) : "r"(ka) : "memory");
-      const uint32_t try_claim = (have && seen == RG_EMPTY) ? 1u : 0u;
-      asm volatile(
-          "{\n"
-          ".reg .pred q;\n"
-          "setp.ne.u32 q, %2, 0;\n"
-          "@q atom.shared.cas.b64 %0, [%1], %3, %4;\n"
-          "}\n"
-          : "+l"(seen)
-          : "r"(ka), "r"(try_claim), "l"((unsigned long long)RG_EMPTY), "l"((unsigned long long)key)
-          : "memory");
-      const bool hit = have && ((seen == RG_EMPTY) | (seen == key));
-      asm volatile(
-          "{\n"
-          ".reg .pred q;\n"
-          "setp.ne.u32 q, %1, 0;\n"
-          "@q red.shared.add.u32 [%0], 1;\n"
-          "}\n" ::"r"(scounts_a + slot * 4u),
-          "r"(hit ? 1u : 0u)
-          : "memory");
-      const bool fail = have && !hit;
+    // NR probes per lane (NR independent dependency chains: with ~6 warps per scheduler the fixed latencies of
+    // one chain leave issue slots empty): key[i] at slot (sp[i] & mask) for the lanes with have[i]; fail[i] =
+    // the lane met another key. The CAS (slot seen empty) and the count increment are predicated.
+    auto probe = [&](auto nr_tag, const uint64_t* key, const uint32_t* sp, const bool* have, bool* fail) {
+      constexpr int NR = decltype(nr_tag)::value;
+      unsigned long long seen[NR];
+      uint32_t ka[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        ka[i] = skeys_a + (sp[i] & (RG_TILE_SLOTS - 1)) * 8u;
+        asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(seen[i]) : "r"(ka[i]) : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const uint32_t try_claim = (have[i] && seen[i] == RG_EMPTY) ? 1u : 0u;
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "setp.ne.u32 q, %2, 0;\n"
+            "@q atom.shared.cas.b64 %0, [%1], %3, %4;\n"
+            "}\n"
+            : "+l"(seen[i])
+            : "r"(ka[i]), "r"(try_claim), "l"((unsigned long long)RG_EMPTY), "l"((unsigned long long)key[i])
+            : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const bool hit = have[i] && ((seen[i] == RG_EMPTY) | (seen[i] == key[i]));
+        asm volatile(
+            "{\n"
+            ".reg .pred q;\n"
+            "setp.ne.u32 q, %1, 0;\n"
+            "@q red.shared.add.u32 [%0], 1;\n"
+            "}\n" ::"r"(scounts_a + (sp[i] & (RG_TILE_SLOTS - 1)) * 4u),
+            "r"(hit ? 1u : 0u)
+            : "memory");
+        fail[i] = have[i] && !hit;
+      }
+    };
+    // the failed lanes push (key, next slot) onto the warp's retry queue (room for 32 more entries required)
+    auto push = [&](uint64_t key, uint32_t sp, bool fail) {
       const uint32_t fm = __ballot_sync(0xFFFFFFFFu, fail);
       if (fm) {                                             // warp-uniform
         if (fail) {
@@ -320,7 +336,9 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
         rg_ovf_add(tv, key, 1u);
         have = false;
       }
-      step(key, sp, have);
+      bool fail;
+      probe(std::integral_constant<int, 1>{}, &key, &sp, &have, &fail);
+      push(key, sp, fail);
     };
 
     for (uint32_t b0 = warp * 32; b0 < n; b0 += TILE_WARPS * 32) {
@@ -343,17 +361,39 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
       if (len) atomicOr(&bm[start >> 5], 1u << (start & 31));
       __syncwarp();
       uint32_t carry = 0xFFFFFFFFu;                         // (records that start before this round) - 1, warp-uniform
-      for (uint32_t j0 = 0; j0 < T; j0 += 32) {
+      // k-mer j of the batch -> (key, home slot): the record it belongs to = (number of record starts at or
+      // before j) - 1; lanes past the batch's end (last round only) wrap to some valid record and are masked
+      auto fetch = [&](uint32_t j0, uint64_t& key, uint32_t& slot) {
         const uint32_t word = bm[j0 >> 5];
-        const uint32_t j = j0 + lane;
-        // the record k-mer j belongs to = (number of record starts at or before j) - 1; lanes past the batch's
-        // end (last round only) wrap to some valid record and are masked by `have`
         const uint32_t r = (carry + __popc(word & le_mask)) & 31u;
         carry += __popc(word);
-        const uint32_t o = (j - __shfl_sync(0xFFFFFFFFu, start, r)) & 15u;
+        const uint32_t o = (j0 + lane - __shfl_sync(0xFFFFFFFFu, start, r)) & 15u;
         const uint4 rr = rq[r];
-        const uint64_t key = sk_key(rr, o, k, canonical);
-        step(key, rg_slot_of_key(key), j < T);
+        key = sk_key(rr, o, k, canonical);
+        slot = rg_slot_of_key(key);
+      };
+      uint32_t j0 = 0;
+      for (; j0 + 32 < T; j0 += 64) {                       // two rounds at a time, their chains interleaved
+        uint64_t key[2];
+        uint32_t slot[2];
+        fetch(j0, key[0], slot[0]);
+        fetch(j0 + 32, key[1], slot[1]);
+        const bool have[2] = {true, j0 + 32 + lane < T};
+        bool fail[2];
+        probe(std::integral_constant<int, 2>{}, key, slot, have, fail);
+        push(key[0], slot[0], fail[0]);
+        while (qlen >= 32) drain();
+        push(key[1], slot[1], fail[1]);
+        while (qlen >= 32) drain();
+      }
+      if (j0 < T) {
+        uint64_t key;
+        uint32_t slot;
+        fetch(j0, key, slot);
+        const bool have = j0 + lane < T;
+        bool fail;
+        probe(std::integral_constant<int, 1>{}, &key, &slot, &have, &fail);
+        push(key, slot, fail);
         while (qlen >= 32) drain();
       }
     }

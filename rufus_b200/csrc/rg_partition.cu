@@ -343,7 +343,8 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
     __syncthreads();
 
     // ---- records of this thread: start mask, first record index, the three forward words
-    uint32_t starts = 0, valid16 = 0, my_first = 0, W0 = 0, W1 = 0, W2 = 0;
+    uint32_t starts = 0, valid16 = 0, my_first = 0;
+    bool stage_pending = SRC == 0 && more;            // the next super-chunk's bases wait in registers (pf)
     uint32_t n_in_chunk = 0;                          // level 2: records of this chunk
     if (SRC == 0) {
       // ---- 2. m-mer order hashes
@@ -372,9 +373,6 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
         const uint32_t skip_local = sc == 0 ? ep.skip : 0u;
         if ((uint32_t)p0 < skip_local) valid16 &= ~((skip_local - p0 >= 32u) ? 0xFFFFFFFFu : ((1u << (skip_local - p0)) - 1u));
       }
-      W0 = sm.fwd[t];
-      W1 = sm.fwd[t + 1];
-      W2 = sm.fwd[t + 2];
       __syncthreads();
       // ---- 3. minimizer value of every k-mer: sliding minimum over W m-mers
       uint32_t kmin[SK_R];
@@ -394,8 +392,6 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
           kmin[i] = mn;
         }
       }
-      // the stage buffers are free (every thread holds its words): store the next super-chunk
-      if (more) part_stage_store(sm, pf);
       __syncthreads();                                 // every neighbour has read y: the rows are reused for kmin
       // ---- 4. record starts
       uint32_t chg = 1u;
@@ -425,6 +421,8 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
     for (uint32_t round0 = 0;; round0 += SK_RMAX) {
       uint32_t foreign = 0;
       if (SRC == 0) {
+        // (a) every thread lists its records: (block, first window, length) descriptors at their record index.
+        // Divergent (0..16 records per thread, ~2.7 on average), so it only does the cheap part.
         uint32_t st = starts, idx = my_first;
         while (st) {
           const uint32_t s = __ffs(st) - 1;
@@ -434,18 +432,26 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
           if (rel >= SK_RMAX) continue;
           // the record runs to the next start, to the next window without a k-mer, or to the end of the block
           const uint32_t nb = ((starts | ~valid16) >> (s + 1)) | (1u << (15 - s));
-          const uint32_t len = __ffs(nb);
-          const uint32_t mh = rg_mix_min(Yt[s * SK_YS + t]);
+          sorted[rel] = (t << 8) | (s << 4) | (__ffs(nb) - 1u);
+        }
+        __syncthreads();
+        // (b) the records themselves, one per thread-iteration whatever block they come from (balanced)
+        const uint32_t n_here = min(SK_RMAX, rec_total - round0);
+        for (uint32_t i = t; i < n_here; i += SK_THREADS) {
+          const uint32_t d = sorted[i];
+          const uint32_t tt = d >> 8, s = (d >> 4) & 15u;
+          const uint32_t mh = rg_mix_min(Yt[s * SK_YS + tt]);
           uint32_t b = rg_group_of_mh(mh, g.n_buckets_global) - g.bucket_first;
           if (b >= g.n_buckets) {                      // another shard's record (sharded single-GPU push)
             ++foreign;
-            metaS[rel] = 0xFFFFFFFFu;
+            metaS[i] = 0xFFFFFFFFu;
             continue;
           }
           const uint32_t rank = atomicAdd(&hist[b], 1u);
-          recs[rel] = make_uint4(__funnelshift_l(W1, W0, 2 * s), __funnelshift_l(W2, W1, 2 * s), W2 << (2 * s),
-                                 mh | (len - 1));
-          metaS[rel] = (b << SK_RBITS) | rank;
+          const uint32_t W0 = sm.fwd[tt], W1 = sm.fwd[tt + 1], W2 = sm.fwd[tt + 2];
+          recs[i] = make_uint4(__funnelshift_l(W1, W0, 2 * s), __funnelshift_l(W2, W1, 2 * s), W2 << (2 * s),
+                               mh | (d & 15u));
+          metaS[i] = (b << SK_RBITS) | rank;
         }
       } else {
 #pragma unroll
@@ -463,6 +469,11 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
       if (foreign) atomicAdd((unsigned long long*)&g.tv.status[RG_ST_FOREIGN], (unsigned long long)foreign);
       __syncthreads();
       const uint32_t n_all = rec_total;
+      // the stage buffers are free once the last round's records are built: store the next super-chunk
+      if (stage_pending && round0 + SK_RMAX >= n_all) {
+        part_stage_store(sm, pf);
+        stage_pending = false;
+      }
       const uint32_t n_round = min(SK_RMAX, n_all - round0);
       // ---- 5. local offsets (exclusive scan of the run lengths); the global run reservations (one
       // atomicAdd per non-empty bucket) are only ISSUED here: their results are consumed after the
@@ -560,6 +571,119 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
       for (uint32_t i = t; i < g.n_buckets; i += SK_THREADS) hist[i] = 0;
       __syncthreads();
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Level 2 with few buckets (group slabs -> the <= 128 tiles of each group): a multi-split without the
+// shared-memory staging of the general kernel. With so few buckets one shared histogram would serialise
+// (hundreds of atomics per address per chunk: measured 0.72 ms per 25 M records); here every WARP owns a
+// histogram row, so an address sees at most the 32 lanes of one instruction. A CTA (256 threads, four per
+// SM) takes chunks of 1024 records (4 per thread, kept in registers); rank inside (warp, bucket) from the atomic, exclusive scan in
+// (bucket, warp) order, one global atomicAdd per non-empty bucket reserves the run, then every thread
+// writes its records straight to their slots (the ~8 records a warp holds for one bucket are contiguous).
+// ---------------------------------------------------------------------------
+constexpr int RG2_THREADS = 256;                         // small CTAs, several per SM: their load / atomic / store latencies overlap
+constexpr int RG2_CTAS = 4;
+constexpr int RG2_WARPS = RG2_THREADS / 32;
+constexpr int RG2_RPT = 4;                               // records per thread
+constexpr uint32_t RG2_CHUNK = RG2_THREADS * RG2_RPT;
+constexpr uint32_t RG2_MAXB = 128;                       // buckets (tiles per group) it handles
+constexpr int RG2_EPT = RG2_WARPS * RG2_MAXB / RG2_THREADS;   // (bucket, warp) cells per thread in the scan
+
+__global__ void __launch_bounds__(RG2_THREADS, RG2_CTAS)
+regroup_kernel(PartGeom g) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t scan_total;
+  __shared__ uint32_t boff[RG2_MAXB + 1];      // first sorted position of every bucket in the chunk
+  __shared__ uint32_t gdelta[RG2_MAXB];        // slab-array index of the bucket's run - boff (0xFFFFFFFF: checked per record)
+  __shared__ uint32_t glimit[RG2_MAXB];        // end of the bucket's slab in the slab array
+  const uint32_t B = g.n_buckets;
+  uint32_t* whist = reinterpret_cast<uint32_t*>(dyn);          // [B][RG2_WARPS]: cell (b, w) at b * RG2_WARPS + w
+  uint32_t* gstart = whist + RG2_WARPS * RG2_MAXB;             // [n_groups + 1]
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // chunk starts of the input slabs (exclusive prefix of their chunk counts)
+  uint32_t run_g = 0;
+  for (uint32_t base = 0; base < g.n_groups; base += RG2_THREADS) {
+    const uint32_t gi = base + t;
+    const uint32_t c = gi < g.n_groups ? (min(g.in_cursor[gi], g.in_cap) + RG2_CHUNK - 1) / RG2_CHUNK : 0u;
+    const uint32_t ex = block_exclusive_scan(c, warp_sums, &scan_total);
+    if (gi < g.n_groups) gstart[gi] = run_g + ex;
+    __syncthreads();
+    run_g += scan_total;
+    __syncthreads();
+  }
+  if (t == 0) gstart[g.n_groups] = run_g;
+  __syncthreads();
+  const uint32_t total_items = run_g;
+  uint32_t og = 0;
+  for (uint32_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    while (item >= gstart[og + 1]) ++og;
+    const uint32_t slab0 = (og / g.in_per_group) * B;
+    const uint32_t sc = item - gstart[og];
+    const uint32_t n_slab = min(g.in_cursor[og], g.in_cap);
+    const uint32_t n_chunk = min(RG2_CHUNK, n_slab - sc * RG2_CHUNK);
+    for (uint32_t i = t; i < RG2_WARPS * B; i += RG2_THREADS) whist[i] = 0;
+    __syncthreads();
+    uint4 rec[RG2_RPT];
+    uint32_t meta[RG2_RPT];                    // bucket << 16 | rank inside (warp, bucket)
+    const uint4* in = g.in_keys + (uint64_t)og * g.in_cap + (uint64_t)sc * RG2_CHUNK;
+#pragma unroll
+    for (int w = 0; w < RG2_RPT; ++w) {
+      const uint32_t i = w * RG2_THREADS + t;
+      rec[w] = i < n_chunk ? __ldg(in + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int w = 0; w < RG2_RPT; ++w) {
+      meta[w] = 0xFFFFFFFFu;
+      if (w * RG2_THREADS + t < n_chunk) {
+        const uint32_t b = rg_tile_in_group_of_mh(rec[w].w & ~15u, g.geo);
+        meta[w] = (b << 16) | atomicAdd(&whist[b * RG2_WARPS + warp], 1u);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the cells in (bucket, warp) order; RG2_EPT consecutive cells per thread
+    {
+      uint32_t v[RG2_EPT], sum = 0;
+#pragma unroll
+      for (int e = 0; e < RG2_EPT; ++e) {
+        const uint32_t c = t * RG2_EPT + e;
+        v[e] = c < RG2_WARPS * B ? whist[c] : 0u;
+        sum += v[e];
+      }
+      uint32_t ex = block_exclusive_scan(sum, warp_sums, &scan_total);
+#pragma unroll
+      for (int e = 0; e < RG2_EPT; ++e) {
+        const uint32_t c = t * RG2_EPT + e;
+        if (c < RG2_WARPS * B) {
+          whist[c] = ex;
+          if (c % RG2_WARPS == 0) boff[c / RG2_WARPS] = ex;
+        }
+        ex += v[e];
+      }
+      if (t == 0) boff[B] = scan_total;
+    }
+    __syncthreads();
+    if (t < B) {
+      const uint32_t cnt = boff[t + 1] - boff[t];
+      const uint32_t slab = slab0 + t;
+      uint32_t gb = 0;
+      if (cnt) gb = atomicAdd(g.out_cursor + slab, cnt);
+      gdelta[t] = slab * g.out_cap + gb - boff[t];
+      glimit[t] = (slab + 1) * g.out_cap;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < RG2_RPT; ++w) {
+      if (meta[w] != 0xFFFFFFFFu) {
+        const uint32_t b = meta[w] >> 16;
+        const uint32_t at = gdelta[b] + whist[b * RG2_WARPS + warp] + (meta[w] & 0xFFFFu);
+        if (at < glimit[b]) g.out_keys[at] = rec[w];
+        else sk_insert_direct(g.tv, rec[w], g.canonical);      // the tile's bucket slab is full
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -663,8 +787,15 @@ int rg_launch_partition_groups(rg_table* t) {
   }
   ExtractParams ep = {};
   // work items = record chunks over all groups (their number is only known on the device): a full grid
-  int rc = launch_sk<2, 0>(ctx, "partition_groups_kernel", ep, g, 1ull << 32, 0);
-  if (rc) return rc;
+  if (g.n_buckets <= RG2_MAXB) {
+    const size_t smem = (size_t)RG2_WARPS * RG2_MAXB * 4 + (size_t)(g.n_groups + 1) * 4;
+    RG_CUDA_OK(cudaFuncSetAttribute(regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rg_launch_scope _ls(ctx, "partition_groups_kernel");
+    regroup_kernel<<<rg_grid(ctx, RG2_CTAS), RG2_THREADS, smem, ctx->stream>>>(g);
+  } else {
+    int rc = launch_sk<2, 0>(ctx, "partition_groups_kernel", ep, g, 1ull << 32, 0);
+    if (rc) return rc;
+  }
   RG_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -97,6 +97,8 @@ class DevicePipeline:
         self.hits2 = torch.empty(self.n_pairs, dtype=torch.int32, device=dev)
         self.keep = torch.empty(self.n_pairs, dtype=torch.uint8, device=dev)
         self.exchange = exchange if world > 1 else "none"
+        import os
+        self.serial = os.environ.get("RG_P2P_SERIAL", "0") == "1"
         if self.exchange == "p2p":
             # peer-to-peer: every rank's partition pass writes straight into the owners' group slabs
             # (CUDA IPC mappings of one exported block per table); no collective in the data path
@@ -157,6 +159,17 @@ class DevicePipeline:
         if self.world == 1:
             for t, s in zip(self.tables, self.streams):
                 t.push_dev(s, s.numel(), self.read_len)   # enqueued only: no host synchronisation between the samples
+        elif self.exchange == "p2p" and self.serial:
+            # no overlap: scatter, barrier, finish, sample after sample on one stream (isolated kernel timings)
+            import torch.distributed as dist
+            for t in self.tables:
+                api._check(L.rg_count_p2p_begin(t.h), "rg_count_p2p_begin")
+            self.stream_barrier()
+            for t, s in zip(self.tables, self.streams):
+                api._check(L.rg_count_p2p_scatter_dev(t.h, api._ptr(s), s.numel(), self.read_len, 0),
+                           "rg_count_p2p_scatter_dev")
+                self.stream_barrier()
+                api._check(L.rg_count_p2p_finish(t.h), "rg_count_p2p_finish")
         elif self.exchange == "p2p":
             import torch.distributed as dist
             main = torch.cuda.current_stream()
