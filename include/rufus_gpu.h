@@ -156,6 +156,19 @@ int rg_count_p2p_finish(rg_table* t);
  * where base = (low<=1 ? 0 : low-1); see rg_histo_rows. */
 uint64_t rg_histo_rows(uint64_t low, uint64_t high);
 int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint64_t* out_host);
+/* same, rows left on the DEVICE (rg_histo_rows(low, high) uint64); enqueued only, no host round trip */
+int rg_histo_dev(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint64_t* out_dev);
+
+/* A whole pass (count -> histo -> subtract -> read pull) enqueued without host round trips: with
+ * rg_defer_checks(ctx, 1) the readers of a table no longer wait for the status words of the enqueued pushes;
+ * the caller fetches them with rg_table_status_async (9 uint64 of pinned host memory: [1] foreign keys,
+ * [2] k-mers that found no slot, [8] records spilled by peer GPUs; all zero = clean), synchronises once at the
+ * end of the pass and, when a table is not clean, turns the deferral off, calls rg_count_end (which resolves
+ * it) and repeats the readers. */
+int rg_defer_checks(rg_ctx* ctx, int on);
+int rg_table_status_async(rg_table* t, uint64_t* host_pinned9);
+/* the same 9 words copied into DEVICE memory (callers that reduce them on the device, e.g. across ranks) */
+int rg_table_status_dev(rg_table* t, uint64_t* dev_out9);
 
 /* ---- K5: dump -----------------------------------------------------------
  * entries with min_count <= count <= max_count (sorted_dumper.hpp:94) as jf keys +
@@ -217,6 +230,11 @@ int64_t rg_subtract(rg_table* subj, uint64_t subj_min, rg_table* const* others, 
 int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
                         int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_dev,
                         uint32_t* counts_dev, uint64_t cap);
+/* same, enqueued only: the number of survivors stays on the device (*count_dev; it may exceed cap, the excess
+ * is dropped) and the unused tail of keys_dev is filled with ~0 (never a canonical key) */
+int rg_subtract_enqueue(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
+                        int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_dev,
+                        uint32_t* counts_dev, uint64_t cap, uint64_t* count_dev);
 
 /* ---- S2: RUFUS.Build, the legacy selection (src/RUFUS.Build.cpp:224-283) -------------
  * { (x, c_S(x), sum_i c_i(x)) : min_subject <= c_S(x) <= max_subject, sum over the control tables
@@ -237,6 +255,10 @@ rg_set* rg_set_from_rufus_keys(rg_ctx* ctx, const uint64_t* rufus_keys_host, uin
 /* from canonical jf keys (e.g. rg_subtract output): inserts k-mer and reverse complement */
 rg_set* rg_set_from_jf_keys(rg_ctx* ctx, const uint64_t* jf_keys_host, uint64_t n, int k);
 rg_set* rg_set_from_jf_keys_dev(rg_ctx* ctx, const uint64_t* jf_keys_dev, uint64_t n, int k);
+/* a set rebuilt in place every pass (no allocation, no host round trip): rg_set_create(k < 32, room for max_keys
+ * jf keys), then rg_set_rebuild_dev(jf_keys_dev, n_max <= max_keys): entries equal to ~0 are padding */
+rg_set* rg_set_create(rg_ctx* ctx, int k, uint64_t max_keys);
+int rg_set_rebuild_dev(rg_set* s, const uint64_t* jf_keys_dev, uint64_t n_max);
 uint64_t rg_set_size(rg_set* s);
 void rg_set_free(rg_set* s);
 /* per-read hit counts; all DEVICE pointers. skip_last=1: paired tool's `i < length()-1` bound */

@@ -78,6 +78,13 @@ def lib():
         "rg_table_canonical": (i32, [vp]),
         "rg_extract_partition_dev": (i32, [vp, vp, u64, u32, vp, vp]),
         "rg_key_shard": (u32, [u64, i32, i32, u32, u32]),
+        "rg_defer_checks": (i32, [vp, i32]),
+        "rg_table_status_async": (i32, [vp, vp]),
+        "rg_table_status_dev": (i32, [vp, vp]),
+        "rg_histo_dev": (i32, [vp, u64, u64, u64, vp]),
+        "rg_subtract_enqueue": (i32, [vp, u64, vp, vp, i32, u64, i64, i64, vp, vp, u64, vp]),
+        "rg_set_create": (vp, [vp, i32, u64]),
+        "rg_set_rebuild_dev": (i32, [vp, vp, u64]),
         "rg_minimizer_len": (i32, [i32, u64]),
         "rg_table_geometry": (i32, [vp, vp, vp, vp, vp]),
         "rg_count_push_keys_dev": (i32, [vp, vp, u64]),

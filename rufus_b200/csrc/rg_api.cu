@@ -571,7 +571,7 @@ static int p2p_collect_spill(rg_table* t) {
 }
 
 int rg_table_finish(rg_table* t) {
-  if (!t->unchecked) return 0;
+  if (!t->unchecked || t->ctx->defer_checks) return 0;
   if (t->p2p_pending) {
     const int prc = p2p_collect_spill(t);
     if (prc) return prc;
@@ -769,12 +769,7 @@ int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_byt
   int rc = rg_launch_partition_multi(t, ep);
   if (rc) return rc;
   // publish the fills of my sub-slabs: owner o's cursor[g][me] = my local cursor of its group g
-  const uint32_t gl = t->n_tiles / t->group_tiles;
-  for (uint32_t o = 0; o < t->shard_parts; ++o)
-    RG_CUDA_OK(cudaMemcpy2DAsync(t->peer_cursor[o] + t->shard_part, (size_t)t->shard_parts * 4,
-                                 t->p2p_src_cursor + (uint64_t)o * gl, 4, 4, gl, cudaMemcpyDeviceToDevice,
-                                 t->ctx->stream));
-  return 0;
+  return rg_launch_publish_cursors(t);
 }
 
 // after every rank's scatter has completed (caller's barrier): my groups -> tiles -> inserts.
@@ -1010,6 +1005,40 @@ int rg_extract_partition_dev(rg_table* t, const char* dev_stream, uint64_t n_byt
                                      ctx->d_scratch + 64);
 }
 
+// ---- deferred checks: a whole pass enqueued without a host round trip ---------
+// With rg_defer_checks(ctx, 1) the readers of a table (histo, subtract, dump ...) no longer wait for the
+// status words of the enqueued pushes; the caller fetches them with rg_table_status_async into pinned
+// memory, synchronises ONCE at the end of its pass and, if a table reports spilled / foreign keys, turns
+// the deferral off, calls rg_count_end (which resolves them) and repeats the readers.
+int rg_defer_checks(rg_ctx* ctx, int on) {
+  if (!ctx) return RG_ERR_ARG;
+  ctx->defer_checks = on != 0;
+  return 0;
+}
+
+// host_pinned[0..7] = the table's RG_ST_* words, [8] = records other GPUs spilled into my exported list
+int rg_table_status_async(rg_table* t, uint64_t* host_pinned) {
+  if (!t || !host_pinned) return RG_ERR_ARG;
+  rg_ctx* ctx = t->ctx;
+  RG_CUDA_OK(cudaMemcpyAsync(host_pinned, t->d_status, RG_ST_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  host_pinned[8] = 0;
+  if (t->p2p_block)
+    RG_CUDA_OK(cudaMemcpyAsync(host_pinned + 8, t->p2p_status, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+// same words into DEVICE memory (9 uint64), for callers that reduce them on the device
+int rg_table_status_dev(rg_table* t, uint64_t* dev_out9) {
+  if (!t || !dev_out9) return RG_ERR_ARG;
+  rg_ctx* ctx = t->ctx;
+  RG_CUDA_OK(cudaMemcpyAsync(dev_out9, t->d_status, RG_ST_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (t->p2p_block)
+    RG_CUDA_OK(cudaMemcpyAsync(dev_out9 + 8, t->p2p_status, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  else
+    RG_CUDA_OK(cudaMemsetAsync(dev_out9 + 8, 0, sizeof(uint64_t), ctx->stream));
+  return 0;
+}
+
 // ---- histo ----------------------------------------------------------------
 static inline uint64_t histo_base(uint64_t low) { return 1 >= low ? 0 : low - 1; }   // histo_main.cc:64
 uint64_t rg_histo_rows(uint64_t low, uint64_t high) { return (high + 1) + 1 - histo_base(low); }
@@ -1032,6 +1061,14 @@ int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint6
     if (e != cudaSuccess) { rg_set_error(cudaGetErrorString(e)); rc = RG_ERR_CUDA; }
   }
   return rc;
+}
+
+// histogram left on the device (rg_histo_rows(low, high) uint64): no host round trip
+int rg_histo_dev(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint64_t* out_dev) {
+  if (!t || high < low || !out_dev) return RG_ERR_ARG;
+  int rc = rg_table_finish(t);
+  if (rc) return rc;
+  return rg_launch_histo(t, min_count, histo_base(low), rg_histo_rows(low, high), out_dev);
 }
 
 // ---- dump / query -----------------------------------------------------------
@@ -1148,6 +1185,29 @@ static int fill_others(OtherTables& ot, rg_table* const* others, const uint64_t*
     ot.min_count[i] = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(m, 1), 0xFFFFFFFFull);
   }
   return 0;
+}
+
+// the subtraction enqueued only: survivors in keys_dev / counts_dev (the unused tail of keys_dev is filled with
+// ~0, never a canonical key, so a fixed-capacity buffer can travel as it is), their number (it may exceed cap:
+// the excess is dropped) in *count_dev. No host round trip.
+int rg_subtract_enqueue(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
+                        int n_others, uint64_t floor, int64_t min_cov, int64_t max_cov, uint64_t* keys_dev,
+                        uint32_t* counts_dev, uint64_t cap, uint64_t* count_dev) {
+  if (!subj || !count_dev) return RG_ERR_ARG;
+  rg_ctx* ctx = subj->ctx;
+  OtherTables ot;
+  int rc = rg_table_finish(subj);
+  if (rc) return rc;
+  rc = fill_others(ot, others, other_min, n_others, subj->k, subj);
+  if (rc) return rc;
+  RG_CUDA_OK(cudaMemsetAsync(keys_dev, 0xFF, cap * 8, ctx->stream));
+  uint64_t lo = std::max<uint64_t>(std::max<uint64_t>(subj_min, floor), 1);
+  if (min_cov > 0) lo = std::max<uint64_t>(lo, (uint64_t)min_cov);
+  if (max_cov < 0) {   // nothing can pass `count <= max`
+    RG_CUDA_OK(cudaMemsetAsync(count_dev, 0, sizeof(uint64_t), ctx->stream));
+    return 0;
+  }
+  return rg_launch_subtract(subj, lo, (uint64_t)max_cov, ot, keys_dev, counts_dev, cap, count_dev);
 }
 
 int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* others, const uint64_t* other_min,
@@ -1404,6 +1464,38 @@ rg_set* rg_set_from_jf_keys_dev(rg_ctx* ctx, const uint64_t* jf_keys_dev, uint64
   return s;
 }
 
+// A set that is rebuilt in place every pass (no allocation, no host round trip): room for max_keys jf keys.
+rg_set* rg_set_create(rg_ctx* ctx, int k, uint64_t max_keys) {
+  if (k >= 32) {
+    rg_set_error("rg_set_create: k < 32 (the all-ones rufus key of k = 32 needs the host's attention)");
+    return nullptr;
+  }
+  rg_set* s = set_alloc(ctx, 2 * max_keys, k);
+  if (!s) return nullptr;
+  if (cudaMalloc(&s->scratch, (max_keys ? max_keys : 1) * 16) != cudaSuccess) {
+    rg_set_error("rg_set_create: out of device memory");
+    rg_set_free(s);
+    return nullptr;
+  }
+  s->max_keys = max_keys;
+  return s;
+}
+
+// members = the n_max canonical jf keys at jf_keys_dev (and their reverse complements); entries equal to ~0 are
+// padding. Enqueued only.
+int rg_set_rebuild_dev(rg_set* s, const uint64_t* jf_keys_dev, uint64_t n_max) {
+  if (!s || !s->scratch || n_max > s->max_keys) {
+    rg_set_error("rg_set_rebuild_dev: needs a set from rg_set_create with room for n_max keys");
+    return RG_ERR_ARG;
+  }
+  rg_ctx* ctx = s->ctx;
+  RG_CUDA_OK(cudaMemsetAsync(s->table, 0xFF, (uint64_t)s->slots * 8, ctx->stream));
+  RG_CUDA_OK(cudaMemsetAsync(s->bitmap, 0, RG_SET_BITMAP_BITS / 8, ctx->stream));
+  int rc = rg_launch_jf_to_rufus(ctx, jf_keys_dev, n_max, s->k, s->scratch);
+  if (rc == 0) rc = rg_launch_set_build(s, s->scratch, 2 * n_max);
+  return rc;
+}
+
 rg_set* rg_set_from_jf_keys(rg_ctx* ctx, const uint64_t* jf_keys_host, uint64_t n, int k) {
   uint64_t* d = nullptr;
   if (n) {
@@ -1468,6 +1560,7 @@ void rg_set_free(rg_set* s) {
   cudaStreamSynchronize(s->ctx->stream);
   cudaFree(s->table);
   cudaFree(s->bitmap);
+  cudaFree(s->scratch);
   delete s;
 }
 

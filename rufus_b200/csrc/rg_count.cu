@@ -128,6 +128,31 @@ int rg_launch_rehash(rg_table* dst, const uint64_t* old_keys, const uint32_t* ol
   return 0;
 }
 
+// peer-to-peer counting: owner o's cursor[g][me] = my local fill of its group g, for every owner, one launch
+struct PeerCursors {
+  uint32_t* p[8];
+};
+__global__ void publish_cursors_kernel(const uint32_t* __restrict__ src, PeerCursors peers, uint32_t groups_local,
+                                       uint32_t n_parts, uint32_t me) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups_local * n_parts) return;
+  const uint32_t o = i / groups_local, g = i - o * groups_local;
+  peers.p[o][g * n_parts + me] = src[i];
+}
+
+int rg_launch_publish_cursors(rg_table* t) {
+  rg_ctx* ctx = t->ctx;
+  const uint32_t gl = t->n_tiles / t->group_tiles, n = gl * t->shard_parts;
+  PeerCursors pc = {};
+  for (uint32_t o = 0; o < t->shard_parts; ++o) pc.p[o] = t->peer_cursor[o];
+  {
+    rg_launch_scope _ls(ctx, "publish_cursors_kernel");
+    publish_cursors_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(t->p2p_src_cursor, pc, gl, t->shard_parts, t->shard_part);
+  }
+  RG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // read-start bitmap from an offsets array
 __global__ void mark_breaks_kernel(const uint64_t* __restrict__ offs, uint64_t n_reads, uint32_t* brk) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_reads;

@@ -75,6 +75,11 @@ int rg_launch_set_build(rg_set* s, const uint64_t* d_vals, uint64_t n) {
 __global__ void jf_to_rufus_kernel(const uint64_t* __restrict__ jf, uint64_t n, int k, uint64_t* out) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t f = jf[i];
+    if (f == RG_EMPTY) {            // padding of a fixed-capacity key list (never a canonical key): skipped by the set build
+      out[2 * i] = RG_EMPTY;
+      out[2 * i + 1] = RG_EMPTY;
+      continue;
+    }
     const uint64_t r = rg_revcomp_jf(f, k);
     uint64_t a = 0, b = 0;
     for (int j = 0; j < k; ++j) {

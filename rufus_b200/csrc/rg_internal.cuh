@@ -61,6 +61,7 @@ struct rg_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
+  bool defer_checks = false;   // rg_defer_checks: readers do not wait for the status words of enqueued pushes
   uint32_t force_groups = 0;   // RG_GROUPS_LOCAL (test knob): tiled tables use this many groups, i.e. the two-level partition
   // small pinned scratch for scalar read-backs
   uint64_t* h_scratch = nullptr;  // pinned, 64 u64
@@ -144,6 +145,8 @@ struct rg_set {
   uint32_t* bitmap = nullptr;  // bitmap_bits-bit prefilter (allocated at RG_SET_BITMAP_BITS)
   uint32_t bitmap_bits = 1u << 15;  // power of two in [2^15, RG_SET_BITMAP_BITS], ~64 bits per member
   int has_all_ones = 0;     // the value ~0 itself is a member (k = 32, all T)
+  uint64_t* scratch = nullptr;   // rg_set_create: room for the 2 * max_keys rufus keys of a rebuild
+  uint64_t max_keys = 0;
 };
 #define RG_SET_BITMAP_BITS (1u << 19)
 
@@ -392,6 +395,7 @@ int rg_launch_tile_insert(rg_table* t);                           // consume buc
 int rg_launch_insert_keys(rg_table* t, const uint64_t* dev_keys, uint64_t n, const uint32_t* dev_counts);
 int rg_launch_insert_records(rg_table* t, const uint4* dev_recs, uint64_t n);
 int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads, uint32_t* brk);
+int rg_launch_publish_cursors(rg_table* t);                       // peer-to-peer: my sub-slab fills -> every owner's cursor array
 int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, RgGeo geo, uint32_t n_parts, uint64_t* keys_out,
                                 uint64_t* part_offsets, uint64_t* d_tmp_counts);
 

@@ -78,7 +78,7 @@ class DevicePipeline:
     def __init__(self, ctx: api.Context, k: int, streams, subject_pairs, read_len: int, est_distinct: int,
                  min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
                  mode: int = api.MODE_TILED, rank: int = 0, world: int = 1, max_mutant: int = 1 << 22,
-                 exchange: str = "p2p", groups_per_shard: int = 0, scatter_ctas: int = 0):
+                 exchange: str = "p2p", groups_per_shard: int = 0, scatter_ctas: int = 0, fast_cap: int = 1 << 16):
         import torch
 
         self.torch = torch
@@ -99,6 +99,26 @@ class DevicePipeline:
         self.exchange = exchange if world > 1 else "none"
         import os
         self.serial = os.environ.get("RG_P2P_SERIAL", "0") == "1"
+        # Fast path: the whole pass is ENQUEUED (deferred status checks, histogram / subtraction count / kept
+        # count left on the device, a set rebuilt in place, one fixed-capacity all-gather of the mutant k-mers)
+        # and the host synchronises once, at the end. Falls back to the step-by-step path when a table reports
+        # spilled keys or a shard finds more than fast_cap mutant k-mers.
+        self.fast_cap = min(fast_cap, max_mutant)
+        self.fast = k < 32 and os.environ.get("RG_PIPELINE_SLOW", "0") != "1"
+        if self.fast:
+            L0 = api.lib()
+            self.fast_set = L0.rg_set_create(ctx.h, k, self.fast_cap * world)
+            if not self.fast_set:
+                raise api._err("rg_set_create")
+            # all-reduced in one go: histogram rows, mutant k-mer count, "some table / shard needs the slow tail"
+            self.red = torch.zeros(10002 + 2, dtype=torch.int64, device=dev)
+            self.count_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.gathered = torch.empty(self.fast_cap * world, dtype=torch.int64, device=dev) if world > 1 else None
+            self.res_dev = torch.zeros(2, dtype=torch.int64, device=dev)           # local mutant count, kept pairs
+            self.status_dev = torch.zeros(len(streams), 9, dtype=torch.int64, device=dev)
+            self.dirty_idx = torch.tensor([1, 2, 8], dtype=torch.int64, device=dev)
+            self.red_host = torch.zeros(10002 + 2, dtype=torch.int64).pin_memory()
+            self.res_host = torch.zeros(2, dtype=torch.int64).pin_memory()
         if self.exchange == "p2p":
             # peer-to-peer: every rank's partition pass writes straight into the owners' group slabs
             # (CUDA IPC mappings of one exported block per table); no collective in the data path
@@ -203,6 +223,58 @@ class DevicePipeline:
                 work.wait()                                # the compute stream waits for the transfer, not the host
                 self.tables[i].push_keys_dev(mine, mine.numel())
                 inflight = nxt
+        if self.fast and self._fast_tail():
+            return self.last
+        return self._slow_tail()
+
+    def _fast_tail(self) -> bool:
+        """histo -> subtract -> set -> read pull enqueued behind the counts, ONE host synchronisation. Returns
+        False (nothing consumed) when the step-by-step tail has to run instead."""
+        torch = self.torch
+        L = api.lib()
+        cap = self.fast_cap
+        api._check(L.rg_defer_checks(self.ctx.h, 1), "rg_defer_checks")
+        try:
+            for i, t in enumerate(self.tables):
+                api._check(L.rg_table_status_dev(t.h, api._ptr(self.status_dev[i])), "rg_table_status_dev")
+            api._check(L.rg_histo_dev(self.tables[0].h, self.lower[0], 1, 10000, api._ptr(self.red)), "rg_histo_dev")
+            others = self.tables[1:]
+            om = np.ascontiguousarray(self.lower[1:], np.uint64)
+            api._check(L.rg_subtract_enqueue(self.tables[0].h, self.lower[0], api._handles(others), api._ptr(om),
+                                             len(others), 5, self.min_cov, self.max_cov, api._ptr(self.mut_keys),
+                                             api._ptr(self.mut_counts), cap, api._ptr(self.count_dev)),
+                       "rg_subtract_enqueue")
+            self.red[10002:10003] = self.count_dev
+            # foreign keys, k-mers without a slot, records spilled by peers, or more mutant k-mers than the fast buffers hold
+            self.red[10003:10004] = self.status_dev.index_select(1, self.dirty_idx).sum() + (self.count_dev > cap).to(torch.int64)
+            keys_all, n_max = self.mut_keys[:cap], cap
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.red)                                   # histogram + total mutant count
+                dist.all_gather_into_tensor(self.gathered, self.mut_keys[:cap])
+                keys_all, n_max = self.gathered, cap * self.world
+            api._check(L.rg_set_rebuild_dev(self.fast_set, api._ptr(keys_all), n_max), "rg_set_rebuild_dev")
+            rc = L.rg_filter_pairs_fixed_dev(self.fast_set, api._ptr(self.s1), api._ptr(self.q1), api._ptr(self.s2),
+                                             api._ptr(self.q2), self.read_len, self.n_pairs, self.minq, self.thresh,
+                                             api._ptr(self.hits1), api._ptr(self.hits2), api._ptr(self.keep))
+            api._check(rc, "rg_filter_pairs_fixed_dev")
+            self.res_dev[0:1] = self.count_dev
+            self.res_dev[1:2] = self.keep.sum(dtype=torch.int64)
+            self.red_host.copy_(self.red, non_blocking=True)
+            self.res_host.copy_(self.res_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()                       # the pass's only host synchronisation
+        finally:
+            api._check(L.rg_defer_checks(self.ctx.h, 0), "rg_defer_checks")
+        if int(self.red_host[10003]) != 0:      # (all-reduced: every rank takes the same path)
+            return False
+        self.n_local = int(self.res_host[0])
+        self.last.update({"n_mutant": int(self.red_host[10002]), "n_kept": int(self.res_host[1]),
+                          "histo": self.red_host[:10002].numpy().astype(np.uint64)})
+        return True
+
+    def _slow_tail(self) -> dict:
+        torch = self.torch
+        L = api.lib()
         for t in self.tables:
             t.end(trim=False)             # one read-back of the status words per table (spill / foreign keys)
         # histogram of the subject (jellyfish histo -f); all-reduced over shards
@@ -272,6 +344,9 @@ class DevicePipeline:
         return self.results()
 
     def free(self):
+        if self.fast and self.fast_set:
+            api.lib().rg_set_free(self.fast_set)
+            self.fast_set = None
         for t in self.tables:
             t.free()
 
