@@ -143,6 +143,12 @@ int rg_table_set_shard(rg_table* t, uint32_t part, uint32_t n_parts);
 int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_keys_per_push);
 int rg_table_p2p_export(rg_table* t, void* handle64_out);
 int rg_table_p2p_import(rg_table* t, uint32_t rank, const void* handle64);
+/* ONE process driving several GPUs (one rg_ctx + one prepared shard table per device; how `jellyfish count` uses
+ * every visible GPU): instead of export / import, attach the shards to one another directly (enables peer access
+ * between their devices). tabs[r] = shard r of n. */
+int rg_tables_p2p_attach(rg_table* const* tabs, int n);
+/* number of CUDA devices visible to the process (0 without a driver) */
+int rg_device_count(void);
 int rg_count_p2p_begin(rg_table* t);
 /* max_ctas: CTAs of the scatter kernel (0 = one per SM). It is NVLink-bound: with fewer CTAs it leaves
  * SMs to the finish kernels of the previous sample running on another stream. */
@@ -210,6 +216,10 @@ int64_t rg_jf_sort(rg_ctx* ctx, uint64_t* keys_host, uint32_t* counts_host, uint
  * for max_count (none) and counter_len (4). */
 int64_t rg_table_write_jhash(rg_table* t, const char* path, uint64_t min_count, uint64_t max_count, uint64_t size,
                              uint32_t counter_len, const char* const* cmdline, int n_cmdline);
+/* the same from the n hash-prefix shards of one table (one per GPU, tabs[r] = shard r): ONE file, records in
+ * the (pos, key) order of a single table */
+int64_t rg_tables_write_jhash(rg_table* const* tabs, int n_tabs, const char* path, uint64_t min_count, uint64_t max_count,
+                              uint64_t size, uint32_t counter_len, const char* const* cmdline, int n_cmdline);
 /* load a .Jhash (ours or real Jellyfish's) into a device table; info (optional) gets the header values */
 rg_table* rg_table_read_jhash(rg_ctx* ctx, const char* path, rg_jf_info* info);
 

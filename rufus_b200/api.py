@@ -78,6 +78,9 @@ def lib():
         "rg_table_canonical": (i32, [vp]),
         "rg_extract_partition_dev": (i32, [vp, vp, u64, u32, vp, vp]),
         "rg_key_shard": (u32, [u64, i32, i32, u32, u32]),
+        "rg_device_count": (i32, []),
+        "rg_tables_p2p_attach": (i32, [vp, i32]),
+        "rg_tables_write_jhash": (i64, [vp, i32, C.c_char_p, u64, u64, u64, u32, vp, i32]),
         "rg_defer_checks": (i32, [vp, i32]),
         "rg_table_status_async": (i32, [vp, vp]),
         "rg_table_status_dev": (i32, [vp, vp]),

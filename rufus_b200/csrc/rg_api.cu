@@ -86,6 +86,7 @@ int rg_use_stream(rg_ctx* ctx, void* cuda_stream) {
 }
 
 int rg_sync(rg_ctx* ctx) {
+  cudaSetDevice(ctx->device);
   RG_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -166,6 +167,7 @@ void rg_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 int rg_h2d(rg_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  cudaSetDevice(ctx->device);
   RG_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
@@ -296,7 +298,8 @@ static int table_alloc_tiles(rg_table* t, uint32_t wanted, uint64_t ovf_slots = 
   t->tile_first = n_tiles * t->shard_part;
   t->ovf_slots = ovf_slots;
   t->ovf_used = 0;
-  t->m = sk_choose_m(t->k, t->n_tiles_global);
+  // (a peer-to-peer table keeps its minimizer length for life: the other GPUs route records with it)
+  if (!t->p2p_block) t->m = sk_choose_m(t->k, t->n_tiles_global);
   return 0;
 }
 
@@ -314,10 +317,8 @@ static int table_grow(rg_table* t, uint32_t new_tiles, uint64_t new_ovf = 0) {
   uint64_t* old_keys = t->keys;
   uint32_t* old_counts = t->counts;
   const uint64_t old_slots = rg_table_slots(t);
-  if (t->p2p_block) {
-    rg_set_error("count: a peer-to-peer table cannot grow (its slabs are exported); raise est_distinct");
-    return RG_ERR_FULL;
-  }
+  // (a peer-to-peer table grows like any other: the number of hash-prefix groups, hence the exported slabs
+  // and what the other GPUs send where, stays; only the tiles per group change, which is local)
   t->keys = nullptr;
   t->counts = nullptr;
   int rc = table_alloc_tiles(t, new_tiles, new_ovf);
@@ -388,11 +389,6 @@ static int table_check_status(rg_table* t) {
     }
     const uint64_t n_spill = st[RG_ST_LOST];
     if (n_spill == 0 && t->ovf_used * 2 <= t->ovf_slots) return 0;
-    if (t->p2p_block) {
-      if (n_spill == 0) return 0;      // (fixed geometry: it runs until the overflow region is really full)
-      rg_set_error("count: a peer-to-peer table is full (its geometry is fixed); raise est_distinct");
-      return RG_ERR_FULL;
-    }
     // Either the tiles are too loaded (more tiles), or a few minimizers own more k-mers than a tile holds
     // (a larger overflow region). The spilled pairs are moved aside and re-inserted into the rebuilt table.
     uint64_t* tmp_k = nullptr;
@@ -696,11 +692,14 @@ int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_ke
   t->p2p_groups = std::max<uint32_t>(1, std::min<uint32_t>(groups_per_shard, std::max<uint32_t>(wanted, 2) / 2));
   int rc = table_alloc_tiles(t, std::max<uint32_t>(wanted, 2));
   if (rc) return rc;
+  // the minimizer length is fixed from here on (every GPU computes the same value: same k, same global tile
+  // count); leave room for the table to grow 16x
+  t->m = sk_choose_m(t->k, (uint64_t)t->n_tiles_global * 16);
   const uint64_t n_groups = (uint64_t)(t->n_tiles / t->group_tiles) * t->shard_parts;      // sub-slabs I own
   const uint64_t n_rec = (uint64_t)((double)max_keys_per_push * rg_partition_record_density(t->k, t->m)) + 1;
   const uint64_t gmean = n_rec / n_groups + 1;
   t->grp_cap = (uint32_t)((gmean + gmean / 2 + 1024 + 3) & ~3ull);
-  t->p2p_spill_cap = 1ull << 20;
+  t->p2p_spill_cap = std::max<uint64_t>(1ull << 20, max_keys_per_push / 16);
   t->p2p_max_keys = max_keys_per_push;
   uint64_t os, osp, osl, tot;
   p2p_layout(t, &os, &osp, &osl, &tot);
@@ -739,8 +738,49 @@ int rg_table_p2p_import(rg_table* t, uint32_t rank, const void* handle64) {
   return 0;
 }
 
+// One process driving several GPUs (no IPC): attach every table's exported block to every other table
+// directly, after enabling peer access between their devices. tabs[r] must be shard r of n.
+int rg_tables_p2p_attach(rg_table* const* tabs, int n) {
+  if (!tabs || n < 1 || n > 8) return RG_ERR_ARG;
+  for (int i = 0; i < n; ++i)
+    if (!tabs[i] || !tabs[i]->p2p_block || tabs[i]->shard_parts != (uint32_t)n || tabs[i]->shard_part != (uint32_t)i) {
+      rg_set_error("rg_tables_p2p_attach: tabs[r] must be the prepared shard r of n");
+      return RG_ERR_ARG;
+    }
+  for (int i = 0; i < n; ++i) {
+    RG_CUDA_OK(cudaSetDevice(tabs[i]->ctx->device));
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      const int dj = tabs[j]->ctx->device;
+      if (dj != tabs[i]->ctx->device) {
+        int can = 0;
+        RG_CUDA_OK(cudaDeviceCanAccessPeer(&can, tabs[i]->ctx->device, dj));
+        if (!can) {
+          rg_set_error("rg_tables_p2p_attach: no peer access between the devices");
+          return RG_ERR_CUDA;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          rg_set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+          return RG_ERR_CUDA;
+        }
+        cudaGetLastError();
+      }
+      p2p_pointers(tabs[j], tabs[j]->p2p_block, (uint32_t)j, tabs[i]);
+    }
+  }
+  return 0;
+}
+
+int rg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
 int rg_count_p2p_begin(rg_table* t) {
   if (!t || !t->p2p_block) return RG_ERR_ARG;
+  cudaSetDevice(t->ctx->device);
   RG_CUDA_OK(cudaMemsetAsync(t->p2p_src_cursor, 0, (uint64_t)t->n_tiles_global / t->group_tiles * 4, t->ctx->stream));
   RG_CUDA_OK(cudaMemsetAsync(t->p2p_status, 0, 64, t->ctx->stream));
   return 0;
@@ -749,6 +789,7 @@ int rg_count_p2p_begin(rg_table* t) {
 int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_bytes, uint32_t read_stride,
                              uint32_t max_ctas) {
   if (!t || !t->p2p_block) return RG_ERR_ARG;
+  cudaSetDevice(t->ctx->device);
   t->p2p_ctas = max_ctas;
   for (uint32_t r = 0; r < t->shard_parts; ++r)
     if (!t->peer_keys[r]) {
@@ -777,6 +818,7 @@ int rg_count_p2p_scatter_dev(rg_table* t, const char* dev_stream, uint64_t n_byt
 // spill list) is picked up by rg_count_end / the first reader (rg_table_finish).
 int rg_count_p2p_finish(rg_table* t) {
   if (!t || !t->p2p_block) return RG_ERR_ARG;
+  cudaSetDevice(t->ctx->device);
   // bucket slabs of my tiles, then (group, source) sub-slabs -> tiles, then the tile inserts
   int rc = prepare_buckets(t, t->p2p_max_keys);
   if (rc == 0) rc = rg_launch_partition_groups(t);
@@ -885,6 +927,7 @@ int rg_count_push_keys_dev(rg_table* t, const uint64_t* dev_keys, uint64_t n_key
 
 int rg_count_end(rg_table* t) {
   if (!t) return RG_ERR_ARG;
+  cudaSetDevice(t->ctx->device);
   t->unchecked = true;
   return rg_table_finish(t);
 }
@@ -895,6 +938,7 @@ int rg_count_end(rg_table* t) {
 // lose a key)
 int rg_table_reserve(rg_table* t, uint64_t extra_distinct) {
   if (!t) return RG_ERR_ARG;
+  cudaSetDevice(t->ctx->device);
   int rc = rg_table_finish(t);
   if (rc) return rc;
   uint64_t distinct = 0;

@@ -501,39 +501,79 @@ int64_t rg_jf_sort(rg_ctx* ctx, uint64_t* keys_host, uint32_t* counts_host, uint
   return rc ? rc : (int64_t)n;
 }
 
-int64_t rg_table_write_jhash(rg_table* t, const char* path, uint64_t min_count, uint64_t max_count, uint64_t size,
-                             uint32_t counter_len, const char* const* cmdline, int n_cmdline) {
-  if (!t || !path) return RG_ERR_ARG;
+// One .Jhash from the hash-prefix shards of a table (n == 1: a plain table). Every shard is dumped on its own
+// GPU; the pieces are gathered on the first shard's GPU (peer copies), which puts them in file order and
+// packs the records.
+int64_t rg_tables_write_jhash(rg_table* const* tabs, int n_tabs, const char* path, uint64_t min_count, uint64_t max_count,
+                              uint64_t size, uint32_t counter_len, const char* const* cmdline, int n_cmdline) {
+  if (!tabs || n_tabs < 1 || !tabs[0] || !path) return RG_ERR_ARG;
   if (counter_len == 0) counter_len = 4;
   if (counter_len > 8) {
     rg_set_error("jhash: counter_len must be 1..8");
     return RG_ERR_ARG;
   }
+  rg_table* t = tabs[0];
   rg_ctx* ctx = t->ctx;
   JfGeometry g;
   int rc = jf_geometry(size, t->k, g);
   if (rc) return rc;
-  rc = rg_table_finish(t);
-  if (rc) return rc;
-  // 1. the entries in range, on the device
-  uint64_t n_distinct = 0;
-  rc = rg_table_stats(t, &n_distinct, nullptr, nullptr);
-  if (rc) return rc;
-  const uint64_t cap = n_distinct ? n_distinct : 1;
+  // 1. the entries in range, on the first shard's device
+  std::vector<uint64_t> n_shard(n_tabs, 0);
+  uint64_t cap = 0;
+  for (int i = 0; i < n_tabs; ++i) {
+    if (!tabs[i] || tabs[i]->k != t->k || tabs[i]->canonical != t->canonical) {
+      rg_set_error("jhash: shards must share k and the canonical flag");
+      return RG_ERR_ARG;
+    }
+    RG_CUDA_OK(cudaSetDevice(tabs[i]->ctx->device));
+    rc = rg_table_finish(tabs[i]);
+    if (rc == 0) rc = rg_table_stats(tabs[i], &n_shard[i], nullptr, nullptr);
+    if (rc) return rc;
+    cap += n_shard[i];
+  }
+  if (cap == 0) cap = 1;
+  RG_CUDA_OK(cudaSetDevice(ctx->device));
   uint64_t* dk = nullptr;
   uint32_t* dc = nullptr;
   unsigned char* drec = nullptr;
   RG_CUDA_OK(cudaMalloc(&dk, cap * 8));
   RG_CUDA_OK(cudaMalloc(&dc, cap * 4));
   int64_t result = 0;
-  rc = rg_launch_dump(t, min_count ? min_count : 1, max_count ? max_count : ~0ull, dk, dc, cap, ctx->d_scratch);
   uint64_t n = 0;
-  if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { rg_set_error(cudaGetErrorString(e)); rc = RG_ERR_CUDA; }
-    n = ctx->h_scratch[0];
+  for (int i = 0; i < n_tabs && rc == 0; ++i) {
+    rg_ctx* ci = tabs[i]->ctx;
+    cudaSetDevice(ci->device);
+    uint64_t *sk = dk + n, *tk = nullptr;
+    uint32_t *sc = dc + n, *tc = nullptr;
+    if (i > 0) {       // dump on the shard's own device, then one peer copy
+      const uint64_t c = n_shard[i] ? n_shard[i] : 1;
+      if (cudaMalloc(&tk, c * 8) != cudaSuccess || cudaMalloc(&tc, c * 4) != cudaSuccess) {
+        rg_set_error("jhash: out of device memory");
+        rc = RG_ERR_CUDA;
+        cudaFree(tk);
+        break;
+      }
+      sk = tk;
+      sc = tc;
+    }
+    rc = rg_launch_dump(tabs[i], min_count ? min_count : 1, max_count ? max_count : ~0ull, sk, sc, n_shard[i], ci->d_scratch);
+    uint64_t got = 0;
+    if (rc == 0) {
+      cudaError_t e = cudaMemcpyAsync(ci->h_scratch, ci->d_scratch, 8, cudaMemcpyDeviceToHost, ci->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ci->stream);
+      if (e != cudaSuccess) { rg_set_error(cudaGetErrorString(e)); rc = RG_ERR_CUDA; }
+      got = ci->h_scratch[0];
+    }
+    if (rc == 0 && i > 0 && got) {
+      cudaError_t e = cudaMemcpyPeer(dk + n, ctx->device, tk, ci->device, got * 8);
+      if (e == cudaSuccess) e = cudaMemcpyPeer(dc + n, ctx->device, tc, ci->device, got * 4);
+      if (e != cudaSuccess) { rg_set_error(std::string("jhash: peer copy: ") + cudaGetErrorString(e)); rc = RG_ERR_CUDA; }
+    }
+    cudaFree(tk);
+    cudaFree(tc);
+    n += got;
   }
+  cudaSetDevice(ctx->device);
   // 2. file order, 3. file bytes
   if (rc == 0) rc = jf_sort_dev(ctx, g, dk, dc, n);
   const unsigned key_bytes = (g.c + 7) / 8, rec = key_bytes + counter_len;
@@ -579,6 +619,11 @@ int64_t rg_table_write_jhash(rg_table* t, const char* path, uint64_t min_count, 
   cudaFree(dc);
   cudaFree(drec);
   return rc ? rc : result;
+}
+
+int64_t rg_table_write_jhash(rg_table* t, const char* path, uint64_t min_count, uint64_t max_count, uint64_t size,
+                             uint32_t counter_len, const char* const* cmdline, int n_cmdline) {
+  return rg_tables_write_jhash(&t, 1, path, min_count, max_count, size, counter_len, cmdline, n_cmdline);
 }
 
 rg_table* rg_table_read_jhash(rg_ctx* ctx, const char* path, rg_jf_info* info) {

@@ -12,7 +12,10 @@
 //        prints `KMER<TAB>COUNT` for the k-mers present in exactly one input with count >= 5
 // Options RUFUS never passes are accepted where they are harmless and rejected otherwise.
 #include <algorithm>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 #include "rg_cli.hpp"
 
@@ -43,6 +46,143 @@ static FILE* open_out(const char* path) {
   if (!f) die(std::string("Error opening output file '") + path + "'");
   return f;
 }
+
+// ---------------------------------------------------------------------------- count on several GPUs
+// The devices `jellyfish count` uses: RG_DEVICES=0,1,... (or "all"), default every visible GPU.
+static std::vector<int> count_devices() {
+  const int n = rg_device_count();
+  if (n <= 0) die("jellyfish count: no CUDA device (librufus_gpu has no CPU fallback)");
+  std::vector<int> d;
+  const char* e = getenv("RG_DEVICES");
+  if (e && *e && strcmp(e, "all") != 0) {
+    for (const char* p = e; *p;) {
+      char* end = nullptr;
+      const long v = strtol(p, &end, 10);
+      if (end == p || v < 0 || v >= n) die(std::string("RG_DEVICES: bad device list '") + e + "'");
+      d.push_back((int)v);
+      p = *end == ',' ? end + 1 : end;
+      if (*end != ',' && *end != 0) die(std::string("RG_DEVICES: bad device list '") + e + "'");
+    }
+  } else {
+    for (int i = 0; i < n && i < 8; ++i) d.push_back(i);
+  }
+  if (d.empty()) d.push_back(0);
+  return d;
+}
+
+struct HostBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n, waiting = 0, phase = 0;
+  explicit HostBarrier(int n_) : n(n_) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const int ph = phase;
+    if (++waiting == n) {
+      waiting = 0;
+      ++phase;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return phase != ph; });
+    }
+  }
+};
+
+// One process, one context + one hash-prefix shard per GPU (RunJellyForRUFUS.sh:29 with every GPU of the box
+// behind it). The reader deals the sequence chunks round-robin; a ROUND = one chunk per GPU, counted in three
+// lock-step phases by one host thread per GPU: (1) make room + zero my slab cursors, (2) upload my chunk and
+// scatter its super-k-mer records straight into the owners' slabs over NVLink (peer stores, no collective),
+// (3) my slabs -> tiles -> inserts. The next round is parsed while this one is counted. One merged .Jhash in
+// (pos, key) order at the end.
+struct MultiCount {
+  std::vector<int> dev;
+  std::vector<rg_ctx*> ctx;
+  std::vector<rg_table*> tab;
+  std::vector<char*> stage;              // device staging of one chunk per GPU
+  size_t chunk;
+  std::vector<ByteBuf> bufs[2];          // two rounds of pinned chunks: one being filled, one being counted
+  int filling = 0, n_filled = 0;
+  std::thread round;
+  std::string err;
+
+  MultiCount(const std::vector<int>& devices, int k, int canonical, size_t chunk_bytes) : dev(devices), chunk(chunk_bytes) {
+    const int n = (int)dev.size();
+    ctx.resize(n);
+    tab.resize(n);
+    stage.resize(n);
+    const uint32_t groups = (uint32_t)std::max(8, 128 / n);
+    for (int i = 0; i < n; ++i) {
+      ctx[i] = rg_init(dev[i]);
+      if (!ctx[i]) die(rg_last_error());
+      tab[i] = rg_count_begin(ctx[i], k, canonical, 1ull << 22, RG_MODE_TILED);
+      if (!tab[i]) die(rg_last_error());
+      check(rg_table_set_shard(tab[i], (uint32_t)i, (uint32_t)n), "count");
+      check(rg_table_p2p_prepare(tab[i], groups, chunk + chunk / 4 + (1u << 20)), "count");
+      stage[i] = (char*)rg_dev_alloc(ctx[i], chunk + (16u << 20));
+      if (!stage[i]) die(rg_last_error());
+    }
+    check(rg_tables_p2p_attach(tab.data(), n), "count");
+    for (int r = 0; r < 2; ++r) {
+      bufs[r] = std::vector<ByteBuf>(n);
+      for (auto& b : bufs[r]) b.reserve(chunk + (8u << 20));
+    }
+  }
+  void run_round(int which, int n_chunks) {
+    const int n = (int)dev.size();
+    size_t total = 0;
+    for (int i = 0; i < n_chunks; ++i) total += bufs[which][i].size();
+    HostBarrier bar(n);
+    std::vector<std::thread> th;
+    std::mutex em;
+    auto fail = [&](const char* what) {
+      std::lock_guard<std::mutex> g(em);
+      if (err.empty()) err = std::string(what) + ": " + rg_last_error();
+    };
+    for (int i = 0; i < n; ++i)
+      th.emplace_back([&, i] {
+        ByteBuf& b = bufs[which][i];
+        const size_t bytes = i < n_chunks ? b.size() : 0;
+        // (1) room for my share of this round's k-mers, whatever their minimizers are; zero my cursors
+        if (rg_table_reserve(tab[i], total / n + total / (2 * n) + 1024) || rg_count_p2p_begin(tab[i]) || rg_sync(ctx[i]))
+          fail("count (reserve)");
+        bar.wait();
+        // (2) upload + scatter into every owner's slabs
+        if (bytes && rg_h2d(ctx[i], stage[i], b.data(), bytes)) fail("count (upload)");
+        if (rg_count_p2p_scatter_dev(tab[i], stage[i], bytes, 0, 0) || rg_sync(ctx[i])) fail("count (scatter)");
+        bar.wait();
+        // (3) my slabs -> tiles -> inserts; spills resolved
+        if (rg_count_p2p_finish(tab[i]) || rg_count_end(tab[i])) fail("count (insert)");
+        b.clear();
+      });
+    for (auto& t : th) t.join();
+  }
+  // the reader's flush: hand over one chunk; a full round starts counting in the background
+  void add_chunk(ByteBuf& b) {
+    bufs[filling][n_filled].swap(b);
+    b.clear();
+    if (++n_filled == (int)dev.size()) launch();
+  }
+  void launch() {
+    if (round.joinable()) round.join();
+    if (!err.empty()) die(err);
+    const int which = filling, cnt = n_filled;
+    round = std::thread([this, which, cnt] { run_round(which, cnt); });
+    filling ^= 1;
+    n_filled = 0;
+  }
+  void finish() {
+    if (n_filled) launch();
+    if (round.joinable()) round.join();
+    if (!err.empty()) die(err);
+  }
+  ~MultiCount() {
+    for (size_t i = 0; i < tab.size(); ++i) {
+      rg_table_free(tab[i]);
+      rg_dev_free(ctx[i], stage[i]);
+      rg_shutdown(ctx[i]);
+    }
+  }
+};
 
 // ---------------------------------------------------------------------------- count
 static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
@@ -77,7 +217,30 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   if (size == 0) die("Missing -s SIZE");
   if (inputs.empty()) die("Missing input file");
 
-  rg_ctx* ctx = rg_init(0);
+  const std::vector<int> devices = count_devices();
+  if (devices.size() > 1) {
+    const char* cm = getenv("RG_CHUNK_MB");
+    const size_t chunk = (size_t)(cm ? std::max(1, atoi(cm)) : 64) << 20;
+    MultiCount mc(devices, k, canonical, chunk);
+    ByteBuf fill;
+    fill.reserve(chunk + (8u << 20));
+    auto flush = [&](ByteBuf& b) {
+      mc.add_chunk(b);
+      b.reserve(chunk + (8u << 20));
+    };
+    for (const char* path : inputs) {
+      FILE* f = fopen(path, "rb");
+      if (!f) die(std::string("Failed to open input file '") + path + "'");
+      read_sequences(f, path, fill, chunk, flush);
+      fclose(f);
+    }
+    if (!fill.empty()) flush(fill);
+    mc.finish();
+    check(rg_tables_write_jhash(mc.tab.data(), (int)mc.tab.size(), out, lower, upper, size, out_counter_len,
+                                full_argv + 1, full_argc - 1), "count");
+    return 0;
+  }
+  rg_ctx* ctx = rg_init(devices[0]);
   if (!ctx) die(rg_last_error());
   // the table grows with the input (rg_table_reserve); -s only fixes the geometry written to the header
   rg_table* t = rg_count_begin(ctx, k, canonical, 1ull << 22, RG_MODE_TILED);

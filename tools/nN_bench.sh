@@ -14,4 +14,4 @@ except Exception as e:
 PY
 }
 run overlap
-RG_P2P_SERIAL=1 run serial --no-e2e
+[ -n "$SERIAL" ] && RG_P2P_SERIAL=1 run serial --no-e2e
