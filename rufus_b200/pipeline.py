@@ -99,7 +99,7 @@ class DevicePipeline:
         self.exchange = exchange if world > 1 else "none"
         import os
         self.serial = os.environ.get("RG_P2P_SERIAL", "0") == "1"
-        self.schedule = os.environ.get("RG_P2P_SCHEDULE", "batched")      # "batched" | "overlap"
+        self.schedule = os.environ.get("RG_P2P_SCHEDULE", "overlap")      # "batched" | "overlap"
         # Fast path: the whole pass is ENQUEUED (deferred status checks, histogram / subtraction count / kept
         # count left on the device, a set rebuilt in place, one fixed-capacity all-gather of the mutant k-mers)
         # and the host synchronises once, at the end. Falls back to the step-by-step path when a table reports

@@ -14,4 +14,4 @@ except Exception as e:
 PY
 }
 run overlap
-[ -n "$SERIAL" ] && RG_P2P_SERIAL=1 run serial --no-e2e
+[ -n "$BATCHED" ] && RG_P2P_SCHEDULE=batched run batched --no-e2e; true
