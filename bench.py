@@ -219,6 +219,212 @@ def workload_config(args, world):
             "l2": "inputs (450 MB reads + GB-scale tables per GPU) larger than L2; no flush needed"}
 
 
+# --------------------------------------------------------------------------- the large configs
+def run_big(args, rank, local_rank, world, dev):
+    """BASELINE configs[2..4], scaled (workload.BIG): inputs generated in HBM by the counter-based generator, the
+    same count -> histo -> subtract -> pull pass (the quad sweeps the min-count cutoff over the counted tables),
+    sliced parity against tests/golden/big_digests.json. One JSON line like the default config's."""
+    import ctypes as C
+    import torch
+    from rufus_b200 import api, pipeline, workload
+    if world > 1:
+        import torch.distributed as dist
+    cfg = workload.BIG[args.config]
+    k, ns = cfg["k"], len(cfg["samples"])
+    ctx = api.Context(local_rank)
+    ctx.use_stream(torch.cuda.current_stream().cuda_stream)
+    L = api.lib()
+    t0 = time.time()
+    streams, subj = [], None
+    for si in range(ns):
+        P = cfg["pairs"][si]
+        buf = torch.empty(2 * P * READ_LEN, dtype=torch.uint8, device=dev)            # both mates, one read stream
+        q = torch.empty(2 * P * READ_LEN, dtype=torch.uint8, device=dev)
+        sp = workload.big_spec(cfg, si, rank, world)
+        api._check(L.rg_synth_pairs_dev(ctx.h, C.byref(sp), api._ptr(buf[:P * READ_LEN]), api._ptr(q[:P * READ_LEN]),
+                                        api._ptr(buf[P * READ_LEN:]), api._ptr(q[P * READ_LEN:])), "rg_synth_pairs_dev")
+        streams.append(buf)
+        if si == 0:
+            subj = (buf[:P * READ_LEN], q[:P * READ_LEN], buf[P * READ_LEN:], q[P * READ_LEN:])
+        else:
+            del q
+    torch.cuda.synchronize()
+    log(f"rank {rank}: {args.config} inputs generated on the GPU in {time.time() - t0:.2f}s "
+        f"({sum(int(s.numel()) for s in streams) / 1e9:.2f} Gbases)")
+    bases_per_step = sum(int(s.numel()) for s in streams)
+    reads_max = max(cfg["pairs"]) * 2
+    est = int((1.05 * cfg["genome_unit"] + 0.27 * k * reads_max) * args.est_scale)
+    sweep = list(cfg["min_cov"])
+    pipe = pipeline.DevicePipeline(ctx, k, streams, subj, READ_LEN, est, max(sweep[0], 5), cfg["max_cov"], MINQ, THRESH,
+                                   lower=(2,) * ns, rank=rank, world=world, exchange=args.exchange,
+                                   groups_per_shard=args.p2p_groups, scatter_ctas=args.scatter_ctas, fast_cap=1 << 18)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        r = pipe.step()
+        out = {sweep[0]: (r["n_mutant"], r["n_kept"])}
+        for mc in sweep[1:]:                       # the quad's min-count sweep: cutoffs over the counted tables
+            r = pipe.rerun_tail(max(mc, 5))
+            out[mc] = (r["n_mutant"], r["n_kept"])
+        pipe.min_cov = max(sweep[0], 5)
+        return out
+
+    for i in range(args.warmup):
+        res = one_step()
+    geo = pipe.tables[0].geometry()
+    st0 = pipe.tables[0].stats()
+    log(f"rank {rank}: warm; (mutant k-mers, pulled pairs) per min-count {res}; subject table {st0}, geometry {geo}")
+    sampler = ClockSampler(local_rank)
+    ctx.profile_reset()
+    ctx.profile(True)
+    launches0 = ctx.launches
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        res = one_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    # ---- sliced parity (untimed): every sample's slice of the table + the slice of the HashList per cutoff
+    exp = workload.big_expected(args.config, world)
+    got = {"samples": [], "hashlist": {}}
+    cap = max(1 << 20, int(pipe.tables[0].stats()["distinct"]) // workload.SLICE_MOD * 2)
+    dk = torch.empty(cap, dtype=torch.int64, device=dev)
+    dc = torch.empty(cap, dtype=torch.int32, device=dev)
+
+    def gather(keys, counts):
+        if world == 1:
+            return keys, counts
+        parts = [None] * world
+        dist.all_gather_object(parts, (keys, counts))
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+    for t in pipe.tables:
+        n = L.rg_dump_slice_dev(t.h, 2, workload.SLICE_MOD, 0, api._ptr(dk), api._ptr(dc), cap, None)
+        if n < 0:
+            raise api._err("rg_dump_slice_dev")
+        kk, cc = gather(dk[:n].cpu().numpy().view(np.uint64), dc[:n].cpu().numpy().view(np.uint32))
+        got["samples"].append(workload.table_digest(kk, cc))
+    for mc in sweep:
+        r = pipe.rerun_tail(max(mc, 5))
+        pr = pipe.results()
+        kk, cc = gather(pr["keys"], pr["counts"])
+        m = workload.slice_hash(kk) % workload.SLICE_MOD == 0
+        got["hashlist"][str(mc)] = workload.table_digest(kk[m], cc[m])
+    if exp is None:
+        parity = dict(got, ok=None, note="no sliced digest committed for this config / GPU count")
+    else:
+        bad = [f"sample{i}" for i in range(ns) if got["samples"][i] != exp["samples"][i]] + \
+              [f"hashlist{mc}" for mc in got["hashlist"] if got["hashlist"][mc] != exp["hashlist"][mc]]
+        parity = {"ok": not bad, "mismatch": bad, "slice": f"slice_hash(key) % {workload.SLICE_MOD} == 0",
+                  "reference": workload.big_key(args.config, world), "slice_keys": [s["n"] for s in got["samples"]],
+                  "hashlist_slice": {mc: d["n"] for mc, d in got["hashlist"].items()}}
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_step = ms_total / args.steps
+    value = bases_per_step * world / (ms_step / 1e3) / 1e9
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, peak_src = float(mp["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    kern = {kk: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for kk, v in prof.items()}
+    names = [n for n in ("partition_kernel", "partition_p2p_kernel", "partition_groups_kernel", "tile_insert_kernel") if n in kern]
+    # per sample push: (sum over its kernels of total time) / pushes; algorithmic bytes B + 16 n (SURVEY 8d)
+    pushes = args.steps * ns
+    count_ms = sum(kern[n]["ms_avg"] * kern[n]["launches"] for n in names) / max(pushes, 1)
+    bases_per_push = bases_per_step / ns
+    alg_bytes = bases_per_push * (1.0 + 16.0 * (READ_LEN - k + 1) / READ_LEN)
+    achieved = alg_bytes / (count_ms / 1e3) / 1e9 if count_ms > 0 else 0.0
+    out = {"metric": METRIC.replace("k=25, 30x trio", cfg["title"]), "value": value, "unit": "Gbases/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": f"{args.config}: {cfg['title']}; per GPU {[2 * p for p in cfg['pairs']]} x {READ_LEN} bp reads "
+                                  f"per sample, genome {cfg['genome_unit']} bp x {world} (5 % repeat families), k={k}, "
+                                  f"min-count {sweep}, max {cfg['max_cov']}; inputs generated on the GPU (seed {cfg['seed']})",
+                      "k": k, "samples": ns, "genome_bp": cfg["genome_unit"] * world,
+                      "reads_per_sample": [2 * p * world for p in cfg["pairs"]],
+                      "partition": f"minimizer hash prefix x{world}" if world > 1 else "single GPU",
+                      "l2": "inputs and tables (GBs per GPU) larger than L2; no flush needed"},
+           "clocks": clocks, "gpu_launches": launches,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": peak_src, "kernel": "+".join(names),
+                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": count_ms,
+                        "note": "one 'launch' = the count of one sample on one GPU: B + 16*n bytes (SURVEY 8d)"},
+           "kernels_ms": kern, "result": {str(mc): {"n_mutant_kmers": v[0], "n_pulled_pairs_rank0": v[1]} for mc, v in res.items()},
+           "table": {"distinct_subject_shard": st0["distinct"], "geometry": geo}, "parity": parity}
+    if rank == 0 and not args.no_cpu_baseline:
+        # the reference's CPU path on 1/64 of rank 0's reads of every sample (generated on the host: same bytes)
+        sub = {}
+        for si in range(ns):
+            n = max(1000, cfg["pairs"][si] // 64)
+            sub[si] = api.synth_pairs_host(workload.big_spec(cfg, si, 0, world, 0, n))
+        wd = tempfile.mkdtemp(prefix="rg_cpu_")
+        try:
+            dt, b = cpu_reference_big(sub, k, max(sweep[0], 5), cfg["max_cov"], wd, os.cpu_count() or 1)
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+        if dt:
+            out["cpu_baseline"] = {"value": b / dt / 1e9, "unit": "Gbases/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                   "extrapolated": True,
+                                   "sample": f"first 1/64 of rank 0's pairs of every sample ({b / 1e6:.0f} Mbases), {dt:.1f}s wall, "
+                                             "jellyfish -s 256M; per-base rate, extrapolated linearly to the full config"}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    pipe.free()
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+    if rank == 0 and parity["ok"] is False:
+        log("SLICED PARITY MISMATCH:", parity)
+        sys.exit(3)
+
+
+def cpu_reference_big(sub, k, min_cov, max_cov, workdir, threads):
+    """the reference's commands on a sub-sample {sample index: (s1, q1, s2, q2)}, subject = index 0"""
+    from rufus_b200 import synth
+    refbin = os.path.join(ROOT, "oracle", "_ref")
+    jf = os.path.join(refbin, "jellyfish")
+    if not (os.path.exists(jf) and os.path.exists(os.path.join(refbin, "RUFUS.Filter"))):
+        return None, 0
+    bases, fq = 0, {}
+    for si, (s1, q1, s2, q2) in sub.items():
+        p1, p2 = os.path.join(workdir, f"s{si}.m1.fq"), os.path.join(workdir, f"s{si}.m2.fq")
+        open(p1, "wb").write(synth.fastq_bytes(s1, q1, prefix=f"s{si}_"))
+        open(p2, "wb").write(synth.fastq_bytes(s2, q2, prefix=f"s{si}_"))
+        fq[si] = (p1, p2)
+        bases += s1.size + s2.size
+    T = max(1, threads)
+    t0 = time.time()
+    for si in fq:
+        subprocess.run(f"cat {fq[si][0]} {fq[si][1]} | {jf} count --disk -m {k} -L 2 -s 256M -t {T} -o s{si}.Jhash -C /dev/stdin "
+                       f"&& {jf} histo -f -o s{si}.Jhash.histo s{si}.Jhash", shell=True, check=True, cwd=workdir,
+                       executable="/bin/bash")
+    subprocess.run(f"{jf} merge " + " ".join(f"s{si}.Jhash" for si in fq) + " > merge.out && "
+                   f"{jf} query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) s0.Jhash | "
+                   f"awk -v var={min_cov} ' $2 >= var ' | awk -v var={max_cov} ' $2 <= var ' > HashList",
+                   shell=True, check=True, cwd=workdir, executable="/bin/bash")
+    subprocess.run(f"{refbin}/RUFUS.Filter HashList {fq[0][0]} {fq[0][1]} out {k} {MINQ} {THRESH} {T} > /dev/null",
+                   shell=True, check=True, cwd=workdir, executable="/bin/bash")
+    return time.time() - t0, bases
+
+
 # --------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -237,6 +443,9 @@ def main():
                     help="CTAs of the (NVLink-bound) peer-to-peer scatter when it overlaps the previous sample's inserts")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: peer-to-peer partition into the owners' slabs, or extract + NCCL all-to-all")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2: BASELINE configs[1] (the default, the metric's config); c3/c4/c5: the large configs[2..4], "
+                         "scaled (rufus_b200/workload.py BIG), inputs generated on the GPU, sliced parity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -260,6 +469,8 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / warnings stay off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.config != "c2":
+        return run_big(args, rank, local_rank, world, dev)
     trio = make_data(args, rank, world)
     ctx = api.Context(local_rank)
     ctx.use_stream(torch.cuda.current_stream().cuda_stream)

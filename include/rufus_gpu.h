@@ -223,6 +223,27 @@ int64_t rg_tables_write_jhash(rg_table* const* tabs, int n_tabs, const char* pat
 /* load a .Jhash (ours or real Jellyfish's) into a device table; info (optional) gets the header values */
 rg_table* rg_table_read_jhash(rg_ctx* ctx, const char* path, rg_jf_info* info);
 
+/* the entries with count >= min_count whose key lies in the slice {key : h(key) % slice_mod == slice_rem} (h = a
+ * fixed 32-bit hash of the key, independent of the table geometry; slice_mod 0 = every key), into DEVICE arrays;
+ * returns their number (RG_ERR_SMALL / *needed when cap is too small). For sliced parity of tables too large to
+ * check whole: a CPU count restricted to the same slice must give exactly these pairs. */
+int64_t rg_dump_slice_dev(rg_table* t, uint64_t min_count, uint32_t slice_mod, uint32_t slice_rem, uint64_t* keys_dev,
+                          uint32_t* counts_dev, uint64_t cap, uint64_t* needed);
+
+/* ---- synthetic inputs ("synth-trio v2"): counter-based read generator ----------------
+ * Pure function of (seed, coordinates): the device and the host entry points write the SAME bytes, so the large
+ * benchmark configs are built in HBM while the CPU restatement reads identical inputs (sliced parity). Not part
+ * of the counting path. Pair i of a sample: 2 x read_len bases + qualities; buffers hold n_pairs * read_len bytes
+ * each, pairs first_pair .. first_pair + n_pairs - 1 (a rank's slice of the sample). */
+#define RG_SYNTH_TRIO 0 /* samples: 0 child/proband, 1 mother, 2 father, 3 sibling (quad) */
+#define RG_SYNTH_PAIR 1 /* samples: 0 tumor, 1 normal */
+typedef struct {
+  uint64_t seed, genome_len, first_pair, n_pairs;
+  uint32_t read_len, sample, kind, repeats; /* repeats != 0: 5 % of the genome in 100 repeat families, 2 % divergence */
+} rg_synth_spec;
+int rg_synth_pairs_dev(rg_ctx* ctx, const rg_synth_spec* spec, char* s1_dev, char* q1_dev, char* s2_dev, char* q2_dev);
+int rg_synth_pairs_host(const rg_synth_spec* spec, char* s1, char* q1, char* s2, char* q2);
+
 /* ---- S1: subtraction ----------------------------------------------------
  * modified `jellyfish merge` (src/modifiedJellyfish/jellyfish/merge_files.cc:86-154):
  * every key present (count >= mins[i]) in EXACTLY ONE table i with count >= floor.

@@ -50,8 +50,47 @@ def lib():
                                                          C.c_uint64, C.c_void_p]
         L.ro_filter_single.argtypes = [C.c_void_p] * 3 + [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
                                                           C.c_void_p]
+        L.ro_slice_hash.argtypes = [C.c_uint64]
+        L.ro_slice_hash.restype = C.c_uint32
+        L.ro_slice_new.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32]
+        L.ro_slice_new.restype = C.c_void_p
+        L.ro_slice_add.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+        L.ro_slice_finish.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(_Table)]
+        L.ro_slice_finish.restype = C.c_int
+        L.ro_slice_free.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
+
+
+class SliceCounter:
+    """k-mers of the slice {key : slice_hash(key) % mod == rem}, accumulated over chunks of fixed-length reads"""
+
+    def __init__(self, k: int, canonical: bool, mod: int, rem: int):
+        self.h = lib().ro_slice_new(k, int(canonical), mod, rem)
+        assert self.h
+
+    def add(self, reads: np.ndarray):
+        r = np.ascontiguousarray(reads, np.uint8)
+        lib().ro_slice_add(self.h, _p(r), r.shape[0], r.shape[1])
+
+    def finish(self, lower: int = 1):
+        t = _Table()
+        assert lib().ro_slice_finish(self.h, lower, C.byref(t)) == 0
+        keys = np.ctypeslib.as_array(t.keys, (t.n,)).copy() if t.n else np.zeros(0, np.uint64)
+        counts = np.ctypeslib.as_array(t.counts, (t.n,)).copy() if t.n else np.zeros(0, np.uint32)
+        lib().ro_table_free(C.byref(t))
+        lib().ro_slice_free(self.h)
+        self.h = None
+        return keys, counts
+
+
+def slice_hash(keys: np.ndarray) -> np.ndarray:
+    """ro_slice_hash vectorised (the CUDA path's rg_hash32b: a fixed function of the key)"""
+    k = np.asarray(keys, np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    h = ((k & m32) * np.uint64(0xC2B2AE35) + (k >> np.uint64(32)) * np.uint64(0x27D4EB2F)) & m32
+    h ^= h >> np.uint64(15)
+    return ((h * np.uint64(0x2C1B3C6D)) & m32).astype(np.uint32)
 
 
 def _p(a):

@@ -205,3 +205,110 @@ void ro_filter_single(const char* s, const char* q, const uint64_t* o, uint64_t 
   for (uint64_t r = 0; r < n_reads; r++)
     hits[r] = ro_filter_hits(s + o[r], q + o[r], (int)(o[r + 1] - o[r]), k, minq, 0, set_sorted, n_set);
 }
+
+
+/* ---------------------------------------------------------------------------
+ * Sliced counting for inputs too large to count whole on the CPU (SURVEY §8d "parity at full scale via
+ * hash-prefix slices"): the same k-mer extraction as ro_count (mer_iterator.hpp:59-89), but only the keys with
+ * slice_hash(key) % mod == rem are kept, accumulated over any number of ro_slice_add calls in an
+ * open-addressed map. The slice hash is a fixed function of the key (independent of any table geometry), so
+ * the CUDA path's dump restricted to the same predicate must hold exactly these (key, count) pairs.
+ * --------------------------------------------------------------------------- */
+struct ro_slice {
+  int k, canonical;
+  uint32_t mod, rem;
+  uint64_t* keys;
+  uint64_t* counts;
+  uint64_t cap, n;       /* cap: power of two */
+};
+
+uint32_t ro_slice_hash(uint64_t key) {
+  uint32_t h = (uint32_t)key * 0xC2B2AE35u + (uint32_t)(key >> 32) * 0x27D4EB2Fu;
+  h ^= h >> 15;
+  return h * 0x2C1B3C6Du;
+}
+
+static void slice_put(ro_slice* s, uint64_t key, uint64_t add) {
+  uint64_t i = (key * 0x9E3779B97F4A7C15ull) >> 20 & (s->cap - 1);
+  for (;;) {
+    if (s->counts[i] == 0) { s->keys[i] = key; s->counts[i] = add; s->n++; return; }
+    if (s->keys[i] == key) { s->counts[i] += add; return; }
+    i = (i + 1) & (s->cap - 1);
+  }
+}
+
+static void slice_grow(ro_slice* s) {
+  uint64_t ocap = s->cap, *ok = s->keys, *oc = s->counts;
+  s->cap = ocap * 2;
+  s->keys = (uint64_t*)calloc(s->cap, sizeof(uint64_t));
+  s->counts = (uint64_t*)calloc(s->cap, sizeof(uint64_t));
+  s->n = 0;
+  for (uint64_t i = 0; i < ocap; i++) if (oc[i]) slice_put(s, ok[i], oc[i]);
+  free(ok); free(oc);
+}
+
+ro_slice* ro_slice_new(int k, int canonical, uint32_t mod, uint32_t rem) {
+  if (k < 1 || k > 32 || mod == 0 || rem >= mod) return NULL;
+  ro_slice* s = (ro_slice*)calloc(1, sizeof(ro_slice));
+  s->k = k; s->canonical = canonical; s->mod = mod; s->rem = rem;
+  s->cap = 1u << 16;
+  s->keys = (uint64_t*)calloc(s->cap, sizeof(uint64_t));
+  s->counts = (uint64_t*)calloc(s->cap, sizeof(uint64_t));
+  return s;
+}
+
+/* n_reads reads of read_len bytes each, back to back */
+void ro_slice_add(ro_slice* s, const char* seq, uint64_t n_reads, uint32_t read_len) {
+  const int k = s->k;
+  const uint64_t mask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+  const int hs = 2 * (k - 1);
+  for (uint64_t r = 0; r < n_reads; r++) {
+    uint64_t m = 0, rc = 0; int filled = 0;
+    const char* p = seq + r * (uint64_t)read_len;
+    for (uint32_t j = 0; j < read_len; j++) {
+      int c = jf_code((unsigned char)p[j]);
+      if (c < 0) { filled = 0; continue; }
+      m = ((m << 2) | (uint64_t)c) & mask;
+      rc = (rc >> 2) | ((uint64_t)(3 - c) << hs);
+      if (filled < k) filled++;
+      if (filled >= k) {
+        const uint64_t key = (!s->canonical || m < rc) ? m : rc;
+        if (ro_slice_hash(key) % s->mod == s->rem) {
+          if (s->n * 2 >= s->cap) slice_grow(s);
+          slice_put(s, key, 1);
+        }
+      }
+    }
+  }
+}
+
+static int cmp_u64(const void* a, const void* b) {
+  const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return x < y ? -1 : x > y;
+}
+
+/* entries with count >= lower, ascending key, counts saturated at 2^32-1 */
+int ro_slice_finish(ro_slice* s, uint64_t lower, ro_table* out) {
+  uint64_t d = 0;
+  for (uint64_t i = 0; i < s->cap; i++) if (s->counts[i] >= lower && s->counts[i]) d++;
+  uint64_t* pairs = (uint64_t*)malloc(sizeof(uint64_t) * 2 * (d ? d : 1));
+  if (!pairs) return -2;
+  uint64_t q = 0;
+  for (uint64_t i = 0; i < s->cap; i++)
+    if (s->counts[i] >= lower && s->counts[i]) { pairs[2 * q] = s->keys[i]; pairs[2 * q + 1] = s->counts[i]; q++; }
+  qsort(pairs, d, 2 * sizeof(uint64_t), cmp_u64);
+  out->keys = (uint64_t*)malloc(sizeof(uint64_t) * (d ? d : 1));
+  out->counts = (uint32_t*)malloc(sizeof(uint32_t) * (d ? d : 1));
+  out->n = d;
+  for (uint64_t i = 0; i < d; i++) {
+    out->keys[i] = pairs[2 * i];
+    out->counts[i] = pairs[2 * i + 1] > 0xffffffffull ? 0xffffffffu : (uint32_t)pairs[2 * i + 1];
+  }
+  free(pairs);
+  return 0;
+}
+
+void ro_slice_free(ro_slice* s) {
+  if (!s) return;
+  free(s->keys); free(s->counts); free(s);
+}

@@ -73,6 +73,16 @@ void ro_filter_pairs(const char* s1, const char* q1, const uint64_t* o1,
 void ro_filter_single(const char* s, const char* q, const uint64_t* o, uint64_t n_reads,
                       int k, int minq, const uint64_t* set_sorted, uint64_t n_set, int32_t* hits);
 
+/* Sliced counting for inputs too large to count whole on the CPU: the k-mer extraction of ro_count,
+ * keeping only the keys with ro_slice_hash(key) % mod == rem, accumulated over any number of ro_slice_add calls
+ * (fixed-length reads, back to back). ro_slice_finish: count >= lower, ascending key. */
+typedef struct ro_slice ro_slice;
+uint32_t ro_slice_hash(uint64_t key);
+ro_slice* ro_slice_new(int k, int canonical, uint32_t mod, uint32_t rem);
+void ro_slice_add(ro_slice* s, const char* seq, uint64_t n_reads, uint32_t read_len);
+int ro_slice_finish(ro_slice* s, uint64_t lower, ro_table* out);
+void ro_slice_free(ro_slice* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,9 @@ def lib():
         "rg_extract_partition_dev": (i32, [vp, vp, u64, u32, vp, vp]),
         "rg_key_shard": (u32, [u64, i32, i32, u32, u32]),
         "rg_device_count": (i32, []),
+        "rg_dump_slice_dev": (i64, [vp, u64, u32, u32, vp, vp, u64, vp]),
+        "rg_synth_pairs_dev": (i32, [vp, vp, vp, vp, vp, vp]),
+        "rg_synth_pairs_host": (i32, [vp, vp, vp, vp, vp]),
         "rg_tables_p2p_attach": (i32, [vp, i32]),
         "rg_tables_write_jhash": (i64, [vp, i32, C.c_char_p, u64, u64, u64, u32, vp, i32]),
         "rg_defer_checks": (i32, [vp, i32]),
@@ -237,6 +240,23 @@ class Context:
         if self.h:
             lib().rg_shutdown(self.h)
             self.h = None
+
+
+class SynthSpec(C.Structure):
+    """rg_synth_spec (include/rufus_gpu.h): the counter-based synthetic read generator's coordinates"""
+    _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint64), ("first_pair", C.c_uint64), ("n_pairs", C.c_uint64),
+                ("read_len", C.c_uint32), ("sample", C.c_uint32), ("kind", C.c_uint32), ("repeats", C.c_uint32)]
+
+
+SYNTH_TRIO, SYNTH_PAIR = 0, 1
+
+
+def synth_pairs_host(spec: SynthSpec):
+    """(seq1, qual1, seq2, qual2) uint8 [n_pairs, read_len], generated on the CPU (same bytes as the device)"""
+    shape = (int(spec.n_pairs), int(spec.read_len))
+    out = [np.empty(shape, np.uint8) for _ in range(4)]
+    _check(lib().rg_synth_pairs_host(C.byref(spec), *[_ptr(a) for a in out]), "rg_synth_pairs_host")
+    return tuple(out)
 
 
 class KmerTable:

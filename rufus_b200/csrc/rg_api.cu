@@ -1152,6 +1152,27 @@ int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* k
   return rc;
 }
 
+// the entries with count >= min_count whose key lies in the slice {key : rg_hash32b(key) % slice_mod == slice_rem}
+// (slice_mod 0: every key), into DEVICE arrays; *needed (host) = their number. A slice is a fixed function of the
+// key, so shards / tables of any geometry can be compared slice by slice with a CPU count of the same slice.
+int64_t rg_dump_slice_dev(rg_table* t, uint64_t min_count, uint32_t slice_mod, uint32_t slice_rem, uint64_t* keys_dev,
+                          uint32_t* counts_dev, uint64_t cap, uint64_t* needed) {
+  if (!t || (slice_mod && slice_rem >= slice_mod)) return RG_ERR_ARG;
+  rg_ctx* ctx = t->ctx;
+  int64_t rc = rg_table_finish(t);
+  if (rc == 0)
+    rc = rg_launch_dump(t, min_count ? min_count : 1, ~0ull, keys_dev, counts_dev, cap, ctx->d_scratch, slice_mod, slice_rem);
+  uint64_t n = 0;
+  if (rc == 0) rc = read_scalars(ctx, ctx->d_scratch, 1, &n);
+  if (rc) return rc;
+  if (needed) *needed = n;
+  if (n > cap) {
+    rg_set_error("rg_dump_slice_dev: output buffer too small");
+    return RG_ERR_SMALL;
+  }
+  return (int64_t)n;
+}
+
 rg_table* rg_table_from_pairs(rg_ctx* ctx, int k, int canonical, const uint64_t* keys_host,
                               const uint32_t* counts_host, uint64_t n) {
   rg_table* t = rg_count_begin(ctx, k, canonical, n ? n : 1, RG_MODE_DIRECT);

@@ -402,7 +402,7 @@ int rg_launch_extract_partition(rg_ctx* ctx, const ExtractParams& ep, RgGeo geo,
 int rg_launch_histo(rg_table* t, uint64_t min_count, uint64_t base, uint64_t nb, uint64_t* d_out);
 int rg_launch_stats(rg_table* t, uint64_t* d_out2);
 int rg_launch_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* d_keys, uint32_t* d_counts,
-                   uint64_t cap, uint64_t* d_cursor);
+                   uint64_t cap, uint64_t* d_cursor, uint32_t slice_mod = 0, uint32_t slice_rem = 0);
 int rg_launch_query(rg_table* t, const uint64_t* d_keys, uint64_t n, uint64_t min_count, uint32_t* d_out);
 struct OtherTables {
   TableView tv[16];

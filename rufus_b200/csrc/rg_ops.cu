@@ -108,28 +108,34 @@ __device__ __forceinline__ void emit_compact(bool sel, uint64_t key, uint32_t cn
 
 __global__ void __launch_bounds__(256)
 dump_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n_slots, uint64_t lo,
-            uint64_t hi, uint64_t* out_keys, uint32_t* out_counts, uint64_t cap, unsigned long long* cursor) {
+            uint64_t hi, uint32_t slice_mod, uint32_t slice_rem, uint64_t* out_keys, uint32_t* out_counts, uint64_t cap,
+            unsigned long long* cursor) {
   const uint64_t n_round = (n_slots + 31) & ~31ull;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round;
        i += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t c = 0;
     uint64_t key = 0;
     if (i < n_slots) c = __ldg(counts + i);
-    const bool sel = c != 0 && c >= lo && c <= hi;
-    if (sel) key = __ldg(keys + i);
+    bool sel = c != 0 && c >= lo && c <= hi;
+    if (sel) {
+      key = __ldg(keys + i);
+      // a slice of the key space (a fixed function of the key, whatever the table geometry): sliced parity of
+      // tables too large to check whole
+      if (slice_mod) sel = rg_hash32b(key) % slice_mod == slice_rem;
+    }
     emit_compact(sel, key, c, out_keys, out_counts, cap, cursor);
   }
 }
 
 int rg_launch_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* d_keys, uint32_t* d_counts,
-                   uint64_t cap, uint64_t* d_cursor) {
+                   uint64_t cap, uint64_t* d_cursor, uint32_t slice_mod, uint32_t slice_rem) {
   rg_ctx* ctx = t->ctx;
   const uint64_t n_slots = rg_table_slots(t);
   RG_CUDA_OK(cudaMemsetAsync(d_cursor, 0, sizeof(uint64_t), ctx->stream));
   {
     rg_launch_scope _ls(ctx, "dump_kernel");
-    dump_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(t->keys, t->counts, n_slots, min_count, max_count, d_keys,
-                                                          d_counts, cap,
+    dump_kernel<<<rg_grid(ctx, 8), 256, 0, ctx->stream>>>(t->keys, t->counts, n_slots, min_count, max_count, slice_mod,
+                                                          slice_rem, d_keys, d_counts, cap,
                                                           reinterpret_cast<unsigned long long*>(d_cursor));
   }
   RG_CUDA_OK(cudaGetLastError());

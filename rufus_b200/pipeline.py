@@ -286,6 +286,15 @@ class DevicePipeline:
                           "histo": self.red_host[:10002].numpy().astype(np.uint64)})
         return True
 
+    def rerun_tail(self, min_cov: int) -> dict:
+        """histo -> subtract -> set -> read pull again over the counted tables with another MutantMinCov (the
+        min-count sweep of BASELINE configs[4]: CheckJellyHashList.sh:12 re-cut at another cutoff)"""
+        self.min_cov = min_cov
+        self.last = {}
+        if self.fast and self._fast_tail():
+            return self.last
+        return self._slow_tail()
+
     def _slow_tail(self) -> dict:
         torch = self.torch
         L = api.lib()

@@ -81,3 +81,66 @@ def check(world: int, histo, keys, counts, names, **kw) -> dict:
         return dict(got, ok=None, note="no reference digest committed for this workload")
     bad = [f for f in got if got[f] != exp[f]]
     return dict(got, ok=not bad, mismatch=bad, reference=digest_key(world, **kw))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The large configs (BASELINE.json configs[2..4]), scaled to what the GPU-minute budget of a
+# build round allows: per-GPU sizes are fixed and the genome grows with the GPU count (true coverage at every N).
+# Inputs come from the counter-based generator (rg_synth_pairs_dev / rg_synth_pairs_host: same bytes on the GPU
+# and on the CPU, include/rufus_gpu.h), 5 % of the genome in repeat families. Full-size CPU counting is out of
+# reach, so parity is SLICED: the keys with slice_hash(key) % SLICE_MOD == 0 (a fixed function of the key) of
+# every sample's table, and the HashList restricted to that slice, against tests/golden/big_digests.json, which
+# tests/golden/make_big_digests.py computes with the CPU restatement on the identical reads.
+# ---------------------------------------------------------------------------------------------------------
+SLICE_MOD = 64
+BIG = {
+    # name: kind, samples (generator sample ids, subject first), pairs per GPU per sample, genome per GPU, k, seed, cutoffs
+    "c3": {"title": "30x WGS trio, k=25 (BASELINE configs[2] scaled)", "kind": 0, "samples": (0, 1, 2),
+           "pairs": (4_000_000, 4_000_000, 4_000_000), "genome_unit": 40_000_000, "k": 25, "seed": 1001,
+           "min_cov": (5,), "max_cov": 150},
+    "c4": {"title": "tumor 60x vs normal 30x, k=25 (BASELINE configs[3] scaled)", "kind": 1, "samples": (0, 1),
+           "pairs": (6_000_000, 3_000_000), "genome_unit": 30_000_000, "k": 25, "seed": 2001,
+           "min_cov": (5,), "max_cov": 300},
+    "c5": {"title": "proband + 3 controls, 30x each, k=31, min-count sweep (BASELINE configs[4] scaled)", "kind": 0,
+           "samples": (0, 1, 2, 3), "pairs": (3_000_000,) * 4, "genome_unit": 30_000_000, "k": 31, "seed": 3001,
+           "min_cov": (3, 5, 8, 12, 20), "max_cov": 150},
+}
+BIG_DIGESTS = os.path.join(os.path.dirname(DIGESTS), "big_digests.json")
+
+
+def big_spec(cfg: dict, sample_index: int, rank: int, world: int, first: int = 0, n: int | None = None):
+    """generator coordinates of pairs [first, first + n) of rank `rank`'s slice of a sample"""
+    from . import api
+    pairs = cfg["pairs"][sample_index]
+    n = pairs - first if n is None else n
+    return api.SynthSpec(seed=cfg["seed"], genome_len=cfg["genome_unit"] * world, first_pair=rank * pairs + first,
+                         n_pairs=n, read_len=READ_LEN, sample=cfg["samples"][sample_index], kind=cfg["kind"], repeats=1)
+
+
+def big_key(name: str, world: int) -> str:
+    c = BIG[name]
+    return f"{name}_seed{c['seed']}_g{c['genome_unit']}x{world}_p{'-'.join(str(p) for p in c['pairs'])}x{world}_k{c['k']}_slice{SLICE_MOD}"
+
+
+def slice_hash(keys) -> np.ndarray:
+    """the library's rg_hash32b, vectorised: a fixed 32-bit function of the key"""
+    k = np.asarray(keys, np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    h = ((k & m32) * np.uint64(0xC2B2AE35) + (k >> np.uint64(32)) * np.uint64(0x27D4EB2F)) & m32
+    h ^= h >> np.uint64(15)
+    return ((h * np.uint64(0x2C1B3C6D)) & m32).astype(np.uint32)
+
+
+def table_digest(keys, counts) -> dict:
+    """digest of a (key, count) set: order-free (sorted by key)"""
+    keys = np.asarray(keys, np.uint64)
+    counts = np.asarray(counts, np.uint32)
+    o = np.argsort(keys, kind="stable")
+    return {"n": int(keys.size), "md5": hashlib.md5(keys[o].tobytes() + counts[o].tobytes()).hexdigest()}
+
+
+def big_expected(name: str, world: int):
+    try:
+        return json.load(open(BIG_DIGESTS)).get(big_key(name, world))
+    except OSError:
+        return None

@@ -370,3 +370,36 @@ def test_bench_workload_matches_reference_digests(ctx):
     pipe.free()
     ctx.use_stream(None)
     assert par["ok"], par
+
+
+def test_synthetic_generator_device_equals_host(ctx):
+    """the counter-based read generator (synth-trio v2) writes the same bytes on the GPU and on the CPU, for every
+    sample kind, with and without repeat families, and for a slice that does not start at pair 0"""
+    import ctypes as C
+    import torch
+    L = api.lib()
+    dev = torch.device("cuda", 0)
+    for kind, sample, repeats, first in ((api.SYNTH_TRIO, 0, 1, 0), (api.SYNTH_TRIO, 3, 0, 12345), (api.SYNTH_PAIR, 0, 1, 777),
+                                         (api.SYNTH_PAIR, 1, 1, 0)):
+        sp = api.SynthSpec(seed=99, genome_len=300_000, first_pair=first, n_pairs=3000, read_len=150, sample=sample,
+                           kind=kind, repeats=repeats)
+        host = api.synth_pairs_host(sp)
+        bufs = [torch.empty(3000 * 150, dtype=torch.uint8, device=dev) for _ in range(4)]
+        api._check(L.rg_synth_pairs_dev(ctx.h, C.byref(sp), *[api._ptr(b) for b in bufs]), "rg_synth_pairs_dev")
+        ctx.sync()
+        for h, d in zip(host, bufs):
+            assert np.array_equal(h.reshape(-1), d.cpu().numpy())
+    # and the sliced dump is the slice of the full dump
+    s1, _, s2, _ = host
+    reads = np.concatenate([s1, s2])
+    offs = np.arange(reads.shape[0] + 1, dtype=np.uint64) * 150
+    t = api.KmerTable.count(ctx, reads, offs, 25, True)
+    keys, counts = t.dump(min_count=2)
+    dk = torch.empty(keys.size + 1, dtype=torch.int64, device=dev)
+    dc = torch.empty(keys.size + 1, dtype=torch.int32, device=dev)
+    n = L.rg_dump_slice_dev(t.h, 2, 16, 5, api._ptr(dk), api._ptr(dc), keys.size + 1, None)
+    sk, sc2 = dk[:n].cpu().numpy().view(np.uint64), dc[:n].cpu().numpy().view(np.uint32)
+    o = np.argsort(sk)
+    m = oracle.slice_hash(keys) % 16 == 5
+    assert n > 0 and np.array_equal(sk[o], keys[m]) and np.array_equal(sc2[o], counts[m])
+    t.free()

@@ -292,3 +292,25 @@ def test_jellyfish_known_answers(tmp_path):
     assert hashlib.md5(_histo_text(c, 2, 3)).hexdigest() == "94625cd2d59e278f08421a673eb0926a"    # ..._m15_s2M_L2_U3.histo
     c = count(["seq1m_0.fa", "seq1m_1.fa", "seq1m_2.fa", "seq10m.fa", "seq1m_3.fa", "seq1m_4.fa"])
     assert hashlib.md5(_histo_text(c)).hexdigest() == "d93b7678037814c256d1d9120a0e6422"          # multi_file_m15_s2M.histo
+
+
+def test_slice_counter_is_the_slice_of_the_full_count():
+    """ro_slice_* (sliced parity of the large configs) = ro_count restricted to slice_hash(key) % mod == rem, and the
+    host side of the synthetic generator is deterministic and sample-specific"""
+    from rufus_b200 import api
+    sp = api.SynthSpec(seed=7, genome_len=200_000, first_pair=0, n_pairs=4000, read_len=150, sample=0, kind=0, repeats=1)
+    s1, q1, s2, q2 = api.synth_pairs_host(sp)
+    again = api.synth_pairs_host(sp)
+    assert all(np.array_equal(a, b) for a, b in zip((s1, q1, s2, q2), again))
+    sp.sample = 1
+    assert not np.array_equal(api.synth_pairs_host(sp)[0], s1)
+    assert set(np.unique(s1).tolist()) <= set(b"ACGTN") and set(np.unique(q1).tolist()) <= set(b"J,#")
+    reads = np.concatenate([s1, s2])
+    offs = np.arange(reads.shape[0] + 1, dtype=np.uint64) * 150
+    keys, counts = oracle.count(reads.reshape(-1), offs, 25, True, 2)
+    sc = oracle.SliceCounter(25, True, 16, 3)
+    sc.add(reads[:3000])
+    sc.add(reads[3000:])
+    sk, scn = sc.finish(2)
+    m = oracle.slice_hash(keys) % 16 == 3
+    assert sk.size > 100 and np.array_equal(keys[m], sk) and np.array_equal(counts[m], scn)
