@@ -178,6 +178,74 @@ def cpu_reference_pass(trio, n_pairs, workdir, threads):
     return time.time() - t0, bases, "port", {"hashlist": int(hk.size), "pulled": int(keep.sum()), "cores": 1}
 
 
+def cli_stage_commands(bindir_jf, bindir_tools, fq, threads, size):
+    """the stage commands of runRufus.sh for a trio, as (stage, shell command) pairs (RunJellyForRUFUS.sh:29,37;
+    runRufus.sh:925-926 + CheckJellyHashList.sh:12; runRufus.sh:981), with the executables of the given directories"""
+    jf = os.path.join(bindir_jf, "jellyfish")
+    cmds = []
+    for s in ("Child", "Mother", "Father"):
+        cmds.append((f"count_{s}", f"cat {fq[s][0]} {fq[s][1]} | {jf} count --disk -m {K} -L 2 -s {size} -t {threads} -o {s}.Jhash -C /dev/stdin"))
+        cmds.append((f"histo_{s}", f"{jf} histo -f -o {s}.Jhash.histo {s}.Jhash"))
+    cmds.append(("merge", f"{jf} merge Child.Jhash Mother.Jhash Father.Jhash > merge.out"))
+    cmds.append(("query", f"{jf} query -s <(awk '{{print \">\"$1\"\\n\"$1}}' merge.out) Child.Jhash | "
+                          f"awk -v var={MIN_COV} ' $2 >= var ' | awk -v var={MAX_COV} ' $2 <= var ' > HashList"))
+    cmds.append(("filter", f"{os.path.join(bindir_tools, 'RUFUS.Filter')} HashList {fq['Child'][0]} {fq['Child'][1]} out {K} {MINQ} {THRESH} "
+                           f"{threads} > /dev/null"))
+    return cmds
+
+
+def cli_leg(trio):
+    """What a user of the pipeline runs: the stage COMMANDS on FASTQ files, with our drop-in executables (tools/bin)
+    and with the reference's (oracle/_ref), same argv, full workload. Wall seconds per stage, and the two outputs
+    compared (sorted HashList, sorted pulled mate-1 names)."""
+    import hashlib
+    from rufus_b200 import synth
+    refbin = os.path.join(ROOT, "oracle", "_ref")
+    ours = os.path.join(ROOT, "tools", "bin")
+    threads = os.cpu_count() or 1
+    out = {}
+    base = tempfile.mkdtemp(prefix="rg_cli_")
+    try:
+        fq = {}
+        for s in synth.SAMPLES:                       # untimed: the FASTQ files both sets of commands read
+            s1, q1, s2, q2 = trio[s]
+            p1, p2 = os.path.join(base, f"{s}.m1.fq"), os.path.join(base, f"{s}.m2.fq")
+            open(p1, "wb").write(synth.fastq_bytes(s1, q1, prefix=s[0]))
+            open(p2, "wb").write(synth.fastq_bytes(s2, q2, prefix=s[0]))
+            fq[s] = (p1, p2)
+        for name, d_jf, d_tools, size in (("rufus_b200", ours, ours, "8G"), ("reference", refbin, refbin, "256M")):
+            if not os.path.exists(os.path.join(d_jf, "jellyfish")):
+                out[name] = {"unavailable": f"{d_jf}/jellyfish not built"}
+                continue
+            wd = os.path.join(base, name)
+            os.makedirs(wd)
+            stages, t_all = {}, time.time()
+            for stage, cmd in cli_stage_commands(d_jf, d_tools, fq, threads, size):
+                t0 = time.time()
+                subprocess.run(cmd, shell=True, check=True, cwd=wd, executable="/bin/bash")
+                key = stage.split("_")[0]
+                stages[key] = round(stages.get(key, 0.0) + time.time() - t0, 3)
+            hl = sorted(open(os.path.join(wd, "HashList")).read().splitlines())
+            names = sorted(open(os.path.join(wd, "out.Mutations.Mate1.fastq")).read().splitlines()[0::4])
+            out[name] = {"seconds": round(time.time() - t_all, 3), "stages_s": stages, "threads": threads, "jellyfish_s": size,
+                         "hashlist_md5": hashlib.md5(("\n".join(hl) + "\n").encode()).hexdigest(), "hashlist_lines": len(hl),
+                         "pulled_md5": hashlib.md5(("\n".join(names) + "\n").encode()).hexdigest(), "pulled_pairs": len(names)}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+    a, b = out.get("rufus_b200", {}), out.get("reference", {})
+    if "seconds" in a and "seconds" in b:
+        out["speedup"] = round(b["seconds"] / a["seconds"], 2)
+        out["identical_outputs"] = a["hashlist_md5"] == b["hashlist_md5"] and a["pulled_md5"] == b["pulled_md5"]
+    bases = sum(trio[s][0].size + trio[s][2].size for s in synth.SAMPLES)
+    for side in (a, b):
+        if "seconds" in side:
+            side["gbases_per_s"] = round(bases / side["seconds"] / 1e9, 4)
+    out["note"] = ("wall clock of the stage commands (count x3, histo x3, merge, query, RUFUS.Filter) on FASTQ files, process start-up, "
+                   "FASTQ parsing and .Jhash I/O included; -s 8G for the drop-in (its table grows with the input; -s only sets the "
+                   "header geometry) and a right-sized -s 256M for the reference (SURVEY 8c: results do not depend on -s)")
+    return out
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -446,8 +514,12 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2: BASELINE configs[1] (the default, the metric's config); c3/c4/c5: the large configs[2..4], "
                          "scaled (rufus_b200/workload.py BIG), inputs generated on the GPU, sliced parity")
+    ap.add_argument("--filter-exchange", default="set", choices=["set", "a2a"],
+                    help="N>1 read pull: all-gather the mutant set (layout 1, default) or keep it sharded and exchange the reads (layout 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cli", action="store_true",
+                    help="N=1: also time the stage COMMANDS (tools/bin/* vs oracle/_ref/*) on FASTQ files of the full workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -488,7 +560,8 @@ def main():
     est = int((1.03 * args.genome + 6.2 * 2 * args.pairs) * args.est_scale)
     pipe = pipeline.DevicePipeline(ctx, K, streams, subj, READ_LEN, est, MIN_COV, MAX_COV, MINQ, THRESH,
                                    mode=mode, rank=rank, world=world, exchange=args.exchange,
-                                   groups_per_shard=args.p2p_groups, scatter_ctas=args.scatter_ctas)
+                                   groups_per_shard=args.p2p_groups, scatter_ctas=args.scatter_ctas,
+                                   filter_exchange=args.filter_exchange)
 
     def barrier():
         if world > 1:
@@ -650,11 +723,16 @@ def main():
                                "sample": f"first {args.ref_pairs} pairs/sample ({b / 1e6:.0f} Mbases) of the same "
                                          f"workload, {dt:.1f}s wall, jellyfish -s 256M; hashlist {info['hashlist']}, "
                                          f"pulled {info['pulled']}"}
+    if rank == 0 and world == 1 and args.cli:
+        ctx.close()
+        ctx = None
+        out["cli"] = cli_leg(trio)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     # a run whose RESULT differs from the reference's is not a measurement: fail it
     if rank == 0 and (parity["ok"] is False or out.get("e2e", {}).get("parity_ok") is False):
         log("PARITY MISMATCH against the reference digests:", parity)

@@ -78,7 +78,8 @@ class DevicePipeline:
     def __init__(self, ctx: api.Context, k: int, streams, subject_pairs, read_len: int, est_distinct: int,
                  min_cov: int = 5, max_cov: int = 150, minq: int = 15, thresh: int = 1, lower=(2, 2, 2),
                  mode: int = api.MODE_TILED, rank: int = 0, world: int = 1, max_mutant: int = 1 << 22,
-                 exchange: str = "p2p", groups_per_shard: int = 0, scatter_ctas: int = 0, fast_cap: int = 1 << 16):
+                 exchange: str = "p2p", groups_per_shard: int = 0, scatter_ctas: int = 0, fast_cap: int = 1 << 16,
+                 filter_exchange: str = "set"):
         import torch
 
         self.torch = torch
@@ -100,12 +101,15 @@ class DevicePipeline:
         import os
         self.serial = os.environ.get("RG_P2P_SERIAL", "0") == "1"
         self.schedule = os.environ.get("RG_P2P_SCHEDULE", "overlap")      # "batched" | "overlap"
+        # "set" (default): the few mutant k-mers are all-gathered, every rank filters its own reads (SURVEY §8e layout 1);
+        # "a2a": the set stays sharded, the reads travel and per-read hit counts are all-reduced (layout 2)
+        self.filter_exchange = filter_exchange
         # Fast path: the whole pass is ENQUEUED (deferred status checks, histogram / subtraction count / kept
         # count left on the device, a set rebuilt in place, one fixed-capacity all-gather of the mutant k-mers)
         # and the host synchronises once, at the end. Falls back to the step-by-step path when a table reports
         # spilled keys or a shard finds more than fast_cap mutant k-mers.
         self.fast_cap = min(fast_cap, max_mutant)
-        self.fast = k < 32 and os.environ.get("RG_PIPELINE_SLOW", "0") != "1"
+        self.fast = k < 32 and os.environ.get("RG_PIPELINE_SLOW", "0") != "1" and filter_exchange == "set"
         if self.fast:
             L0 = api.lib()
             self.fast_set = L0.rg_set_create(ctx.h, k, self.fast_cap * world)
@@ -317,6 +321,8 @@ class DevicePipeline:
             raise api._err("rg_subtract_dev")
         self.n_local = int(n)
         keys = self.mut_keys[:n]
+        if self.world > 1 and self.filter_exchange == "a2a":
+            return self._filter_sharded_set(keys, h)
         if self.world > 1:
             keys = gather_varlen(keys)
         mset = api.MutantSet(self.ctx, L.rg_set_from_jf_keys_dev(self.ctx.h, api._ptr(keys), keys.numel(), self.k),
@@ -328,6 +334,38 @@ class DevicePipeline:
         n_kept = int(self.keep.sum().item())     # device -> host read of the step's result
         mset.free()
         self.last.update({"n_mutant": int(keys.numel()), "n_kept": n_kept, "histo": h})
+        return self.last
+
+    def _filter_sharded_set(self, local_keys, h) -> dict:
+        """SURVEY §8e layout (2), the north-star wording: the mutant set STAYS SHARDED and the reads travel. Every
+        rank receives every rank's subject reads (one exchange of reads), counts their hits against ITS shard of the
+        mutant set, and the per-read hit counts are summed over the ranks (each mutant k-mer lives in exactly one
+        shard, so hits add up); a pair is pulled when either mate reaches the threshold (RUFUS.Filter.cpp:222).
+        Strictly more traffic than layout (1) (all-gather of the few mutant k-mers): kept behind
+        filter_exchange="a2a" for sets too large to replicate."""
+        import torch.distributed as dist
+        torch = self.torch
+        L = api.lib()
+        W, n = self.world, self.s1.numel()
+        allr = [torch.empty(W * n, dtype=torch.uint8, device=self.s1.device) for _ in range(4)]
+        for dst, src in zip(allr, (self.s1, self.q1, self.s2, self.q2)):
+            dist.all_gather_into_tensor(dst, src)
+        mset = api.MutantSet(self.ctx, L.rg_set_from_jf_keys_dev(self.ctx.h, api._ptr(local_keys), local_keys.numel(), self.k),
+                             self.k)
+        hits = [torch.zeros(W * self.n_pairs, dtype=torch.int32, device=self.s1.device) for _ in range(2)]
+        for hh, (sq, ql) in zip(hits, ((allr[0], allr[1]), (allr[2], allr[3]))):
+            api._check(L.rg_filter_hits_fixed_dev(mset.h, api._ptr(sq), api._ptr(ql), self.read_len, W * self.n_pairs,
+                                                  self.minq, 1, api._ptr(hh)), "rg_filter_hits_fixed_dev")
+            dist.all_reduce(hh)
+        mine = slice(self.rank * self.n_pairs, (self.rank + 1) * self.n_pairs)
+        self.keep.copy_(((hits[0][mine] >= self.thresh) | (hits[1][mine] >= self.thresh)).to(torch.uint8))
+        self.hits1.copy_(hits[0][mine])
+        self.hits2.copy_(hits[1][mine])
+        nm = torch.tensor([local_keys.numel()], dtype=torch.int64, device=self.s1.device)
+        dist.all_reduce(nm)
+        n_kept = int(self.keep.sum().item())
+        mset.free()
+        self.last.update({"n_mutant": int(nm.item()), "n_kept": n_kept, "histo": h})
         return self.last
 
     def mutant_keys_host(self):

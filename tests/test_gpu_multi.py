@@ -11,7 +11,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "nccl", "p2p+filter-a2a", "p2p+slow-tail"])
 def test_two_gpu_sharded_pipeline_matches_oracle(tmp_path, exchange):
     import torch
     if torch.cuda.device_count() < 2:
@@ -20,7 +20,11 @@ def test_two_gpu_sharded_pipeline_matches_oracle(tmp_path, exchange):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    env = dict(os.environ, RG_TMP=str(tmp_path), RG_EXCHANGE=exchange)
+    env = dict(os.environ, RG_TMP=str(tmp_path), RG_EXCHANGE=exchange.split("+")[0])
+    if exchange.endswith("filter-a2a"):          # SURVEY 8e layout (2): sharded mutant set, reads exchanged, hit counts all-reduced
+        env["RG_FILTER_EXCHANGE"] = "a2a"
+    if exchange.endswith("slow-tail"):           # the step-by-step tail instead of the single-sync one
+        env["RG_PIPELINE_SLOW"] = "1"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tools", "multigpu_check.py")], env=env, capture_output=True, text=True,

@@ -40,7 +40,7 @@ def main():
     est = int(1.1 * G / world + 14 * n_pairs)
     exchange = os.environ.get("RG_EXCHANGE", "p2p")
     pipe = pipeline.DevicePipeline(ctx, k, streams, subj, L, est, 5, 40 * world, 15, 1, rank=rank, world=world,
-                                   exchange=exchange)
+                                   exchange=exchange, filter_exchange=os.environ.get("RG_FILTER_EXCHANGE", "set"))
     r = pipe.step()
     r = pipe.step()          # twice: tables are cleared and re-used
     dumps = [t.dump(min_count=1) for t in pipe.tables]
