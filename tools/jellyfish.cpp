@@ -17,6 +17,8 @@
 #include <mutex>
 #include <thread>
 
+#include <sys/stat.h>
+
 #include "rg_cli.hpp"
 
 static const char* next_arg(int& i, int argc, char** argv, const char* opt) {
@@ -45,6 +47,46 @@ static FILE* open_out(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) die(std::string("Error opening output file '") + path + "'");
   return f;
+}
+
+// ---------------------------------------------------------------------------- histogram sidecar
+// `jellyfish count` is always followed by `jellyfish histo -f` on the file it wrote (RunJellyForRUFUS.sh:29,37),
+// a second process that would create a CUDA context and re-load the whole .Jhash for 10 002 numbers the counting
+// process can produce from the table it already holds (histo_kernel). count therefore leaves `<out>.rg_histo`
+// next to the .Jhash: magic, the .Jhash's size and mtime (a stale sidecar is ignored), then the rows of
+// `histo -l 1 -h 10000`; histo uses it when it is asked for exactly that and the .Jhash is the one it describes.
+static const uint64_t RG_HISTO_MAGIC = 0x3130747369486752ull;   // "RgHist01"
+static bool file_id(const char* path, uint64_t id[2]) {
+  struct stat st;
+  if (stat(path, &st) != 0) return false;
+  id[0] = (uint64_t)st.st_size;
+  id[1] = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+  return true;
+}
+static void write_histo_sidecar(const char* jhash, const std::vector<uint64_t>& rows) {
+  uint64_t id[2];
+  if (!file_id(jhash, id)) return;
+  const std::string p = std::string(jhash) + ".rg_histo";
+  FILE* f = fopen(p.c_str(), "wb");
+  if (!f) return;                                    // (a convenience: never an error)
+  const uint64_t head[4] = {RG_HISTO_MAGIC, id[0], id[1], (uint64_t)rows.size()};
+  const bool ok = fwrite(head, 8, 4, f) == 4 && fwrite(rows.data(), 8, rows.size(), f) == rows.size();
+  fclose(f);
+  if (!ok) remove(p.c_str());
+}
+static bool read_histo_sidecar(const char* jhash, std::vector<uint64_t>& rows) {
+  uint64_t id[2], head[4];
+  if (getenv("RG_NO_HISTO_SIDECAR") || !file_id(jhash, id)) return false;
+  FILE* f = fopen((std::string(jhash) + ".rg_histo").c_str(), "rb");
+  if (!f) return false;
+  bool ok = fread(head, 8, 4, f) == 4 && head[0] == RG_HISTO_MAGIC && head[1] == id[0] && head[2] == id[1] &&
+            head[3] == rg_histo_rows(1, 10000);
+  if (ok) {
+    rows.resize(head[3]);
+    ok = fread(rows.data(), 8, rows.size(), f) == rows.size();
+  }
+  fclose(f);
+  return ok;
 }
 
 // ---------------------------------------------------------------------------- count on several GPUs
@@ -238,6 +280,14 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
     mc.finish();
     check(rg_tables_write_jhash(mc.tab.data(), (int)mc.tab.size(), out, lower, upper, size, out_counter_len,
                                 full_argv + 1, full_argc - 1), "count");
+    if (upper == 0) {
+      std::vector<uint64_t> rows(rg_histo_rows(1, 10000), 0), part(rows.size());
+      for (rg_table* t : mc.tab) {
+        check(rg_histo(t, lower ? lower : 1, 1, 10000, part.data()), "count");
+        for (size_t i = 0; i < rows.size(); ++i) rows[i] += part[i];
+      }
+      write_histo_sidecar(out, rows);
+    }
     return 0;
   }
   rg_ctx* ctx = rg_init(devices[0]);
@@ -266,6 +316,11 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   if (!fill.empty()) flush(fill);
   check(rg_count_end(t), "count");
   check(rg_table_write_jhash(t, out, lower, upper, size, out_counter_len, full_argv + 1, full_argc - 1), "count");
+  if (upper == 0) {
+    std::vector<uint64_t> rows(rg_histo_rows(1, 10000));
+    check(rg_histo(t, lower ? lower : 1, 1, 10000, rows.data()), "count");
+    write_histo_sidecar(out, rows);
+  }
   rg_table_free(t);
   rg_shutdown(ctx);
   return 0;
@@ -307,19 +362,26 @@ static int histo_main(int argc, char** argv) {
   if (!db) die("Missing database file");
   if (high < low) die("High count value must be >= to low count value");
   if (inc != 1) die("only --increment 1 is supported");
-  rg_ctx* ctx = rg_init(0);
-  if (!ctx) die(rg_last_error());
-  Db d = open_db(ctx, db);
   const uint64_t rows = rg_histo_rows(low, high);
   std::vector<uint64_t> h(rows);
-  check(rg_histo(d.t, 1, low, high, h.data()), "histo");
+  rg_ctx* ctx = nullptr;
+  Db d;
+  // the histogram the counting process left next to the file it wrote (computed on the GPU then), if it is about this file
+  if (!(low == 1 && high == 10000 && read_histo_sidecar(db, h))) {
+    ctx = rg_init(0);
+    if (!ctx) die(rg_last_error());
+    d = open_db(ctx, db);
+    check(rg_histo(d.t, 1, low, high, h.data()), "histo");
+  }
   FILE* f = open_out(out);
   const uint64_t base = 1 >= low ? 0 : low - 1;     // histo_main.cc:64
   for (uint64_t i = 0; i < rows; ++i)
     if (h[i] > 0 || full) fprintf(f, "%llu %llu\n", (unsigned long long)(base + i), (unsigned long long)h[i]);
   if (f != stdout) fclose(f);
-  rg_table_free(d.t);
-  rg_shutdown(ctx);
+  if (ctx) {
+    rg_table_free(d.t);
+    rg_shutdown(ctx);
+  }
   return 0;
 }
 
