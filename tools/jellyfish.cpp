@@ -295,17 +295,19 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   // the table grows with the input (rg_table_reserve); -s only fixes the geometry written to the header
   rg_table* t = rg_count_begin(ctx, k, canonical, 1ull << 22, RG_MODE_TILED);
   if (!t) die(rg_last_error());
-  // two pinned buffers: the reader fills one while the other is copied and counted
-  const size_t chunk = 128u << 20;
+  // two pinned buffers: the reader fills one while the other is copied and counted. The chunk starts small (a
+  // small input should not pay for 2 x 128 MiB of pinned memory) and grows to 128 MiB.
+  size_t chunk = 8u << 20;
   ByteBuf fill, inflight;
-  fill.reserve(chunk + (8u << 20));
-  inflight.reserve(chunk + (8u << 20));
+  fill.reserve(chunk + (1u << 20));
   auto flush = [&](ByteBuf& b) {
     check(rg_count_end(t), "count");                 // the previous chunk (in `inflight`) is done; spills resolved
     check(rg_table_reserve(t, b.size()), "count");   // room for this chunk's k-mers, whatever they are
     inflight.swap(b);
     b.clear();
     check(rg_count_push(t, inflight.data(), inflight.size()), "count");   // asynchronous
+    chunk = std::min<size_t>(chunk * 4, 128u << 20);
+    b.reserve(chunk + (1u << 20));
   };
   for (const char* path : inputs) {
     FILE* f = fopen(path, "rb");

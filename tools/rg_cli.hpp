@@ -134,9 +134,10 @@ struct LineReader {
 // Appends the sequence of every record of a FASTA/FASTQ stream to `out`, one 'N' after each
 // record (what mer_overlap_sequence_parser.hpp:179-207 puts between reads: k-mers never span two
 // records, and the lines of a multi-line record are joined). Format sniffed from the first byte
-// (:124-153). flush(out) is called whenever `out` holds at least `chunk` bytes.
+// (:124-153). flush(out) is called whenever `out` holds at least `chunk` bytes (read again after every flush: the
+// caller may grow it).
 template <typename Buf, typename Flush>
-static inline void read_sequences(FILE* f, const char* path, Buf& out, size_t chunk, Flush&& flush) {
+static inline void read_sequences(FILE* f, const char* path, Buf& out, const size_t& chunk, Flush&& flush) {
   LineReader lr(f);
   const int c0 = lr.peek();
   if (c0 == EOF) return;
