@@ -413,7 +413,7 @@ def run_big(args, rank, local_rank, world, dev):
     except Exception:
         pass
     kern = {kk: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for kk, v in prof.items()}
-    names = [n for n in ("partition_kernel", "partition_p2p_kernel", "partition_groups_kernel", "tile_insert_kernel") if n in kern]
+    names = [n for n in ("partition_kernel", "partition_p2p_kernel", "partition_groups_kernel", "dedup_kernel", "tile_insert_kernel") if n in kern]
     # per sample push: (sum over its kernels of total time) / pushes; algorithmic bytes B + 16 n
     pushes = args.steps * ns
     count_ms = sum(kern[n]["ms_avg"] * kern[n]["launches"] for n in names) / max(pushes, 1)
@@ -617,10 +617,10 @@ def main():
         pass
     kern = {k: {"ms_avg": v[0] / max(v[1], 1), "launches": v[1]} for k, v in prof.items()}
     if world == 1:
-        names = ["partition_kernel", "partition_groups_kernel", "tile_insert_kernel"] if mode == api.MODE_TILED \
+        names = ["partition_kernel", "partition_groups_kernel", "dedup_kernel", "tile_insert_kernel"] if mode == api.MODE_TILED \
             else ["count_direct_kernel"]          # (partition_groups_kernel only runs for tables beyond one partition pass)
     elif args.exchange == "p2p":
-        names = ["partition_p2p_kernel", "partition_groups_kernel", "tile_insert_kernel"]
+        names = ["partition_p2p_kernel", "partition_groups_kernel", "dedup_kernel", "tile_insert_kernel"]
     else:
         names = ["extract_parts_kernel<count>", "extract_parts_kernel<scatter>", "partition_keys_kernel",
                  "tile_insert_kernel"] if mode == api.MODE_TILED else ["extract_parts_kernel<count>",

@@ -180,14 +180,14 @@ int rg_launch_mark_breaks(rg_ctx* ctx, const uint64_t* d_offs, uint64_t n_reads,
 // (~3 bytes per k-mer) + tile written once (+ read once when the table already holds data).
 // ---------------------------------------------------------------------------
 #ifndef TILE_WARPS_N
-#define TILE_WARPS_N 24
+#define TILE_WARPS_N 22
 #endif
 constexpr int TILE_WARPS = TILE_WARPS_N;
 constexpr int TILE_THREADS = TILE_WARPS * 32;
-// per warp: retry queue of 64 x (8-byte key, 4-byte slot | probes << RG_TILE_BITS), the 32 records of the
-// current batch, and the 512-bit map of the k-mer positions where a record starts
+// per warp: retry queue of 64 x (8-byte key, 4-byte slot | probes << RG_TILE_BITS, 4-byte multiplicity), the 32
+// records of the current batch, and the 512-bit map of the k-mer positions where a record starts
 constexpr uint32_t TILE_Q = 64;
-constexpr uint32_t TILE_WARP_SMEM = TILE_Q * 12 + 32 * 16 + 16 * 4;
+constexpr uint32_t TILE_WARP_SMEM = TILE_Q * 16 + 32 * 16 + 16 * 4;
 constexpr size_t TILE_SMEM = RG_TILE_KEY_BYTES + RG_TILE_CNT_BYTES + 64 + (size_t)TILE_WARPS * TILE_WARP_SMEM;
 static_assert(TILE_SMEM <= 232448, "tile insert: shared memory");
 
@@ -288,7 +288,8 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
     uint64_t* qkey = reinterpret_cast<uint64_t*>(wbase);                       // [TILE_Q]
     uint4* rq = reinterpret_cast<uint4*>(wbase + TILE_Q * 8);                  // [32]
     uint32_t* qsp = reinterpret_cast<uint32_t*>(wbase + TILE_Q * 8 + 512);     // [TILE_Q]
-    uint32_t* bm = qsp + TILE_Q;                                               // [16]
+    uint32_t* qadd = qsp + TILE_Q;                                             // [TILE_Q]
+    uint32_t* bm = qadd + TILE_Q;                                              // [16]
     const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
     uint32_t qhead = 0, qlen = 0;     // warp-uniform
     const uint32_t k = tv.geo.k;
@@ -297,7 +298,7 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
     // NR probes per lane (NR independent dependency chains: with ~6 warps per scheduler the fixed latencies of
     // one chain leave issue slots empty): key[i] at slot (sp[i] & mask) for the lanes with have[i]; fail[i] =
     // the lane met another key. The CAS (slot seen empty) and the count increment are predicated.
-    auto probe = [&](auto nr_tag, const uint64_t* key, const uint32_t* sp, const bool* have, bool* fail) {
+    auto probe = [&](auto nr_tag, const uint64_t* key, const uint32_t* sp, const uint32_t* add, const bool* have, bool* fail) {
       constexpr int NR = decltype(nr_tag)::value;
       unsigned long long seen[NR];
       uint32_t ka[NR];
@@ -326,15 +327,15 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
             "{\n"
             ".reg .pred q;\n"
             "setp.ne.u32 q, %1, 0;\n"
-            "@q red.shared.add.u32 [%0], 1;\n"
+            "@q red.shared.add.u32 [%0], %2;\n"
             "}\n" ::"r"(scounts_a + (sp[i] & (RG_TILE_SLOTS - 1)) * 4u),
-            "r"(hit ? 1u : 0u)
+            "r"(hit ? 1u : 0u), "r"(add[i])
             : "memory");
         fail[i] = have[i] && !hit;
       }
     };
     // the failed lanes push (key, next slot) onto the warp's retry queue (room for 32 more entries required)
-    auto push = [&](uint64_t key, uint32_t sp, bool fail) {
+    auto push = [&](uint64_t key, uint32_t sp, uint32_t add, bool fail) {
       const uint32_t fm = __ballot_sync(0xFFFFFFFFu, fail);
       if (fm) {                                             // warp-uniform
         if (fail) {
@@ -342,6 +343,7 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
           const uint32_t at = (qhead + qlen + __popc(fm & lt_mask)) & (TILE_Q - 1);
           qkey[at] = key;
           qsp[at] = sp + RG_TILE_SLOTS + 1u;
+          qadd[at] = add;
         }
         qlen += __popc(fm);
       }
@@ -353,17 +355,18 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
       const uint32_t at = (qhead + lane) & (TILE_Q - 1);
       const uint64_t key = qkey[at];
       const uint32_t sp = qsp[at];
+      const uint32_t add = qadd[at];
       __syncwarp();                                         // every lane has its entry before the step overwrites the ring
       bool have = lane < take;
       qhead = (qhead + take) & (TILE_Q - 1);
       qlen -= take;
       if (have && (sp >> RG_TILE_BITS) >= RG_PROBE_MAX) {   // probe window exhausted: the key lives in the overflow region
-        rg_ovf_add(tv, key, 1u);
+        rg_ovf_add(tv, key, add);
         have = false;
       }
       bool fail;
-      probe(std::integral_constant<int, 1>{}, &key, &sp, &have, &fail);
-      push(key, sp, fail);
+      probe(std::integral_constant<int, 1>{}, &key, &sp, &add, &have, &fail);
+      push(key, sp, add, fail);
     };
 
     for (uint32_t b0 = warp * 32; b0 < n; b0 += TILE_WARPS * 32) {
@@ -388,7 +391,7 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
       uint32_t carry = 0xFFFFFFFFu;                         // (records that start before this round) - 1, warp-uniform
       // k-mer j of the batch -> (key, home slot): the record it belongs to = (number of record starts at or
       // before j) - 1; lanes past the batch's end (last round only) wrap to some valid record and are masked
-      auto fetch = [&](uint32_t j0, uint64_t& key, uint32_t& slot) {
+      auto fetch = [&](uint32_t j0, uint64_t& key, uint32_t& slot, uint32_t& add) {
         const uint32_t word = bm[j0 >> 5];
         const uint32_t r = (carry + __popc(word & le_mask)) & 31u;
         carry += __popc(word);
@@ -396,29 +399,30 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
         const uint4 rr = rq[r];
         key = sk_key(rr, o, k, canonical);
         slot = rg_slot_of_key(key);
+        add = rr.w >> 4;                                    // how many identical records this one stands for (dedup_kernel)
       };
       uint32_t j0 = 0;
       for (; j0 + 32 < T; j0 += 64) {                       // two rounds at a time, their chains interleaved
         uint64_t key[2];
-        uint32_t slot[2];
-        fetch(j0, key[0], slot[0]);
-        fetch(j0 + 32, key[1], slot[1]);
+        uint32_t slot[2], add[2];
+        fetch(j0, key[0], slot[0], add[0]);
+        fetch(j0 + 32, key[1], slot[1], add[1]);
         const bool have[2] = {true, j0 + 32 + lane < T};
         bool fail[2];
-        probe(std::integral_constant<int, 2>{}, key, slot, have, fail);
-        push(key[0], slot[0], fail[0]);
+        probe(std::integral_constant<int, 2>{}, key, slot, add, have, fail);
+        push(key[0], slot[0], add[0], fail[0]);
         while (qlen >= 32) drain();
-        push(key[1], slot[1], fail[1]);
+        push(key[1], slot[1], add[1], fail[1]);
         while (qlen >= 32) drain();
       }
       if (j0 < T) {
         uint64_t key;
-        uint32_t slot;
-        fetch(j0, key, slot);
+        uint32_t slot, add;
+        fetch(j0, key, slot, add);
         const bool have = j0 + lane < T;
         bool fail;
-        probe(std::integral_constant<int, 1>{}, &key, &slot, &have, &fail);
-        push(key, slot, fail);
+        probe(std::integral_constant<int, 1>{}, &key, &slot, &add, &have, &fail);
+        push(key, slot, add, fail);
         while (qlen >= 32) drain();
       }
     }
@@ -440,8 +444,140 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
   }
 }
 
+// ---------------------------------------------------------------------------
+// Path 2, step 1.5: identical records of a tile's bucket collapse into one record + multiplicity. At 30x the
+// same locus is read ~30 times and a super-k-mer record is a pure function of the locus' bases (and of where
+// the 16-base block cut fell), so a bucket holds each record several times: the tile insert then probes the
+// hash table once per DISTINCT record k-mer, with the multiplicity as the increment. One CTA per bucket, a
+// shared-memory set of DD_SLOTS records keyed by the full 96 bits of bases + length (two 64-bit CAS words per
+// slot: either word is written once, and a record counts itself only in a slot where BOTH match), emptied into
+// the bucket IN PLACE whenever it could fill up (outputs never pass the inputs consumed). Record format out:
+// w = (multiplicity << 4) | (len - 1): the hash prefix is no longer needed once a record sits in its bucket.
+// ---------------------------------------------------------------------------
+constexpr uint32_t DD_SLOTS = 8192;
+constexpr int DD_THREADS = 1024;
+constexpr uint32_t DD_RPT = 4;                              // records per thread per chunk
+constexpr uint32_t DD_CHUNK = DD_THREADS * DD_RPT;
+constexpr uint32_t DD_PROBES = 16;
+constexpr size_t DD_SMEM = (size_t)DD_SLOTS * (8 + 8 + 4) + 64;
+
+__global__ void __launch_bounds__(DD_THREADS, 1)
+dedup_kernel(uint4* __restrict__ part_recs, uint32_t* __restrict__ cursor, uint32_t bucket_cap, uint32_t k) {
+  extern __shared__ __align__(16) unsigned char dd_raw[];
+  unsigned long long* A = reinterpret_cast<unsigned long long*>(dd_raw);                   // bases 0..31
+  unsigned long long* B = A + DD_SLOTS;                                                    // bases 32..47 : len - 1
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(B + DD_SLOTS);
+  uint32_t* s_out = cnt + DD_SLOTS;                                                        // [0] records written, [1] set entries
+  const uint32_t tile = blockIdx.x, t = threadIdx.x;
+  uint32_t n = cursor[tile];
+  if (n > bucket_cap) n = bucket_cap;
+  if (n == 0) return;
+  uint4* bucket = part_recs + (uint64_t)tile * bucket_cap;
+  for (uint32_t i = t; i < DD_SLOTS; i += DD_THREADS) {
+    A[i] = ~0ull;
+    B[i] = ~0ull;
+    cnt[i] = 0;
+  }
+  if (t < 2) s_out[t] = 0;
+  __syncthreads();
+  const uint32_t lane = t & 31u, lt_mask = (1u << lane) - 1u;
+  // a warp reserves output positions with ONE shared atomic (thousands of atomics on one address serialise)
+  auto reserve = [&](bool want) -> uint32_t {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+    uint32_t base = 0;
+    if (m && lane == 0) base = atomicAdd(&s_out[0], (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + __popc(m & lt_mask);
+  };
+  auto flush = [&]() {                      // every set entry -> one record with its multiplicity; the set is emptied
+    for (uint32_t i = t; i < DD_SLOTS; i += DD_THREADS) {
+      const uint32_t c = cnt[i];
+      const uint32_t pos = reserve(c != 0);
+      if (c) {
+        const unsigned long long a = A[i], b = B[i];
+        bucket[pos] = make_uint4((uint32_t)(a >> 32), (uint32_t)a, (uint32_t)(b >> 32), (c << 4) | ((uint32_t)b & 15u));
+        A[i] = ~0ull;
+        B[i] = ~0ull;
+        cnt[i] = 0;
+      }
+    }
+  };
+  // one chunk ahead: the next chunk's loads are in flight while this one is inserted
+  uint4 nxt[DD_RPT];
+#pragma unroll
+  for (uint32_t w = 0; w < DD_RPT; ++w) {
+    const uint32_t i = w * DD_THREADS + t;
+    nxt[w] = i < n ? bucket[i] : make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (uint32_t base = 0; base < n; base += DD_CHUNK) {
+    // a chunk's records are in registers before anything is written back: outputs may land on their positions
+    // (outputs never pass the records consumed, and the prefetched chunk counts as consumed)
+    uint4 rec[DD_RPT];
+#pragma unroll
+    for (uint32_t w = 0; w < DD_RPT; ++w) {
+      rec[w] = nxt[w];
+      const uint32_t i = base + DD_CHUNK + w * DD_THREADS + t;
+      nxt[w] = i < n ? bucket[i] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    // empty the set when it is 5/8 full: a chunk may still overfill it, records that find their neighbourhood
+    // crowded are written out as they are
+    if (s_out[1] > DD_SLOTS * 5 / 8) {
+      __syncthreads();
+      flush();
+      __syncthreads();
+      if (t == 0) s_out[1] = 0;
+      __syncthreads();
+    }
+#pragma unroll
+    for (uint32_t w = 0; w < DD_RPT; ++w) {
+      const bool have = base + w * DD_THREADS + t < n;
+      const uint32_t len1 = rec[w].w & 15u;
+      // bases beyond the record's len + k - 1 belong to what follows in the read: zero them, they are not part of the record
+      const uint32_t nb = len1 + k;                          // bases held (<= 47)
+      const uint32_t k0 = nb >= 16 ? 16u : nb, k1 = nb >= 32 ? 16u : (nb > 16 ? nb - 16u : 0u), k2 = nb > 32 ? nb - 32u : 0u;
+      const uint32_t x = k0 == 16 ? rec[w].x : rec[w].x & ~(0xFFFFFFFFu >> (2 * k0));
+      const uint32_t y = k1 == 16 ? rec[w].y : (k1 ? rec[w].y & ~(0xFFFFFFFFu >> (2 * k1)) : 0u);
+      const uint32_t z = k2 ? rec[w].z & ~(0xFFFFFFFFu >> (2 * k2)) : 0u;
+      const unsigned long long a = ((unsigned long long)x << 32) | y, b = ((unsigned long long)z << 32) | len1;
+      bool placed = false, fresh = false;
+      if (have && a != ~0ull) {
+        uint32_t h = x * 0x9E3779B1u + y * 0x85EBCA77u + (z ^ len1) * 0xC2B2AE35u;
+        h ^= h >> 15;
+        uint32_t slot = (h * 0x2C1B3C6Du) >> 19;             // 13 bits
+        for (uint32_t p = 0; p < DD_PROBES && !placed; ++p) {
+          const unsigned long long sa = atomicCAS(&A[slot], ~0ull, a);
+          if (sa == ~0ull || sa == a) {
+            const unsigned long long sb = atomicCAS(&B[slot], ~0ull, b);
+            if (sb == ~0ull || sb == b) {
+              fresh = atomicAdd(&cnt[slot], 1u) == 0;
+              placed = true;
+            }
+          }
+          slot = (slot + 1) & (DD_SLOTS - 1);
+        }
+      }
+      const uint32_t fm = __ballot_sync(0xFFFFFFFFu, fresh);
+      if (fm && lane == 0) atomicAdd(&s_out[1], (uint32_t)__popc(fm));
+      // crowded neighbourhood (or the all-T sentinel): as it is, once
+      const uint32_t pos = reserve(have && !placed);
+      if (have && !placed) bucket[pos] = make_uint4(x, y, z, (1u << 4) | len1);
+    }
+    __syncthreads();
+  }
+  flush();
+  __syncthreads();
+  if (t == 0) cursor[tile] = s_out[0];
+}
+
 int rg_launch_tile_insert(rg_table* t) {
   rg_ctx* ctx = t->ctx;
+  RG_CUDA_OK(cudaFuncSetAttribute(dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_SMEM));
+  {
+    rg_launch_scope _ls(ctx, "dedup_kernel");
+    dedup_kernel<<<t->n_tiles, DD_THREADS, DD_SMEM, ctx->stream>>>(t->part_keys, t->part_cursor, t->bucket_cap, (uint32_t)t->k);
+  }
+  RG_CUDA_OK(cudaGetLastError());
   const size_t smem = TILE_SMEM;
   // (the attribute is per device: set on every launch, a process may drive several GPUs)
   RG_CUDA_OK(cudaFuncSetAttribute(tile_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

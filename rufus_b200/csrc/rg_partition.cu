@@ -50,7 +50,7 @@ struct PartStage {
   uint32_t brk[BIT_WORDS + 2];
 };
 
-constexpr size_t sk_static_smem() { return sizeof(PartStage) + 80 * sizeof(uint32_t) + 512; }
+constexpr size_t sk_static_smem() { return sizeof(PartStage) + 80 * sizeof(uint32_t) + 3 * (SK_THREADS + 2) * 2 + 512; }
 // y/kmin rows, records, (bucket, rank) and sorted entries; run length -> slab delta and local offset per
 // bucket; overflow bitmap; level 2: chunk starts of the input slabs
 static size_t sk_dynamic_smem(uint32_t n_buckets, uint32_t n_groups = 0) {
@@ -267,6 +267,7 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
   __shared__ uint32_t scan_total;
   __shared__ uint32_t any_overflow;
   __shared__ uint32_t rec_total;
+  __shared__ uint16_t blk_valid[SK_THREADS + 2], blk_bnd[SK_THREADS + 2], blk_cut[SK_THREADS + 2];
   // MULTI: the owners' base pointers, indexed per bucket / per record (a dynamically indexed kernel
   // parameter array would be copied to local memory)
   __shared__ uint4* s_owner_keys[PART_MAX_OWNERS];
@@ -343,7 +344,7 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
     __syncthreads();
 
     // ---- records of this thread: start mask, first record index, the three forward words
-    uint32_t starts = 0, valid16 = 0, my_first = 0;
+    uint32_t starts = 0, valid16 = 0, my_first = 0, own_cuts = 0, next_cuts = 0;
     bool stage_pending = SRC == 0 && more;            // the next super-chunk's bases wait in registers (pf)
     uint32_t n_in_chunk = 0;                          // level 2: records of this chunk
     if (SRC == 0) {
@@ -393,13 +394,55 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
         }
       }
       __syncthreads();                                 // every neighbour has read y: the rows are reused for kmin
-      // ---- 4. record starts
-      uint32_t chg = 1u;
+      // ---- 4. record starts. A record = a maximal run of consecutive k-mers with the same minimizer value, cut only
+      // where the read says so (a window without a k-mer), every 16 k-mers of an over-long run, and at the edges of
+      // the super-chunk: NOT at the 16-base blocks of the threads, so that every read covering a locus produces the
+      // same records (dedup_kernel collapses them). Three exchanges through shared memory:
+      //   (a) kmin (own column of Yt) + the validity bits of the block        -> bit 0 of the boundary mask
+      //   (b) the boundary masks (position without a k-mer, or minimizer != previous position's)
+      //       -> forced cuts: a position 16, 32, .. k-mers after the last boundary (looked up in the two blocks before)
+      //   (c) boundary | forced masks                                           -> the length of each record
 #pragma unroll
-      for (int i = 1; i < SK_R; ++i) chg |= (kmin[i] != kmin[i - 1] ? 1u : 0u) << i;
-      starts = valid16 & (chg | ~(valid16 << 1));
+      for (int i = 0; i < SK_R; ++i) Yt[i * SK_YS + t] = kmin[i];   // own column (its y values have been consumed)
+      blk_valid[t] = (uint16_t)valid16;
+      uint32_t bnd = 0;
 #pragma unroll
-      for (int i = 0; i < SK_R; ++i) Yt[i * SK_YS + t] = kmin[i];   // own column: read back by this thread only
+      for (int i = 1; i < SK_R; ++i) bnd |= (kmin[i] != kmin[i - 1] ? 1u : 0u) << i;
+      bnd |= ~valid16 | ~(valid16 << 1);                   // no k-mer here, or none just before
+      bnd &= 0xFFFEu;
+      __syncthreads();
+      {
+        const bool prev_ok = t > 0 && ((blk_valid[t - 1] >> 15) & 1u);
+        const uint32_t prev_k = t > 0 ? Yt[15 * SK_YS + t - 1] : 0u;
+        if (!(valid16 & 1u) || !prev_ok || prev_k != kmin[0]) bnd |= 1u;      // (t == 0: the super-chunk's edge)
+      }
+      blk_bnd[t] = (uint16_t)bnd;
+      __syncthreads();
+      uint32_t cuts = bnd;
+      {
+        // positions whose 16 predecessors-and-self hold no boundary: an over-long run (repeated minimizer value)
+        const uint64_t m = (uint64_t)(t > 1 ? blk_bnd[t - 2] : 0xFFFFu) | ((uint64_t)(t > 0 ? blk_bnd[t - 1] : 0xFFFFu) << 16) |
+                           ((uint64_t)bnd << 32);
+        uint64_t o = m | (m << 1);
+        o |= o << 2;
+        o |= o << 4;
+        o |= o << 8;
+        uint32_t cand = (uint32_t)(~o >> 32) & 0xFFFFu;
+        while (cand) {                                      // rare
+          const int i = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const uint64_t below = m & ((2ull << (32 + i)) - 1ull);
+          // distance to the last boundary seen (none within the two blocks before: cut at the block's first position)
+          const bool force = below ? ((32 + i - (63 - __clzll((long long)below))) & 15) == 0 : i == 0;
+          if (force) cuts |= 1u << i;
+        }
+      }
+      blk_cut[t] = (uint16_t)cuts;
+      if (t == 0) blk_cut[SK_THREADS] = 0xFFFFu;           // nothing continues past the super-chunk
+      __syncthreads();
+      starts = cuts & valid16;
+      next_cuts = blk_cut[t + 1];
+      own_cuts = cuts;
       const uint32_t nrec = __popc(starts);
       uint32_t incl = nrec;
 #pragma unroll
@@ -430,8 +473,8 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
           const uint32_t rel = idx - round0;
           ++idx;
           if (rel >= SK_RMAX) continue;
-          // the record runs to the next start, to the next window without a k-mer, or to the end of the block
-          const uint32_t nb = ((starts | ~valid16) >> (s + 1)) | (1u << (15 - s));
+          // the record runs to the next cut (this block's or the next one's), at most 16 k-mers
+          const uint32_t nb = (((own_cuts & 0xFFFFu) | (next_cuts << 16)) >> (s + 1)) | (1u << 15);
           sorted[rel] = (t << 8) | (s << 4) | (__ffs(nb) - 1u);
         }
         __syncthreads();
@@ -448,8 +491,8 @@ sk_partition_kernel(ExtractParams ep, PartGeom g) {
             continue;
           }
           const uint32_t rank = atomicAdd(&hist[b], 1u);
-          const uint32_t W0 = sm.fwd[tt], W1 = sm.fwd[tt + 1], W2 = sm.fwd[tt + 2];
-          recs[i] = make_uint4(__funnelshift_l(W1, W0, 2 * s), __funnelshift_l(W2, W1, 2 * s), W2 << (2 * s),
+          const uint32_t W0 = sm.fwd[tt], W1 = sm.fwd[tt + 1], W2 = sm.fwd[tt + 2], W3 = sm.fwd[tt + 3];
+          recs[i] = make_uint4(__funnelshift_l(W1, W0, 2 * s), __funnelshift_l(W2, W1, 2 * s), __funnelshift_l(W3, W2, 2 * s),
                                mh | (d & 15u));
           metaS[i] = (b << SK_RBITS) | rank;
         }
