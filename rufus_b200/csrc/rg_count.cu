@@ -454,20 +454,24 @@ tile_insert_kernel(TableView tv, const uint4* __restrict__ part_recs, const uint
 // the bucket IN PLACE whenever it could fill up (outputs never pass the inputs consumed). Record format out:
 // w = (multiplicity << 4) | (len - 1): the hash prefix is no longer needed once a record sits in its bucket.
 // ---------------------------------------------------------------------------
-constexpr uint32_t DD_SLOTS = 8192;
+constexpr uint32_t DD_SLOTS = 13 * 1024;                    // 16-byte entries: 208 KiB of shared memory
 constexpr int DD_THREADS = 1024;
 constexpr uint32_t DD_RPT = 4;                              // records per thread per chunk
 constexpr uint32_t DD_CHUNK = DD_THREADS * DD_RPT;
 constexpr uint32_t DD_PROBES = 16;
-constexpr size_t DD_SMEM = (size_t)DD_SLOTS * (8 + 8 + 4) + 64;
+constexpr uint32_t DD_FLUSH_AT = DD_SLOTS * 7 / 16;         // keep the load low: a warp pays for its longest probe sequence
+constexpr size_t DD_SMEM = (size_t)DD_SLOTS * 16 + 64;
 
 __global__ void __launch_bounds__(DD_THREADS, 1)
 dedup_kernel(uint4* __restrict__ part_recs, uint32_t* __restrict__ cursor, uint32_t bucket_cap, uint32_t k) {
   extern __shared__ __align__(16) unsigned char dd_raw[];
-  unsigned long long* A = reinterpret_cast<unsigned long long*>(dd_raw);                   // bases 0..31
-  unsigned long long* B = A + DD_SLOTS;                                                    // bases 32..47 : len - 1
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(B + DD_SLOTS);
-  uint32_t* s_out = cnt + DD_SLOTS;                                                        // [0] records written, [1] set entries
+  // entry = A: bases 0..31 | B: bases 32..47 << 32 | multiplicity << 4 | len - 1. A is claimed by CAS, then B by CAS
+  // (multiplicity 0), then the multiplicity is raised by atomic adds of 16 on B's low word: either word's key part is
+  // written once, and a record counts itself only in a slot where BOTH match.
+  unsigned long long* A = reinterpret_cast<unsigned long long*>(dd_raw);
+  unsigned long long* B = A + DD_SLOTS;
+  uint32_t* s_out = reinterpret_cast<uint32_t*>(B + DD_SLOTS);                             // [0] records written, [1] set entries
+  constexpr unsigned long long KEYPART = 0xFFFFFFFF0000000Full;
   const uint32_t tile = blockIdx.x, t = threadIdx.x;
   uint32_t n = cursor[tile];
   if (n > bucket_cap) n = bucket_cap;
@@ -476,7 +480,6 @@ dedup_kernel(uint4* __restrict__ part_recs, uint32_t* __restrict__ cursor, uint3
   for (uint32_t i = t; i < DD_SLOTS; i += DD_THREADS) {
     A[i] = ~0ull;
     B[i] = ~0ull;
-    cnt[i] = 0;
   }
   if (t < 2) s_out[t] = 0;
   __syncthreads();
@@ -491,14 +494,13 @@ dedup_kernel(uint4* __restrict__ part_recs, uint32_t* __restrict__ cursor, uint3
   };
   auto flush = [&]() {                      // every set entry -> one record with its multiplicity; the set is emptied
     for (uint32_t i = t; i < DD_SLOTS; i += DD_THREADS) {
-      const uint32_t c = cnt[i];
-      const uint32_t pos = reserve(c != 0);
-      if (c) {
-        const unsigned long long a = A[i], b = B[i];
-        bucket[pos] = make_uint4((uint32_t)(a >> 32), (uint32_t)a, (uint32_t)(b >> 32), (c << 4) | ((uint32_t)b & 15u));
+      const unsigned long long a = A[i], b = B[i];
+      const bool used = a != ~0ull;          // (a claimed A always gets its B and a multiplicity >= 1 before the next barrier)
+      const uint32_t pos = reserve(used);
+      if (used) {
+        bucket[pos] = make_uint4((uint32_t)(a >> 32), (uint32_t)a, (uint32_t)(b >> 32), (uint32_t)b);
         A[i] = ~0ull;
         B[i] = ~0ull;
-        cnt[i] = 0;
       }
     }
   };
@@ -520,9 +522,9 @@ dedup_kernel(uint4* __restrict__ part_recs, uint32_t* __restrict__ cursor, uint3
       nxt[w] = i < n ? bucket[i] : make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    // empty the set when it is 5/8 full: a chunk may still overfill it, records that find their neighbourhood
-    // crowded are written out as they are
-    if (s_out[1] > DD_SLOTS * 5 / 8) {
+    // empty the set before it gets crowded: a chunk may still overfill it, records that find their neighbourhood
+    // full are written out as they are
+    if (s_out[1] > DD_FLUSH_AT) {
       __syncthreads();
       flush();
       __syncthreads();
@@ -533,28 +535,49 @@ dedup_kernel(uint4* __restrict__ part_recs, uint32_t* __restrict__ cursor, uint3
     for (uint32_t w = 0; w < DD_RPT; ++w) {
       const bool have = base + w * DD_THREADS + t < n;
       const uint32_t len1 = rec[w].w & 15u;
-      // bases beyond the record's len + k - 1 belong to what follows in the read: zero them, they are not part of the record
+      // bases beyond the record's len + k - 1 belong to what follows in the read: zero them, they are not part of the
+      // record (measured: comparing them as they are costs a quarter of the merges)
       const uint32_t nb = len1 + k;                          // bases held (<= 47)
-      const uint32_t k0 = nb >= 16 ? 16u : nb, k1 = nb >= 32 ? 16u : (nb > 16 ? nb - 16u : 0u), k2 = nb > 32 ? nb - 32u : 0u;
-      const uint32_t x = k0 == 16 ? rec[w].x : rec[w].x & ~(0xFFFFFFFFu >> (2 * k0));
-      const uint32_t y = k1 == 16 ? rec[w].y : (k1 ? rec[w].y & ~(0xFFFFFFFFu >> (2 * k1)) : 0u);
-      const uint32_t z = k2 ? rec[w].z & ~(0xFFFFFFFFu >> (2 * k2)) : 0u;
+      uint32_t x = rec[w].x;
+      unsigned long long yz = ((unsigned long long)rec[w].y << 32) | rec[w].z;
+      if (nb >= 16) {
+        yz &= ~(~0ull >> (2 * (nb - 16)));                   // (nb == 16: nothing of y, z is kept)
+      } else {
+        yz = 0;
+        x &= ~(0xFFFFFFFFu >> (2 * nb));
+      }
+      const uint32_t y = (uint32_t)(yz >> 32), z = (uint32_t)yz;
       const unsigned long long a = ((unsigned long long)x << 32) | y, b = ((unsigned long long)z << 32) | len1;
       bool placed = false, fresh = false;
       if (have && a != ~0ull) {
         uint32_t h = x * 0x9E3779B1u + y * 0x85EBCA77u + (z ^ len1) * 0xC2B2AE35u;
         h ^= h >> 15;
-        uint32_t slot = (h * 0x2C1B3C6Du) >> 19;             // 13 bits
-        for (uint32_t p = 0; p < DD_PROBES && !placed; ++p) {
-          const unsigned long long sa = atomicCAS(&A[slot], ~0ull, a);
+        uint32_t slot = (uint32_t)(((uint64_t)(h * 0x2C1B3C6Du) * DD_SLOTS) >> 32);
+        uint32_t probes = 0;
+        while (!placed && probes < DD_PROBES) {
+          // (1) walk past the slots other records own: a tiny loop, a warp pays for its longest walk
+          unsigned long long sa;
+          for (;;) {
+            sa = *(volatile unsigned long long*)&A[slot];
+            if (sa == a || sa == ~0ull || ++probes >= DD_PROBES) break;
+            slot = slot + 1 == DD_SLOTS ? 0u : slot + 1;
+          }
+          if (probes >= DD_PROBES) break;
+          // (2) claim or join; most records repeat one that is already in the set (plain loads, one atomic add)
+          if (sa == ~0ull) sa = atomicCAS(&A[slot], ~0ull, a);
           if (sa == ~0ull || sa == a) {
-            const unsigned long long sb = atomicCAS(&B[slot], ~0ull, b);
-            if (sb == ~0ull || sb == b) {
-              fresh = atomicAdd(&cnt[slot], 1u) == 0;
+            unsigned long long sb = *(volatile unsigned long long*)&B[slot];
+            if (sb == ~0ull) sb = atomicCAS(&B[slot], ~0ull, b);
+            if (sb == ~0ull || ((sb ^ b) & KEYPART) == 0) {
+              const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(&B[slot]), 16u);   // low word (little-endian)
+              fresh = (old >> 4) == 0;
               placed = true;
             }
           }
-          slot = (slot + 1) & (DD_SLOTS - 1);
+          if (!placed) {                                      // lost the slot to another record: go on
+            ++probes;
+            slot = slot + 1 == DD_SLOTS ? 0u : slot + 1;
+          }
         }
       }
       const uint32_t fm = __ballot_sync(0xFFFFFFFFu, fresh);
