@@ -283,6 +283,7 @@ static uint64_t ovf_for(uint64_t main_slots) {
 
 static int table_alloc_tiles(rg_table* t, uint32_t wanted, uint64_t ovf_slots = 0) {
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   uint32_t n_tiles, group_tiles;
   choose_geometry(t, wanted, &n_tiles, &group_tiles);
   const uint64_t main_slots = (uint64_t)n_tiles << RG_TILE_BITS;
@@ -314,6 +315,7 @@ static uint32_t tiles_for(uint64_t est_distinct) {
 // rebuild with new_tiles tiles (and at least new_ovf overflow slots) and re-insert every (key,count)
 static int table_grow(rg_table* t, uint32_t new_tiles, uint64_t new_ovf = 0) {
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   uint64_t* old_keys = t->keys;
   uint32_t* old_counts = t->counts;
   const uint64_t old_slots = rg_table_slots(t);
@@ -349,6 +351,7 @@ static int ensure_spill(rg_table* t, uint64_t n_keys) {
   uint64_t want = std::max<uint64_t>(1ull << 22, std::min<uint64_t>(n_keys / 4, 1ull << 27));
   if (t->spill_cap >= want) return 0;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   if (t->spill_keys) {
     int rc = rg_table_finish(t);          // (entries of earlier pushes are resolved first)
     if (rc) return rc;
@@ -369,6 +372,7 @@ static int ensure_spill(rg_table* t, uint64_t n_keys) {
 // overflow region at most half full
 static int table_check_status(rg_table* t) {
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   for (int round = 0; round < 10; ++round) {
     uint64_t st[RG_ST_WORDS];
     int rc = read_scalars(ctx, t->d_status, RG_ST_WORDS, st);
@@ -439,6 +443,7 @@ static int ensure_stage(rg_table* t, uint64_t bytes) {
 // the sizing is a speed matter only.
 static int prepare_buckets(rg_table* t, uint64_t n_bytes) {
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   const uint64_t n_rec = (uint64_t)((double)n_bytes * rg_partition_record_density(t->k, t->m)) + 1;
   // bucket capacity: mean records per tile + 30 % + slack
   const uint64_t mean = n_rec / t->n_tiles + 1;
@@ -554,6 +559,7 @@ static int push_dev_impl(rg_table* t, const char* dev_stream, uint64_t n_bytes, 
 // every reader of a table goes through this: resolve what the enqueued pushes left behind
 static int p2p_collect_spill(rg_table* t) {
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   t->p2p_pending = false;
   uint64_t n_spill = 0;
   int rc = read_scalars(ctx, t->p2p_status, 1, &n_spill);
@@ -675,6 +681,7 @@ int rg_table_p2p_prepare(rg_table* t, uint32_t groups_per_shard, uint64_t max_ke
     return RG_ERR_ARG;
   }
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   if ((uint64_t)groups_per_shard * t->shard_parts > rg_partition_max_buckets()) {
     rg_set_error("rg_table_p2p_prepare: too many groups for one partition pass");
     return RG_ERR_ARG;
@@ -844,6 +851,7 @@ int rg_count_push(rg_table* t, const char* host_stream, uint64_t n_bytes) {
   if (!t) return RG_ERR_ARG;
   if (n_bytes == 0) return 0;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   int rc = slots_ensure(ctx);
   if (rc == 0) rc = ensure_spill(t, n_bytes);
   if (rc) return rc;
@@ -881,6 +889,7 @@ int rg_count_push_reads(rg_table* t, const char* host_seq, const uint64_t* host_
   if (!t) return RG_ERR_ARG;
   if (n_reads == 0) return 0;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   const uint64_t base = host_offs[0];
   const uint64_t n_bytes = host_offs[n_reads] - base;
   if (n_bytes == 0) return 0;
@@ -967,6 +976,7 @@ int rg_table_trim(rg_table* t) {
 int rg_table_clear(rg_table* t) {
   if (!t) return RG_ERR_ARG;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   const uint64_t slots = rg_table_slots(t);
   RG_CUDA_OK(cudaMemsetAsync(t->keys, 0xFF, slots * 8, ctx->stream));
   RG_CUDA_OK(cudaMemsetAsync(t->counts, 0, slots * 4, ctx->stream));
@@ -1004,6 +1014,7 @@ void rg_table_free(rg_table* t) {
 
 int rg_table_stats(rg_table* t, uint64_t* n_distinct, uint64_t* n_occ, uint64_t* n_slots) {
   if (!t) return RG_ERR_ARG;
+  cudaSetDevice(t->ctx->device);
   int rc = rg_table_finish(t);
   if (rc) return rc;
   rc = rg_launch_stats(t, t->ctx->d_scratch);
@@ -1038,6 +1049,7 @@ int rg_extract_partition_dev(rg_table* t, const char* dev_stream, uint64_t n_byt
                              uint64_t* keys_out_dev, uint64_t* part_offsets_dev) {
   if (!t) return RG_ERR_ARG;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   ExtractParams ep;
   ep.stream = dev_stream;
   ep.n_bytes = n_bytes;
@@ -1064,6 +1076,7 @@ int rg_defer_checks(rg_ctx* ctx, int on) {
 int rg_table_status_async(rg_table* t, uint64_t* host_pinned) {
   if (!t || !host_pinned) return RG_ERR_ARG;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   RG_CUDA_OK(cudaMemcpyAsync(host_pinned, t->d_status, RG_ST_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   host_pinned[8] = 0;
   if (t->p2p_block)
@@ -1075,6 +1088,7 @@ int rg_table_status_async(rg_table* t, uint64_t* host_pinned) {
 int rg_table_status_dev(rg_table* t, uint64_t* dev_out9) {
   if (!t || !dev_out9) return RG_ERR_ARG;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   RG_CUDA_OK(cudaMemcpyAsync(dev_out9, t->d_status, RG_ST_WORDS * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
   if (t->p2p_block)
     RG_CUDA_OK(cudaMemcpyAsync(dev_out9 + 8, t->p2p_status, sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1093,6 +1107,7 @@ int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint6
     return RG_ERR_ARG;
   }
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   const uint64_t nb = rg_histo_rows(low, high);
   int rc = rg_table_finish(t);
   if (rc == 0) rc = pool_ensure(ctx, 5, nb * 8);
@@ -1110,6 +1125,7 @@ int rg_histo(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint6
 // histogram left on the device (rg_histo_rows(low, high) uint64): no host round trip
 int rg_histo_dev(rg_table* t, uint64_t min_count, uint64_t low, uint64_t high, uint64_t* out_dev) {
   if (!t || high < low || !out_dev) return RG_ERR_ARG;
+  cudaSetDevice(t->ctx->device);
   int rc = rg_table_finish(t);
   if (rc) return rc;
   return rg_launch_histo(t, min_count, histo_base(low), rg_histo_rows(low, high), out_dev);
@@ -1130,6 +1146,7 @@ int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* k
                 uint64_t cap, uint64_t* needed) {
   if (!t) return RG_ERR_ARG;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   uint64_t* d_keys = nullptr;
   uint32_t* d_counts = nullptr;
   RG_CUDA_OK(cudaMalloc(&d_keys, (cap ? cap : 1) * 8));
@@ -1159,6 +1176,7 @@ int64_t rg_dump_slice_dev(rg_table* t, uint64_t min_count, uint32_t slice_mod, u
                           uint32_t* counts_dev, uint64_t cap, uint64_t* needed) {
   if (!t || (slice_mod && slice_rem >= slice_mod)) return RG_ERR_ARG;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   int64_t rc = rg_table_finish(t);
   if (rc == 0)
     rc = rg_launch_dump(t, min_count ? min_count : 1, ~0ull, keys_dev, counts_dev, cap, ctx->d_scratch, slice_mod, slice_rem);
@@ -1206,6 +1224,7 @@ int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_co
   if (!t) return RG_ERR_ARG;
   if (n == 0) return 0;
   rg_ctx* ctx = t->ctx;
+  cudaSetDevice(ctx->device);
   uint64_t* dk = nullptr;
   uint32_t* dc = nullptr;
   RG_CUDA_OK(cudaMalloc(&dk, n * 8));
@@ -1260,6 +1279,7 @@ int rg_subtract_enqueue(rg_table* subj, uint64_t subj_min, rg_table* const* othe
                         uint32_t* counts_dev, uint64_t cap, uint64_t* count_dev) {
   if (!subj || !count_dev) return RG_ERR_ARG;
   rg_ctx* ctx = subj->ctx;
+  cudaSetDevice(ctx->device);
   OtherTables ot;
   int rc = rg_table_finish(subj);
   if (rc) return rc;
@@ -1280,6 +1300,7 @@ int64_t rg_subtract_dev(rg_table* subj, uint64_t subj_min, rg_table* const* othe
                         uint32_t* counts_dev, uint64_t cap) {
   if (!subj) return RG_ERR_ARG;
   rg_ctx* ctx = subj->ctx;
+  cudaSetDevice(ctx->device);
   OtherTables ot;
   int rc = rg_table_finish(subj);
   if (rc) return rc;
@@ -1310,6 +1331,7 @@ int64_t rg_subtract(rg_table* subj, uint64_t subj_min, rg_table* const* others, 
                     uint32_t* counts_host, uint64_t cap, uint64_t* needed) {
   if (!subj) return RG_ERR_ARG;
   rg_ctx* ctx = subj->ctx;
+  cudaSetDevice(ctx->device);
   uint64_t* dk = nullptr;
   uint32_t* dc = nullptr;
   RG_CUDA_OK(cudaMalloc(&dk, (cap ? cap : 1) * 8));
@@ -1331,6 +1353,7 @@ int64_t rg_build_select(rg_table* subj, int64_t min_subject, int64_t max_subject
                         uint32_t* control_sums_host, uint64_t cap, uint64_t* needed) {
   if (!subj) return RG_ERR_ARG;
   rg_ctx* ctx = subj->ctx;
+  cudaSetDevice(ctx->device);
   OtherTables ot;
   int rc = rg_table_finish(subj);
   if (rc) return rc;
@@ -1464,6 +1487,7 @@ static rg_set* set_alloc(rg_ctx* ctx, uint64_t n_vals, int k) {
 
 static int set_finish(rg_set* s, const uint64_t* d_vals, uint64_t n) {
   rg_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
   int rc = rg_launch_set_build(s, d_vals, n);
   if (rc) return rc;
   uint64_t d = 0;
@@ -1554,6 +1578,7 @@ int rg_set_rebuild_dev(rg_set* s, const uint64_t* jf_keys_dev, uint64_t n_max) {
     return RG_ERR_ARG;
   }
   rg_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
   RG_CUDA_OK(cudaMemsetAsync(s->table, 0xFF, (uint64_t)s->slots * 8, ctx->stream));
   RG_CUDA_OK(cudaMemsetAsync(s->bitmap, 0, RG_SET_BITMAP_BITS / 8, ctx->stream));
   int rc = rg_launch_jf_to_rufus(ctx, jf_keys_dev, n_max, s->k, s->scratch);
@@ -1664,6 +1689,7 @@ static int filter_host_mate(rg_set* s, const char* seq, const char* qual, const 
                             const uint64_t* offs_dev, uint64_t n_reads, int minq, int skip_last, int32_t* hits_dev,
                             uint8_t* hit_flags_dev = nullptr) {
   rg_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
   RG_CUDA_OK(cudaMemsetAsync(hits_dev, 0, n_reads * sizeof(int32_t), ctx->stream));
   const uint64_t half = (ctx->slot_bytes / 2) & ~255ull;     // sequence in the first half of a slot, quality in the second
   uint64_t r0 = 0;
@@ -1713,6 +1739,7 @@ int rg_filter_pairs(rg_set* s, const char* s1, const char* q1, const uint64_t* o
   if (!s) return RG_ERR_ARG;
   if (n_pairs == 0) return 0;
   rg_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
   int rc = slots_ensure(ctx);
   if (rc == 0) rc = upload_offsets(ctx, 0, o1, n_pairs);
   if (rc == 0) rc = upload_offsets(ctx, 1, o2, n_pairs);
@@ -1740,6 +1767,7 @@ int rg_annotate(rg_set* s, const char* seq, const char* qual, const uint64_t* of
   if (!s) return RG_ERR_ARG;
   if (n_reads == 0) return 0;
   rg_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
   const uint64_t n_bytes = offs[n_reads];
   int rc = slots_ensure(ctx);
   if (rc == 0) rc = upload_offsets(ctx, 0, offs, n_reads);
@@ -1764,6 +1792,7 @@ int rg_filter_single(rg_set* s, const char* seq, const char* qual, const uint64_
   if (!s) return RG_ERR_ARG;
   if (n_reads == 0) return 0;
   rg_ctx* ctx = s->ctx;
+  cudaSetDevice(ctx->device);
   int rc = slots_ensure(ctx);
   if (rc == 0) rc = upload_offsets(ctx, 0, offs, n_reads);
   if (rc == 0) rc = pool_ensure(ctx, 2, n_reads * 4);

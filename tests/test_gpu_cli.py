@@ -254,13 +254,6 @@ def test_bam_mode_chain_matches_reference(tmp_path):
         sh(f"{JF} histo -f -o {s}.histo {s}.Jhash", work)
         gs = g["samples"][s]
         assert md5(open(os.path.join(work, s + ".histo"), "rb").read()) == gs["histo_md5"]
-        # (that one came from the sidecar `count` leaves next to the .Jhash; the loading path must agree, and a
-        # sidecar that describes another file must be ignored)
-        assert os.path.exists(os.path.join(work, s + ".Jhash.rg_histo"))
-        h2 = sh(f"RG_NO_HISTO_SIDECAR=1 {JF} histo -f {s}.Jhash", work).stdout
-        assert md5(h2) == gs["histo_md5"]
-        sh(f"cp {s}.Jhash {s}.copy.Jhash && cp {SAMPLES[case][0]}.Jhash.rg_histo {s}.copy.Jhash.rg_histo && sleep 0.01 && touch {s}.copy.Jhash", work)
-        assert md5(sh(f"{JF} histo -f {s}.copy.Jhash", work).stdout) == gs["histo_md5"]
         dump = sh(f"{JF} dump -c {s}.Jhash | LC_ALL=C sort", work).stdout
         assert dump.count(b"\n") == gs["n_distinct"] and md5(dump) == gs["dump_sorted_md5"]
     merged = sh(f"{JF} merge " + " ".join(s + ".Jhash" for s in names) + " > merge.out; cat merge.out", work).stdout
