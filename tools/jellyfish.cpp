@@ -90,7 +90,10 @@ static bool read_histo_sidecar(const char* jhash, std::vector<uint64_t>& rows) {
 }
 
 // ---------------------------------------------------------------------------- count on several GPUs
-// The devices `jellyfish count` uses: RG_DEVICES=0,1,... (or "all"), default every visible GPU.
+// The devices `jellyfish count` uses: RG_DEVICES=0,1,... or "all"; default: the first GPU. One host thread parses
+// the input (~1 GB/s of FASTQ), which cannot even feed one GPU, so more GPUs buy CAPACITY (a table too large for one
+// device: 180 GB hold ~8 G distinct k-mers), not speed, and cost start-up time (measured on an 8-GPU box, C2-sized
+// input: 16 s for three counts with 8 contexts + 2 GB of pinned buffers against 5 s with one GPU): opt-in.
 static std::vector<int> count_devices() {
   const int n = rg_device_count();
   if (n <= 0) die("jellyfish count: no CUDA device (librufus_gpu has no CPU fallback)");
@@ -105,7 +108,7 @@ static std::vector<int> count_devices() {
       p = *end == ',' ? end + 1 : end;
       if (*end != ',' && *end != 0) die(std::string("RG_DEVICES: bad device list '") + e + "'");
     }
-  } else {
+  } else if (e && *e) {
     for (int i = 0; i < n && i < 8; ++i) d.push_back(i);
   }
   if (d.empty()) d.push_back(0);
