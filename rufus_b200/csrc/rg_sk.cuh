@@ -2,11 +2,17 @@
 //
 // The reference inserts every k-mer occurrence on its own (count_main.cc:154-157 ->
 // large_hash_array.hpp:298-302). Here the consecutive k-mers of a read that share a minimizer (same hash
-// prefix mh, rg_internal.cuh) are kept together as ONE 16-byte record, so the partition moves ~2-3 bytes
+// prefix mh, rg_internal.cuh) are kept together as ONE 16-byte record, so the partition moves ~2.3 bytes
 // per k-mer instead of 8, and the tile insert re-extracts the k-mers from the record:
 //   x, y, z : the record's bases, 2 bits each, A0 C1 G2 T3, BIG-endian (base 0 in bits 31..30 of x);
-//             a record of len k-mers holds len + k - 1 <= 47 bases
-//   w       : mh (low 4 bits clear) | (len - 1), len = 1..16 k-mers
+//             a record of len k-mers holds len + k - 1 <= 47 bases (what follows in x, y, z is whatever the read
+//             continued with: not part of the record)
+//   w       : out of the partition: mh (low 4 bits clear) | (len - 1), len = 1..16 k-mers;
+//             out of dedup_kernel (what the tile insert reads): (multiplicity << 4) | (len - 1)
+// A record is a PURE super-k-mer: a maximal run of k-mers with the same minimizer value, cut only where the read
+// has no k-mer, every 16 k-mers of an over-long run, and at the edges of a 16384-window super-chunk — never at
+// the 16-base blocks of the partition's threads. Every read that covers a locus therefore produces the same
+// records, and dedup_kernel collapses the ~30 copies a 30x sample holds of each into one record + multiplicity.
 // The minimizer only ROUTES (tile = f(mh)); the counted keys are the canonical k-mers themselves, so the
 // table content is independent of how reads were cut into records.
 #pragma once
