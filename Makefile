@@ -11,7 +11,7 @@ LIB  := rufus_b200/librufus_gpu.so
 all: lib tools oracle
 
 lib: $(LIB)
-rufus_b200/csrc/%.o: rufus_b200/csrc/%.cu rufus_b200/csrc/rg_internal.cuh include/rufus_gpu.h
+rufus_b200/csrc/%.o: rufus_b200/csrc/%.cu $(wildcard rufus_b200/csrc/*.cuh) include/rufus_gpu.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ccbin $(CXX)

@@ -276,12 +276,9 @@ int rg_launch_filter_hits(rg_set* s, const char* seq, const char* qual, const ui
   if (zero_hits) RG_CUDA_OK(cudaMemsetAsync(hits, 0, n_reads * sizeof(int32_t), ctx->stream));
   if (n_bytes == 0 || n_reads == 0) return 0;
   const size_t smem = s->bitmap_bits / 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RG_CUDA_OK(cudaFuncSetAttribute(filter_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(RG_SET_BITMAP_BITS / 8)));
-    attr_set = true;
-  }
+  // (the attribute is per device: set on every launch, a process may drive several GPUs)
+  RG_CUDA_OK(cudaFuncSetAttribute(filter_hits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(RG_SET_BITMAP_BITS / 8)));
   const uint64_t n_chunks = (n_bytes + FCHUNK - 1) / FCHUNK;
   unsigned grid = rg_grid(ctx, smem >= 65536 ? 3 : 4);
   if (n_chunks < grid) grid = (unsigned)n_chunks;

@@ -35,11 +35,18 @@ def test_product_code_never_touches_the_oracle():
 
 
 def test_bench_uses_the_oracle_only_for_the_cpu_baseline():
+    """every mention of oracle/ in bench.py sits inside a function that times the REFERENCE'S side: cpu_reference_pass
+    (cpu_baseline leg and --impl reference), cpu_reference_big (the large configs' cpu_baseline) and cli_leg (the
+    reference's stage commands next to ours). Nothing on the measured CUDA path touches it."""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    # every mention of oracle/ sits inside cpu_reference_pass (the cpu_baseline leg and --impl reference)
-    start = src.index("def cpu_reference_pass")
-    end = src.index("def run_reference_arm")
-    outside = src[:start] + src[end:]
+    allowed = ("cpu_reference_pass", "cpu_reference_big", "cli_leg")
+    outside, pos = [], 0
+    for m in re.finditer(r"^def (\w+)\(.*?(?=^def |\Z)", src, re.S | re.M):
+        if m.group(1) in allowed:
+            outside.append(src[pos:m.start()])
+            pos = m.end()
+    outside = "".join(outside) + src[pos:]
+    assert "def main" in outside and "def run_big" in outside
     assert "import oracle" not in outside and '"oracle"' not in outside
 
 
