@@ -85,6 +85,9 @@ def test_bamview_synthetic_matches_hand_built_sam():
     # stdin input
     r = subprocess.run([os.path.join(BIN, "rg_bamview"), "-"], input=open(bam, "rb").read(), capture_output=True)
     assert r.returncode == 0 and r.stdout == want
+    # zlib's inflate instead of tools/rg_inflate.hpp (the fallback path for a member the fast decoder rejects)
+    r = subprocess.run([os.path.join(BIN, "rg_bamview"), bam], capture_output=True, env=dict(os.environ, RG_BAMVIEW_ZLIB="1"))
+    assert r.returncode == 0 and r.stdout == want
 
 
 def test_bamview_rejects_bad_input(tmp_path):
