@@ -272,3 +272,32 @@ def test_bamview_fuzz_against_spec_writer_and_restatement(seed, tmp_path):
         r = _bamview("-F", str(excl), "-f", str(req), "-@", str(rnd.choice([1, 2, 5])), str(bam))
         assert r.returncode == 0, r.stderr
         assert r.stdout.decode().splitlines() == keep
+
+
+def test_bamview_header_and_records_larger_than_a_batch(tmp_path):
+    """a BAM header of ~0.5 MB and reads of 70 k / 150 k bases in BGZF blocks of 61 bytes: the header and the long
+    records straddle several pipeline batches (4096 members each), so they are stitched from the carried bytes of
+    the batches before (the path beside the 64 KiB headroom)"""
+    import random
+    import bam_oracle
+    from bam_build import build_bam, expected_sam
+    rnd = random.Random(3)
+    refs = [(f"contig_{i:05d}_with_a_long_name", 1000 + i) for i in range(6000)]
+    text = "@HD\tVN:1.6\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
+    recs = []
+    for r, L in enumerate([150, 70_000, 151, 150_000, 1, 149]):
+        seq = "".join(rnd.choice("ACGT") for _ in range(L))
+        qual = "".join(chr(33 + rnd.randrange(41)) for _ in range(L))
+        recs.append((f"read{r}", 99 if r % 2 == 0 else 147, r * 7, 100 + r, 60, [(L, "M")], r * 7, 400 + r, 300, seq, qual,
+                     [("NM", "C", r), ("RG", "Z", "grp")]))
+    bam = tmp_path / "big.bam"
+    bam.write_bytes(build_bam(text, refs, recs, block=61))
+    want = expected_sam(refs, recs)
+    for threads in ("1", "4"):
+        r = _bamview("-@", threads, str(bam))
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.decode().splitlines() == want
+    r = _bamview("-h", "-f", "16", str(bam))
+    assert r.stdout.decode() == text + "".join(l + "\n" for l in want if int(l.split("\t")[1]) & 16)
+    hdr, lines = bam_oracle.view(str(bam))
+    assert lines == want and hdr == text
