@@ -1,9 +1,11 @@
 """CPU-side parity of the host-only drop-ins (tools/bin/PassThroughSamCheck, .stranded; SURVEY §8a
 P1/P2) against the committed outputs of the reference binaries, and against the binaries
 themselves where oracle/_ref is present."""
+import gzip
 import hashlib
 import json
 import os
+import shutil
 import subprocess
 
 import pytest
@@ -301,3 +303,49 @@ def test_bamview_header_and_records_larger_than_a_batch(tmp_path):
     assert r.stdout.decode() == text + "".join(l + "\n" for l in want if int(l.split("\t")[1]) & 16)
     hdr, lines = bam_oracle.view(str(bam))
     assert lines == want and hdr == text
+
+
+# ---- FASTQ -> SAM text: tools/bin/rg_fastq_to_sam, the drop-in for `perl scripts/FastqToSam.pl` (the generator line
+# runRufus.sh:159-161 writes for a FASTQ input)
+F2S = os.path.join(BIN, "rg_fastq_to_sam")
+F2S_PERL = "/root/reference/scripts/FastqToSam.pl"
+
+
+def test_fastq_to_sam_matches_the_reference_script_golden():
+    if not os.path.exists(F2S):
+        pytest.fail("tools/bin/rg_fastq_to_sam is missing: run `make tools`")
+    g = os.path.join(GOLDEN, "fastq_to_sam")
+    r = subprocess.run([F2S, os.path.join(g, "edge.fastq")], capture_output=True)
+    assert r.returncode == 0 and r.stdout == open(os.path.join(g, "edge.sam"), "rb").read()
+    assert subprocess.run([F2S, os.path.join(g, "missing.fastq")], capture_output=True).returncode != 0
+    # through a FIFO, as `perl FastqToSam.pl <(cat X.fastq)` is used, and on into PassThroughSamCheck:
+    # FASTQ -> SAM text -> FASTQ gives back name (first word), sequence and quality of every record
+    fq = gzip.open(os.path.join(GOLDEN, "testRun", "Child.mate1.fastq.gz")).read()
+    r = subprocess.run(["bash", "-c", f"{F2S} <(cat) | {os.path.join(BIN, 'PassThroughSamCheck')} /dev/null"], input=fq, capture_output=True)
+    assert r.returncode == 0
+    lines, back = fq.split(b"\n"), r.stdout.split(b"\n")
+    assert len(back) == len(lines)
+    assert back[1::4] == lines[1::4] and back[3::4] == lines[3::4]
+    assert [l.split()[0] for l in lines[0:-1:4]] == back[0:-1:4]
+
+
+@pytest.mark.skipif(not (os.path.exists(F2S_PERL) and shutil.which("perl")), reason="needs perl and the reference script (build container)")
+@pytest.mark.parametrize("seed", range(4))
+def test_fastq_to_sam_differential_fuzz_against_the_perl_script(seed, tmp_path):
+    import random
+    rnd = random.Random(500 + seed)
+    out = bytearray()
+    for _ in range(rnd.randrange(1, 400)):
+        name = b"".join(rnd.choice([b"@", b"r", b"1", b"/", b" ", b"\t", b"\x0b", b"\x0c", b":", b"x"]) for _ in range(rnd.randrange(0, 12)))
+        eol = rnd.choice([b"\n", b"\n", b"\r\n"])
+        L = rnd.choice([0, 1, 5, 150, 3000])
+        seq = bytes(rnd.choice(b"ACGTNacgt") for _ in range(L))
+        qual = bytes(33 + rnd.randrange(60) for _ in range(L))
+        out += name + eol + seq + eol + b"+" + (name if rnd.random() < 0.3 else b"") + eol + qual + eol
+    if rnd.random() < 0.5:
+        out = out[:rnd.randrange(len(out) + 1)]          # cut anywhere: short last record, no trailing newline
+    fq = tmp_path / "f.fastq"
+    fq.write_bytes(bytes(out))
+    want = subprocess.run(["perl", F2S_PERL, str(fq)], capture_output=True).stdout
+    got = subprocess.run([F2S, str(fq)], capture_output=True)
+    assert got.returncode == 0 and got.stdout == want

@@ -110,6 +110,20 @@ def main():
                      timed(f"{BIN}/rg_bamview view -F 3328 -@ 8 x.bam | {BIN}/PassThroughSamCheck.stranded chr.q st.q", d)))
         for name, s in rows:
             print(f"{name}\t{s:.2f}\t{bases / 1e6 / s:.0f}\t{sam / 1e9 / s:.2f}")
+        # FASTQ-mode generator line (runRufus.sh:159-161): perl scripts/FastqToSam.pl vs tools/bin/rg_fastq_to_sam
+        subprocess.run(f"{BIN}/PassThroughSamCheck chr.f < x.sam > x.fastq", shell=True, check=True, cwd=d)
+        fq = os.path.getsize(os.path.join(d, "x.fastq"))
+        print(f"# FASTQ -> SAM text ({fq / 1e6:.0f} MB FASTQ, {bases / 1e6:.0f} Mbases)")
+        t = timed(f"{BIN}/rg_fastq_to_sam x.fastq > /dev/null", d)
+        print(f"rg_fastq_to_sam x.fastq > /dev/null\t{t:.2f}\t{bases / 1e6 / t:.0f}\t-")
+        pl = "/root/reference/scripts/FastqToSam.pl"
+        if os.path.exists(pl) and shutil.which("perl"):
+            t = timed(f"perl {pl} x.fastq > /dev/null", d)
+            print(f"perl scripts/FastqToSam.pl x.fastq > /dev/null (reference)\t{t:.2f}\t{bases / 1e6 / t:.0f}\t-")
+            same = subprocess.run(f"cmp <({BIN}/rg_fastq_to_sam x.fastq) <(perl {pl} x.fastq)", shell=True, cwd=d, executable="/bin/bash").returncode == 0
+            print(f"# identical output: {same}")
+        t = timed(f"{BIN}/rg_fastq_to_sam x.fastq | {BIN}/PassThroughSamCheck chr.g > /dev/null", d)
+        print(f"rg_fastq_to_sam x.fastq | PassThroughSamCheck (ours) > /dev/null\t{t:.2f}\t{bases / 1e6 / t:.0f}\t-")
         same = all(open(os.path.join(d, f"st.ours.mate{m}.fastq"), "rb").read() == open(os.path.join(d, f"st.reference.mate{m}.fastq"), "rb").read()
                    for m in (1, 2)) if os.path.exists(os.path.join(d, "st.reference.mate1.fastq")) else None
         print(f"# re-paired FASTQ files of ours and the reference identical: {same}")
