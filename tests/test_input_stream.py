@@ -1,0 +1,94 @@
+"""The input side of `jellyfish count` (tools/rg_cli.hpp:read_sequences, tools/rg_bam_input.hpp:read_input), on the
+host: tools/bin/rg_input_to_seq prints the byte stream the counter is handed. FASTA/FASTQ: the parsing rules of
+mer_overlap_sequence_parser.hpp:124-207 (sequence lines joined, one 'N' after every record). BAM: what the reference's
+chain `samtools view -F 3328 X.bam | PassThroughSamCheck` would feed it, produced in process — compared with OUR
+chain (rg_bamview | PassThroughSamCheck, itself pinned to the reference tools in test_tools_host.py)."""
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+BIN = os.path.join(ROOT, "tools", "bin")
+EXE = os.path.join(BIN, "rg_input_to_seq")
+
+
+def stream(path, *args, env=None):
+    r = subprocess.run([EXE, *args, str(path)], capture_output=True, env=env)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def chain(bam, excl=3328):
+    p1 = subprocess.run([os.path.join(BIN, "rg_bamview"), "view", "-F", str(excl), str(bam)], capture_output=True, check=True)
+    p2 = subprocess.run([os.path.join(BIN, "PassThroughSamCheck"), os.devnull], input=p1.stdout, capture_output=True, check=True)
+    return p2.stdout
+
+
+@pytest.fixture(scope="module", autouse=True)
+def exe():
+    if not os.path.exists(EXE):
+        pytest.fail("tools/bin/rg_input_to_seq is missing: run `make tools`")
+
+
+def test_fastq_and_fasta_streams(tmp_path):
+    fq = tmp_path / "a.fq"
+    fq.write_bytes(b"@r1 x\nACGT\n+\nIIII\n@r2\nAC\nGT\nNN\n+r2\nII\nII\nII\n@r3\n\n+\n\n@r4\nacgtn\n+\n@@@@@")
+    assert stream(fq) == b"ACGTN" + b"ACGTNNN" + b"N" + b"acgtnN"
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">s1\nACGT\nAC\n>s2\n>s3\nGGNN\n")
+    assert stream(fa) == b"ACGTACN" + b"GGNN"          # an empty record adds nothing; a record ending in N gets no second N
+    (tmp_path / "empty").write_bytes(b"")
+    assert stream(tmp_path / "empty") == b""
+    (tmp_path / "bad").write_bytes(b"hello\n")
+    assert subprocess.run([EXE, str(tmp_path / "bad")], capture_output=True).returncode != 0
+    # chunked: flushing every few bytes changes nothing
+    assert stream(fq, "-c", "3") == stream(fq)
+
+
+@pytest.mark.parametrize("sample", ["Child", "Mother", "Father"])
+def test_bam_stream_equals_the_chain(sample, tmp_path):
+    bam = os.path.join(GOLDEN, "testRun_bam", sample + ".bam")
+    fq = tmp_path / "chain.fq"
+    fq.write_bytes(chain(bam))
+    want = stream(fq)
+    assert want.count(b"N") >= 2000
+    for args in ((), ("-t", "4"), ("-t", "3", "-c", "1000")):
+        assert stream(bam, *args) == want
+    # a different flag filter through the environment
+    fq.write_bytes(chain(bam, 16))
+    assert stream(bam, env=dict(os.environ, RG_BAM_EXCLUDE_FLAGS="16")) == stream(fq)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_bam_stream_fuzz(seed, tmp_path):
+    """random records (empty SEQ, IUPAC codes, odd lengths, every flag), tiny BGZF blocks"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bam_build import build_bam
+    rnd = random.Random(900 + seed)
+    refs = [("chr1", 100000), ("chr2", 5000)]
+    recs = []
+    for r in range(rnd.randrange(1, 300)):
+        L = rnd.choice([0, 1, 2, 3, 24, 25, 26, 149, 150, 151, 1000])
+        seq = "".join(rnd.choice("ACGT" if rnd.random() < 0.95 else "=ACMGRSVTWYHKDBN") for _ in range(L))
+        qual = None if rnd.random() < 0.1 else "".join(chr(33 + rnd.randrange(41)) for _ in range(L))
+        recs.append((f"q{r}", rnd.choice([0, 16, 83, 99, 147, 163, 256 + 99, 1024 + 83, 2048 + 99, 4]), 0, r, 60,
+                     [(L, "M")] if L else [], 0, r + 100, 250, seq, qual, [("NM", "C", 1)] if rnd.random() < 0.7 else []))
+    bam = tmp_path / "f.bam"
+    bam.write_bytes(build_bam("@HD\tVN:1.6\n", refs, recs, block=rnd.choice([61, 500, 4096, 65280])))
+    want = b"".join((rec[9] or "*").encode() + b"N" for rec in recs if not rec[1] & 3328)
+    assert stream(bam, "-t", str(rnd.choice([1, 2, 6]))) == want
+
+
+def test_bam_errors(tmp_path):
+    data = open(os.path.join(GOLDEN, "testRun_bam", "Child.bam"), "rb").read()
+    (tmp_path / "cut.bam").write_bytes(data[:len(data) // 2])
+    r = subprocess.run([EXE, str(tmp_path / "cut.bam")], capture_output=True)
+    assert r.returncode == 1 and b"truncated" in r.stderr
+    import gzip
+    (tmp_path / "plain.gz").write_bytes(gzip.compress(b"@r\nACGT\n+\nIIII\n"))
+    r = subprocess.run([EXE, str(tmp_path / "plain.gz")], capture_output=True)
+    assert r.returncode == 1 and b"BGZF" in r.stderr      # a gzip file that is not BGZF: refused, not mis-parsed

@@ -108,6 +108,11 @@ def main():
                      timed(f"{BIN}/rg_bamview view -F 3328 -@ 8 x.bam | {BIN}/PassThroughSamCheck chr.p > /dev/null", d)))
         rows.append(("rg_bamview -@ 8 | PassThroughSamCheck.stranded (ours) -> 2 FASTQ files",
                      timed(f"{BIN}/rg_bamview view -F 3328 -@ 8 x.bam | {BIN}/PassThroughSamCheck.stranded chr.q st.q", d)))
+        # the same BAM decoded in process by `jellyfish count X.bam` (tools/rg_bam_input.hpp), up to the bytes handed to the counter
+        for t in (1, 8):
+            rows.append((f"BAM -> counter input in process (rg_input_to_seq -t {t} x.bam > /dev/null)", timed(f"{BIN}/rg_input_to_seq -t {t} x.bam > /dev/null", d)))
+        rows.append(("  the chain up to the same bytes: rg_bamview -@ 8 | PassThroughSamCheck | rg_input_to_seq /dev/stdin",
+                     timed(f"{BIN}/rg_bamview view -F 3328 -@ 8 x.bam | {BIN}/PassThroughSamCheck chr.r | {BIN}/rg_input_to_seq /dev/stdin > /dev/null", d)))
         for name, s in rows:
             print(f"{name}\t{s:.2f}\t{bases / 1e6 / s:.0f}\t{sam / 1e9 / s:.2f}")
         # FASTQ-mode generator line (runRufus.sh:159-161): perl scripts/FastqToSam.pl vs tools/bin/rg_fastq_to_sam

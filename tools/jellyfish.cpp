@@ -4,7 +4,9 @@
 //
 //   jellyfish count [--disk] -m K [-C] [-L min] [-U max] -s SIZE [-t T] [-o OUT] IN...
 //        IN: FASTA/FASTQ files, FIFOs or /dev/stdin. OUT: a .Jhash byte-compatible with
-//        Jellyfish 2.2.5 binary/sorted (count_main.cc:214-354)
+//        Jellyfish 2.2.5 binary/sorted (count_main.cc:214-354). An extension: IN may also be a BAM file, which
+//        is decoded in process on T threads and counted as `samtools view -F 3328 IN | PassThroughSamCheck`
+//        would present it (tools/rg_bam_input.hpp)
 //   jellyfish histo [-f] [-l low] [-h high] [-o OUT] DB          (histo_main.cc:46-110)
 //   jellyfish dump  [-c] [-t] [-L min] [-U max] [-o OUT] DB      (dump_main.cc)
 //   jellyfish query [-s FASTA]... [-o OUT] DB [MER...]           (query_main.cc:44-129)
@@ -19,7 +21,14 @@
 
 #include <sys/stat.h>
 
+#include "rg_bam_input.hpp"
 #include "rg_cli.hpp"
+
+[[noreturn]] void rgbam::fail(const std::string& m) {   // (raised on a pipeline thread: leave without unwinding the others)
+  fprintf(stderr, "jellyfish count: BAM input: %s\n", m.c_str());
+  fflush(stderr);
+  _exit(1);
+}
 
 static const char* next_arg(int& i, int argc, char** argv, const char* opt) {
   if (i + 1 >= argc) die(std::string("Missing argument for ") + opt);
@@ -232,6 +241,7 @@ struct MultiCount {
 // ---------------------------------------------------------------------------- count
 static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   int k = 0, canonical = 0;
+  unsigned threads = 1;
   uint64_t size = 0, lower = 0, upper = 0;
   uint32_t out_counter_len = 4;
   const char* out = "mer_counts.jf";
@@ -243,7 +253,7 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
     else if (!strcmp(a, "--disk") || !strcmp(a, "--text") || !strcmp(a, "--no-write")) { if (a[2] == 't') die("--text output is not supported"); }
     else if (opt_value(a, "-m", "--mer-len", i, argc, argv, &v)) k = atoi(v);
     else if (opt_value(a, "-s", "--size", i, argc, argv, &v)) size = parse_size(v);
-    else if (opt_value(a, "-t", "--threads", i, argc, argv, &v)) {}
+    else if (opt_value(a, "-t", "--threads", i, argc, argv, &v)) threads = (unsigned)std::max(1, std::min(64, atoi(v)));   // BAM inputs decode on this many threads
     else if (opt_value(a, "-o", "--output", i, argc, argv, &v)) out = v;
     else if (opt_value(a, "-L", "--lower-count", i, argc, argv, &v)) lower = parse_size(v);
     else if (opt_value(a, "-U", "--upper-count", i, argc, argv, &v)) upper = parse_size(v);
@@ -276,7 +286,7 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
     for (const char* path : inputs) {
       FILE* f = fopen(path, "rb");
       if (!f) die(std::string("Failed to open input file '") + path + "'");
-      read_sequences(f, path, fill, chunk, flush);
+      read_input(f, path, fill, chunk, flush, threads);
       fclose(f);
     }
     if (!fill.empty()) flush(fill);
@@ -315,7 +325,7 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   for (const char* path : inputs) {
     FILE* f = fopen(path, "rb");
     if (!f) die(std::string("Failed to open input file '") + path + "'");
-    read_sequences(f, path, fill, chunk, flush);
+    read_input(f, path, fill, chunk, flush, threads);
     fclose(f);
   }
   if (!fill.empty()) flush(fill);

@@ -137,8 +137,7 @@ struct LineReader {
 // (:124-153). flush(out) is called whenever `out` holds at least `chunk` bytes (read again after every flush: the
 // caller may grow it).
 template <typename Buf, typename Flush>
-static inline void read_sequences(FILE* f, const char* path, Buf& out, const size_t& chunk, Flush&& flush) {
-  LineReader lr(f);
+static inline void read_sequences(LineReader& lr, const char* path, Buf& out, const size_t& chunk, Flush&& flush) {
   const int c0 = lr.peek();
   if (c0 == EOF) return;
   if (c0 != '>' && c0 != '@') die(std::string("Unsupported format in '") + path + "'");
@@ -171,4 +170,9 @@ static inline void read_sequences(FILE* f, const char* path, Buf& out, const siz
       if (out.size() >= chunk) flush(out);
     }
   }
+}
+template <typename Buf, typename Flush>
+static inline void read_sequences(FILE* f, const char* path, Buf& out, const size_t& chunk, Flush&& flush) {
+  LineReader lr(f);
+  read_sequences(lr, path, out, chunk, flush);
 }
