@@ -300,6 +300,11 @@ int main(int argc, char** argv) {
   }
   log.str("SC = "); log.d(SC); log.str(" vlaue = "); log.d(SCvalue); log.nl();
   const int rawSC = (int)SC;
+  if (!((double)N / (SC * 1.1) > 2)) {   // the model needs at least the het, 1-copy and 2-copy columns (the reference reads out of bounds here)
+    log.str("ERROR the histogram is too short to fit a model\n");
+    flush_log();
+    return 1;
+  }
   stdvalue = SCvalue * exp(-.5);
   for (i = (long)SC; i < N; i++)
     if (histo[i] - stdvalue < 0) break;

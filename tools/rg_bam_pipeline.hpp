@@ -162,6 +162,7 @@ struct Pipeline {
           m.clen = (uint32_t)clen;
           m.crc = le32(h + bsize + 1 - 8);
           m.isize = le32(h + bsize + 1 - 4);
+          if (m.isize > (1u << 16)) fail("corrupt BGZF block (inflated size above 64 KiB)");
           m.out = out;
           out += m.isize;
           b.members.push_back(m);
