@@ -96,7 +96,10 @@ int main(int argc, char** argv) {
   if (!set) die(rg_last_error());
   printf("Mutant k-mers loaded: %llu\n", (unsigned long long)rg_set_size(set));
 
-  const uint64_t batch_reads = 1u << 20;
+  // 64 Ki reads (pairs) per call: ~40 MB of host buffers that stay resident and are reused, instead of 1 Mi reads whose
+  // growing vectors fault in 1.2 GB of fresh pages per batch (measured on the host side alone, 500 k pairs:
+  // 1.19 s at 1 Mi, 0.46 s at 64 Ki; profiles/r2_host_ingest.txt); still ~20 Mbases per kernel launch
+  const uint64_t batch_reads = 1u << 16;
   uint64_t n_in = 0, n_out = 0;
   LineReader r1(f1);
   Batch b1;
