@@ -92,3 +92,62 @@ def test_bam_errors(tmp_path):
     (tmp_path / "plain.gz").write_bytes(gzip.compress(b"@r\nACGT\n+\nIIII\n"))
     r = subprocess.run([EXE, str(tmp_path / "plain.gz")], capture_output=True)
     assert r.returncode == 1 and b"BGZF" in r.stderr      # a gzip file that is not BGZF: refused, not mis-parsed
+
+
+# ---- the paired input of RUFUS.Filter: two FASTQ files (the chain's re-paired mates) or the BAM itself, re-paired in
+# process (tools/rg_bam_pairs.hpp); tools/bin/rg_pairs_check writes the pairs and a digest of the batch arrays
+PAIRS = os.path.join(BIN, "rg_pairs_check")
+
+
+def stranded_chain(bam, stub, excl=3328):
+    p1 = subprocess.run([os.path.join(BIN, "rg_bamview"), "view", "-F", str(excl), str(bam)], capture_output=True, check=True)
+    subprocess.run([os.path.join(BIN, "PassThroughSamCheck.stranded"), os.devnull, str(stub)], input=p1.stdout, capture_output=True, check=True)
+    return open(f"{stub}.mate1.fastq", "rb").read(), open(f"{stub}.mate2.fastq", "rb").read()
+
+
+def pairs_check(*args):
+    r = subprocess.run([PAIRS, *[str(a) for a in args]], capture_output=True)
+    assert r.returncode == 0, r.stderr
+    stub = str(args[-1])
+    return open(stub + ".mate1.fastq", "rb").read(), open(stub + ".mate2.fastq", "rb").read(), r.stdout
+
+
+@pytest.mark.parametrize("sample", ["Child", "Mother"])
+def test_bam_pairs_equal_the_repaired_fastq_files_of_the_chain(sample, tmp_path):
+    bam = os.path.join(GOLDEN, "testRun_bam", sample + ".bam")
+    m1, m2 = stranded_chain(bam, tmp_path / "chain")
+    assert m1.count(b"\n") >= 4000
+    f1, f2, digest_fastq = pairs_check("-b", "300", tmp_path / "chain.mate1.fastq", tmp_path / "chain.mate2.fastq", tmp_path / "viafastq")
+    assert (f1, f2) == (m1, m2)
+    for args in (("-b", "300"), ("-b", "300", "-t", "5")):
+        b1, b2, digest_bam = pairs_check(*args, bam, tmp_path / "direct")
+        assert (b1, b2) == (m1, m2)
+        assert digest_bam == digest_fastq          # the arrays handed to rg_filter_pairs, batch by batch
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_bam_pairs_fuzz(seed, tmp_path):
+    """mates in any order and distance, reverse strands, IUPAC codes (dropped on the reverse strand), empty SEQ, absent
+    QUAL, odd lengths, secondary/duplicate/supplementary records, reads whose mate never comes"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bam_build import build_bam
+    rnd = random.Random(4000 + seed)
+    refs = [("chr1", 100000)]
+    recs = []
+    for p in range(rnd.randrange(1, 200)):
+        mates = []
+        for m in range(rnd.choice([1, 2, 2, 2, 3])):
+            L = rnd.choice([0, 1, 2, 25, 26, 149, 150, 151])
+            seq = "".join(rnd.choice("ACGT" if rnd.random() < 0.9 else "=ACMGRSVTWYHKDBN") for _ in range(L))
+            qual = None if rnd.random() < 0.1 else "".join(chr(33 + rnd.randrange(41)) for _ in range(L))
+            flag = rnd.choice([65, 81, 97, 113, 129, 145, 161, 177, 99, 147, 83, 163, 256 + 99, 1024 + 147, 2048 + 83])
+            mates.append((f"pair{p}", flag, 0, p, 60, [(L, "M")] if L else [], 0, p + 200, 300, seq, qual, [("NM", "C", 0)]))
+        recs += mates
+    rnd.shuffle(recs)
+    bam = tmp_path / "f.bam"
+    bam.write_bytes(build_bam("@HD\tVN:1.6\n", refs, recs, block=rnd.choice([61, 700, 65280])))
+    m1, m2 = stranded_chain(bam, tmp_path / "chain")
+    _, _, digest_fastq = pairs_check("-b", "7", tmp_path / "chain.mate1.fastq", tmp_path / "chain.mate2.fastq", tmp_path / "viafastq")
+    b1, b2, digest_bam = pairs_check("-b", "7", "-t", rnd.choice([1, 3]), bam, tmp_path / "direct")
+    assert (b1, b2) == (m1, m2)
+    assert digest_bam == digest_fastq

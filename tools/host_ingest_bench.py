@@ -113,6 +113,14 @@ def main():
             rows.append((f"BAM -> counter input in process (rg_input_to_seq -t {t} x.bam > /dev/null)", timed(f"{BIN}/rg_input_to_seq -t {t} x.bam > /dev/null", d)))
         rows.append(("  the chain up to the same bytes: rg_bamview -@ 8 | PassThroughSamCheck | rg_input_to_seq /dev/stdin",
                      timed(f"{BIN}/rg_bamview view -F 3328 -@ 8 x.bam | {BIN}/PassThroughSamCheck chr.r | {BIN}/rg_input_to_seq /dev/stdin > /dev/null", d)))
+        # the paired input of RUFUS.Filter, up to the batch arrays handed to rg_filter_pairs (rg_pairs_check -n: no files written)
+        subprocess.run(f"{BIN}/PassThroughSamCheck.stranded chr.s pairs < x.sam", shell=True, check=True, cwd=d)
+        rows.append(("read pull input, the chain: rg_bamview -@ 8 | PassThroughSamCheck.stranded -> 2 FIFOs -> RUFUS.Filter's reader",
+                     timed(f"rm -f q.mate1.fastq q.mate2.fastq; mkfifo q.mate1.fastq q.mate2.fastq; ({BIN}/rg_bamview view -F 3328 -@ 8 x.bam | "
+                           f"{BIN}/PassThroughSamCheck.stranded chr.t q > /dev/null &) ; {BIN}/rg_pairs_check -n q.mate1.fastq q.mate2.fastq qq > /dev/null", d)))
+        for t in (1, 8):
+            rows.append((f"read pull input in process (RUFUS.Filter HashList x.bam x.bam ...: rg_pairs_check -n -t {t} x.bam)",
+                         timed(f"{BIN}/rg_pairs_check -n -t {t} x.bam pp > /dev/null", d)))
         for name, s in rows:
             print(f"{name}\t{s:.2f}\t{bases / 1e6 / s:.0f}\t{sam / 1e9 / s:.2f}")
         # FASTQ-mode generator line (runRufus.sh:159-161): perl scripts/FastqToSam.pl vs tools/bin/rg_fastq_to_sam

@@ -9,11 +9,23 @@
 //        -> OutStub.Mutations.fastq (read name + ":MH<hits>")
 // The two mate files may be FIFOs: records are read 4 lines at a time, alternating between the
 // files, like the reference does (a lock-step reader never blocks the producer pair).
+// An extension (paired tool): when Mate1.fq is a BAM file (and Mate2.fq names the same file or is "-"), the BAM is
+// decoded and re-paired in process on `Threads` threads — the pairs PassThroughSamCheck.stranded would have written
+// to the two files, in the same order (tools/rg_bam_pairs.hpp).
 // Like the reference, problems opening files are reported on stdout and the exit code stays 0
 // for the cases the reference returns 0 for (runRufus.sh only looks at the outputs).
 #include "rg_cli.hpp"
 
 #include "rg_fastq_batch.hpp"
+#ifndef RG_SINGLE
+#include "rg_bam_pairs.hpp"
+
+[[noreturn]] void rgbam::fail(const std::string& m) {   // (raised on a pipeline thread: leave without unwinding the others)
+  fprintf(stderr, "RUFUS.Filter: BAM input: %s\n", m.c_str());
+  fflush(stderr);
+  _exit(1);
+}
+#endif
 
 static std::string slurp(const char* path) {
   FILE* f = fopen(path, "rb");
@@ -48,6 +60,8 @@ int main(int argc, char** argv) {
   const int k = atoi(argv[a++]);
   const int minq = atoi(argv[a++]);
   const int thresh = atoi(argv[a++]);
+  const int threads = atoi(argv[a++]);   // (BAM input: decode threads; the GPU needs none)
+  (void)threads;
   if (k < 1 || k > 32) die("HashSize must be 1..32");
 
   FILE* hf = fopen(hashlist, "rb");
@@ -60,8 +74,8 @@ int main(int argc, char** argv) {
   FILE* f1 = fopen(!strcmp(in1, "stdin") ? "/dev/stdin" : in1, "rb");
 #else
   FILE* f1 = fopen(in1, "rb");
-  FILE* f2 = fopen(in2, "rb");
-  if (!f2) {
+  FILE* f2 = !strcmp(in2, "-") ? nullptr : fopen(in2, "rb");
+  if (!f2 && strcmp(in2, "-") != 0) {
     printf("Error, MutFile2 could not be opened");
     return 0;
   }
@@ -104,8 +118,25 @@ int main(int argc, char** argv) {
   LineReader r1(f1);
   Batch b1;
 #ifndef RG_SINGLE
-  LineReader r2(f2);
+  LineReader r2(f2 ? f2 : f1);   // (f2 is absent only for a BAM input, where r2 is never read)
   Batch b2;
+  const bool is_bam = r1.peek() == 0x1f;   // (the first read of mate 1, which the loop below would do next anyway)
+  if (!f2 && !is_bam) {
+    printf("Error, MutFile2 could not be opened");
+    return 0;
+  }
+  bool first = true;
+  auto filter_and_write = [&](Batch& x, Batch& y) {
+    std::vector<uint8_t> keep(x.n());
+    check(rg_filter_pairs(set, x.seq.data(), x.qual.data(), x.offs.data(), y.seq.data(), y.qual.data(), y.offs.data(), x.n(),
+                          minq, thresh, keep.data()), "filter");
+    for (uint64_t i = 0; i < x.n(); ++i)
+      if (keep[i]) {
+        fwrite(x.text.data() + x.text_offs[i], 1, x.text_offs[i + 1] - x.text_offs[i], o1);
+        fwrite(y.text.data() + y.text_offs[i], 1, y.text_offs[i + 1] - y.text_offs[i], o2);
+        ++n_out;
+      }
+  };
 #endif
   for (bool more = true; more;) {
     b1.clear();
@@ -124,17 +155,21 @@ int main(int argc, char** argv) {
       }
 #else
     b2.clear();
-    more = read_pair_batch(r1, r2, b1, b2, batch_reads);
+    if (first && is_bam) {                 // a BAM file: every pair comes from it, re-paired in process
+      rgbam::bam_pairs(f1, r1.buf.data() + r1.pos, r1.len - r1.pos, (unsigned)(threads > 0 ? threads : 1), b1, b2, batch_reads,
+                       [&](Batch& x, Batch& y) {
+                         filter_and_write(x, y);
+                         n_in += x.n();
+                         x.clear();
+                         y.clear();
+                       });
+      more = false;
+    } else {
+      more = read_pair_batch(r1, r2, b1, b2, batch_reads);
+    }
+    first = false;
     if (b1.n() == 0) break;
-    std::vector<uint8_t> keep(b1.n());
-    check(rg_filter_pairs(set, b1.seq.data(), b1.qual.data(), b1.offs.data(), b2.seq.data(), b2.qual.data(),
-                          b2.offs.data(), b1.n(), minq, thresh, keep.data()), "filter");
-    for (uint64_t i = 0; i < b1.n(); ++i)
-      if (keep[i]) {
-        fwrite(b1.text.data() + b1.text_offs[i], 1, b1.text_offs[i + 1] - b1.text_offs[i], o1);
-        fwrite(b2.text.data() + b2.text_offs[i], 1, b2.text_offs[i + 1] - b2.text_offs[i], o2);
-        ++n_out;
-      }
+    filter_and_write(b1, b2);
 #endif
     n_in += b1.n();
   }
@@ -142,7 +177,7 @@ int main(int argc, char** argv) {
   fclose(f1);
 #ifndef RG_SINGLE
   fclose(o2);
-  fclose(f2);
+  if (f2) fclose(f2);
 #endif
   printf("Read in %llu records: Found %llu\n\nDone running RUFUS.Filter (GPU)\n", (unsigned long long)n_in,
          (unsigned long long)n_out);
