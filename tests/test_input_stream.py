@@ -96,7 +96,7 @@ def test_bam_errors(tmp_path):
 
 # ---- the paired input of RUFUS.Filter: two FASTQ files (the chain's re-paired mates) or the BAM itself, re-paired in
 # process (tools/rg_bam_pairs.hpp); tools/bin/rg_pairs_check writes the pairs and a digest of the batch arrays
-PAIRS = os.path.join(BIN, "rg_pairs_check")
+PAIRS = os.environ.get("RG_PAIRS_CHECK", os.path.join(BIN, "rg_pairs_check"))   # (override: a sanitizer build)
 
 
 def stranded_chain(bam, stub, excl=3328):
@@ -151,3 +151,26 @@ def test_bam_pairs_fuzz(seed, tmp_path):
     b1, b2, digest_bam = pairs_check("-b", "7", "-t", rnd.choice([1, 3]), bam, tmp_path / "direct")
     assert (b1, b2) == (m1, m2)
     assert digest_bam == digest_fastq
+
+
+def test_bam_pairs_with_thousands_of_parked_reads(tmp_path):
+    """all first mates, then all second mates in another order: the parked-read table grows several times and
+    every deletion shifts its probe sequences"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from bam_build import build_bam
+    rnd = random.Random(77)
+    n = 6000
+    def rec(p, flag):
+        L = rnd.choice([50, 100, 151])
+        return (f"r{p % 97}_{p}", flag, 0, p, 60, [(L, "M")], 0, p + 200, 300, "".join(rnd.choice("ACGT") for _ in range(L)),
+                "".join(chr(33 + rnd.randrange(41)) for _ in range(L)), [("NM", "C", 0)])
+    first = [rec(p, rnd.choice([99, 83])) for p in range(n)]
+    second = [rec(p, rnd.choice([147, 163])) for p in range(n)]
+    rnd.shuffle(second)
+    bam = tmp_path / "f.bam"
+    bam.write_bytes(build_bam("@HD\tVN:1.6\n", [("chr1", 10 ** 6)], first + second, block=65280))
+    m1, m2 = stranded_chain(bam, tmp_path / "chain")
+    assert m1.count(b"\n") == 4 * n
+    _, _, digest_fastq = pairs_check("-b", "1000", tmp_path / "chain.mate1.fastq", tmp_path / "chain.mate2.fastq", tmp_path / "viafastq")
+    b1, b2, digest_bam = pairs_check("-b", "1000", "-t", "4", bam, tmp_path / "direct")
+    assert (b1, b2) == (m1, m2) and digest_bam == digest_fastq

@@ -4,7 +4,7 @@
 // to STUB.mate1.fastq / STUB.mate2.fastq and prints a digest of the arrays a batch hands to rg_filter_pairs
 // (sequences, qualities, offsets, name lengths), batch by batch.
 //   rg_pairs_check [-t THREADS] [-b BATCH_PAIRS] [-n] MATE1.fastq MATE2.fastq STUB
-//   rg_pairs_check [-t THREADS] [-b BATCH_PAIRS] [-n] X.bam STUB          (-n: no files, digest only)
+//   rg_pairs_check [-t THREADS] [-b BATCH_PAIRS] [-n] [-q] X.bam STUB     (-n: no files, digest only; -q: no digest either)
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -28,12 +28,13 @@ static uint64_t fnv(uint64_t h, const void* p, size_t n) {   // (zlib's CRC-32 o
 int main(int argc, char** argv) {
   unsigned threads = 1;
   uint64_t batch = 1u << 16;
-  bool write_files = true;
+  bool write_files = true, digest = true;
   std::vector<const char*> pos;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "-t") && i + 1 < argc) threads = (unsigned)atoi(argv[++i]);
     else if (!strcmp(argv[i], "-b") && i + 1 < argc) batch = strtoull(argv[++i], nullptr, 10);
     else if (!strcmp(argv[i], "-n")) write_files = false;   // timing: digest only
+    else if (!strcmp(argv[i], "-q")) digest = false;        // timing: not even the digest (what is left is the reader)
     else pos.push_back(argv[i]);
   }
   if (pos.size() != 2 && pos.size() != 3) return 2;
@@ -48,6 +49,7 @@ int main(int argc, char** argv) {
   b2.clear();
   auto take = [&](Batch& x, Batch& y) {
     for (Batch* b : {&x, &y}) {
+      if (!digest) break;
       h = fnv(h, b->seq.data(), b->seq.size());
       h = fnv(h, b->qual.data(), b->qual.size());
       h = fnv(h, b->offs.data(), b->offs.size() * 8);
