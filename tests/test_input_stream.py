@@ -174,3 +174,51 @@ def test_bam_pairs_with_thousands_of_parked_reads(tmp_path):
     _, _, digest_fastq = pairs_check("-b", "1000", tmp_path / "chain.mate1.fastq", tmp_path / "chain.mate2.fastq", tmp_path / "viafastq")
     b1, b2, digest_bam = pairs_check("-b", "1000", "-t", "4", bam, tmp_path / "direct")
     assert (b1, b2) == (m1, m2) and digest_bam == digest_fastq
+
+
+# ---- `jellyfish count -t T reads.fastq`: the scan of a regular FASTQ file on several threads (tools/rg_fastq_parallel.hpp)
+def par_env(segment):
+    return dict(os.environ, RG_PARALLEL_FASTQ_MIN_BYTES="1", RG_PARALLEL_FASTQ_SEGMENT=str(segment))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_parallel_fastq_scan_equals_the_serial_reader(seed, tmp_path):
+    """segments of 1-5 kB over records of every length: quality lines starting with '@' or '+', N bases, CRLF, a last
+    record without a newline or cut short"""
+    rnd = random.Random(6000 + seed)
+    eol = b"\r\n" if seed == 4 else b"\n"
+    out = bytearray()
+    for r in range(rnd.randrange(50, 600)):
+        L = rnd.choice([0, 1, 24, 25, 100, 150, 151, 2000])
+        seq = bytes(rnd.choice(b"ACGTN" if rnd.random() < 0.05 else b"ACGT") for _ in range(L))
+        qual = bytes(rnd.choice(b"@+IJF#,5") for _ in range(L))
+        out += b"@read%d extra" % r + eol + seq + eol + (b"+" if rnd.random() < 0.7 else b"+read%d" % r) + eol + qual + eol
+    data = bytes(out)
+    if seed == 1:
+        data = data[:-len(eol)]                    # no trailing newline
+    if seed == 2:
+        data = data[:len(data) - rnd.randrange(1, 150)]    # cut inside the last record
+    fq = tmp_path / "a.fq"
+    fq.write_bytes(data)
+    want = stream(fq)                              # -t 1: the serial reader
+    for seg in (1024, 3000, 5000, 10 ** 6):
+        assert stream(fq, "-t", "3", env=par_env(seg)) == want
+    assert stream(fq, "-t", "8", "-c", "4096", env=par_env(2048)) == want
+
+
+def test_parallel_fastq_scan_refuses_wrapped_records_and_leaves_fifos_to_the_serial_reader(tmp_path):
+    wrapped = tmp_path / "w.fq"
+    wrapped.write_bytes(b"@r1\nACGT\nACGT\n+\nIIII\nIIII\n" * 400)
+    want = stream(wrapped)                          # the serial reader joins the lines
+    assert want == b"ACGTACGTN" * 400
+    r = subprocess.run([EXE, "-t", "4", str(wrapped)], capture_output=True, env=par_env(1024))
+    assert r.returncode == 1 and b"run with -t 1" in r.stderr
+    # a FIFO is not a regular file: serial reader whatever -t says
+    plain = tmp_path / "p.fq"
+    plain.write_bytes(b"@r\nACGTA\n+\nIIIII\n" * 1000)
+    r = subprocess.run(["bash", "-c", f"{EXE} -t 4 <(cat {plain})"], capture_output=True, env=par_env(1024))
+    assert r.returncode == 0 and r.stdout == b"ACGTAN" * 1000
+    # FASTA keeps the serial reader too
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">s\nACGT\nACGT\n" * 300)
+    assert stream(fa, "-t", "4", env=par_env(1024)) == b"ACGTACGTN" * 300

@@ -135,6 +135,9 @@ def main():
             print(f"perl scripts/FastqToSam.pl x.fastq > /dev/null (reference)\t{t:.2f}\t{bases / 1e6 / t:.0f}\t-")
             same = subprocess.run(f"cmp <({BIN}/rg_fastq_to_sam x.fastq) <(perl {pl} x.fastq)", shell=True, cwd=d, executable="/bin/bash").returncode == 0
             print(f"# identical output: {same}")
+        for th in (1, 2, 4, 6):
+            t = timed(f"{BIN}/rg_input_to_seq -t {th} x.fastq > /dev/null", d)
+            print(f"FASTQ file -> counter input (`jellyfish count -t {th} x.fastq`: rg_input_to_seq -t {th})\t{t:.2f}\t{bases / 1e6 / t:.0f}\t-")
         t = timed(f"{BIN}/rg_fastq_to_sam x.fastq | {BIN}/PassThroughSamCheck chr.g > /dev/null", d)
         print(f"rg_fastq_to_sam x.fastq | PassThroughSamCheck (ours) > /dev/null\t{t:.2f}\t{bases / 1e6 / t:.0f}\t-")
         same = all(open(os.path.join(d, f"st.ours.mate{m}.fastq"), "rb").read() == open(os.path.join(d, f"st.reference.mate{m}.fastq"), "rb").read()

@@ -9,6 +9,7 @@
 #pragma once
 #include "rg_bam_pipeline.hpp"
 #include "rg_cli.hpp"
+#include "rg_fastq_parallel.hpp"
 
 namespace rgbam {
 
@@ -66,13 +67,16 @@ static inline void bam_sequences(FILE* f, const char* head, size_t head_len, Buf
 
 }  // namespace rgbam
 
-// FASTA / FASTQ / BAM by the first byte of the input (0x1f = a gzip member: BGZF)
+// FASTA / FASTQ / BAM by the first byte of the input (0x1f = a gzip member: BGZF); `threads` serves the BAM decode
+// and the scan of a large regular FASTQ file
 template <typename Buf, typename Flush>
 static inline void read_input(FILE* f, const char* path, Buf& out, const size_t& chunk, Flush&& flush, unsigned threads) {
   LineReader lr(f);
-  if (lr.peek() == 0x1f) {
+  const int c0 = lr.peek();
+  if (c0 == 0x1f) {
     rgbam::bam_sequences(f, lr.buf.data() + lr.pos, lr.len - lr.pos, out, chunk, flush, threads);
     return;
   }
+  if (rgfq::read_fastq_parallel(f, path, c0, out, chunk, flush, threads)) return;   // a large regular FASTQ file, -t > 1
   read_sequences(lr, path, out, chunk, flush);
 }
