@@ -108,3 +108,22 @@ def test_rufus_filter_single_marks_the_names(rec, tmp_path):
     assert r.returncode == 0 and b"n=10 minq=15" in r.stderr
     out = open(os.path.join(work, "single.Mutations.fastq"), "rb").read()
     assert out == b"".join(b"@r%d x:MH%d\nACGTACGTAC\n+\nIIIIIIIIII\n" % (i, i % 4) for i in range(10) if i % 4 >= 2)
+
+
+def test_a_batch_that_inflates_to_many_megabytes_is_pushed_in_bounded_chunks(rec, tmp_path):
+    """200 000 identical reads compress 200:1: one pipeline batch holds all of them (57 MB inflated, 30 MB of bases). The chunk handed
+    over must still stay near the chunk size — the multi-GPU count stages it in a device buffer of chunk + 16 MB."""
+    import struct
+    from bam_build import bgzf
+    seq = "ACGTTGCA" * 18 + "ACGTAC"                # 150 bases
+    packed = bytes((("=ACMGRSVTWYHKDBN".index(seq[i]) << 4) | "=ACMGRSVTWYHKDBN".index(seq[i + 1])) for i in range(0, 150, 2))
+    r = struct.pack("<iiBBHHHiiii", 0, 100, 3, 60, 4680, 1, 99, 150, 0, 400, 300) + b"rd\0" + struct.pack("<I", (150 << 4)) + packed + bytes([30] * 150)
+    text = "@HD\tVN:1.6\n"
+    body = b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", 1) + struct.pack("<i", 5) + b"chr1\0" + struct.pack("<i", 10 ** 6)
+    n = 200000
+    bam = tmp_path / "same.bam"
+    bam.write_bytes(bgzf(body + (struct.pack("<i", len(r)) + r) * n, 65280))
+    assert os.path.getsize(bam) < (1 << 20)
+    got, sizes = count(rec, tmp_path, bam, threads=2)
+    assert got == (seq.encode() + b"N") * n
+    assert sizes[0] < (8 << 20) + (5 << 20) and max(sizes) < (32 << 20) + (5 << 20)

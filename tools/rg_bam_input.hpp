@@ -59,10 +59,7 @@ static inline void bam_sequences(FILE* f, const char* head, size_t head_len, Buf
   pl.req = flags_from_env("RG_BAM_REQUIRE_FLAGS", 0);
   pl.render = sequence_record;
   setvbuf(f, nullptr, _IONBF, 0);   // the pipeline's reader asks for a megabyte at a time
-  pl.run([&](const char* p, size_t n) {
-    out.append(p, n);
-    if (out.size() >= chunk) flush(out);
-  });
+  pl.run([&](const char* p, size_t n) { rgfq::append_in_pieces(p, n, out, chunk, flush); });
 }
 
 }  // namespace rgbam

@@ -162,6 +162,24 @@ struct Scanner {
   }
 };
 
+// Appends a run of "bases + 'N'" records to the chunk in pieces of ~4 MB, flushing whenever the chunk is full, so that a
+// chunk never grows far beyond `chunk` (the multi-GPU count stages a chunk in a device buffer of chunk + 16 MB). A piece
+// ends behind an 'N': no k-mer spans one, so none is lost between two chunks.
+template <typename Buf, typename Flush>
+static inline void append_in_pieces(const char* p, size_t n, Buf& out, const size_t& chunk, Flush&& flush) {
+  for (size_t at = 0; at < n;) {
+    size_t take = std::min(n - at, (size_t)(4u << 20));
+    if (at + take < n) {
+      const char* cut = (const char*)memrchr(p + at, 'N', take);
+      if (!cut) cut = (const char*)memchr(p + at + take, 'N', n - at - take);
+      take = cut ? (size_t)(cut - (p + at)) + 1 : n - at;
+    }
+    out.append(p + at, take);
+    at += take;
+    if (out.size() >= chunk) flush(out);
+  }
+}
+
 // true: the whole file has been read and flushed through (out, flush). false: not applicable (not a regular file,
 // too small, one thread, not FASTQ) — nothing was consumed, use the serial reader.
 template <typename Buf, typename Flush>
@@ -217,18 +235,7 @@ static inline bool read_fastq_parallel(FILE* f, const char* path, int first_byte
       ++consumed;
       cv.notify_all();
     }
-    // in pieces, so that a flush happens where the serial reader's would (a chunk never grows far beyond `chunk`)
-    for (size_t at = 0; at < seq.size();) {
-      size_t take = std::min(seq.size() - at, (size_t)(4u << 20));
-      if (at + take < seq.size()) {           // cut only behind an 'N': no k-mer spans one, so none is lost between two chunks
-        const char* cut = (const char*)memrchr(seq.data() + at, 'N', take);
-        if (!cut) cut = (const char*)memchr(seq.data() + at + take, 'N', seq.size() - at - take);
-        take = cut ? (size_t)(cut - (seq.data() + at)) + 1 : seq.size() - at;
-      }
-      out.append(seq.data() + at, take);
-      at += take;
-      if (out.size() >= chunk) flush(out);
-    }
+    append_in_pieces(seq.data(), seq.size(), out, chunk, flush);
   }
   for (auto& th : pool) th.join();
   return true;
