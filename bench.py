@@ -120,23 +120,50 @@ def make_data(args, rank, world):
 
 
 # --------------------------------------------------------------------------- CPU reference
-def cpu_reference_pass(trio, n_pairs, workdir, threads):
+def have_reference_binaries():
+    """oracle/_ref holds the reference's own executables (built by oracle/Makefile where /root/reference exists)"""
+    refbin = os.path.join(ROOT, "oracle", "_ref")
+    return os.path.exists(os.path.join(refbin, "jellyfish")) and os.path.exists(os.path.join(refbin, "RUFUS.Filter"))
+
+
+def write_reference_fastq(trio, n_pairs, fqdir):
+    """the FASTQ files the reference's commands read (untimed; written once per run): first n_pairs pairs of every sample"""
+    from rufus_b200 import synth
+    fq = {}
+    for s in synth.SAMPLES:
+        s1, q1, s2, q2 = (a[:n_pairs] for a in trio[s])
+        p1, p2 = os.path.join(fqdir, f"{s}.m1.fq"), os.path.join(fqdir, f"{s}.m2.fq")
+        open(p1, "wb").write(synth.fastq_bytes(s1, q1, prefix=s[0]))
+        open(p2, "wb").write(synth.fastq_bytes(s2, q2, prefix=s[0]))
+        fq[s] = (p1, p2)
+    return fq
+
+
+def reference_output_digests(workdir):
+    """order-free digests of what the reference's commands left in `workdir` (the same three digests as
+    rufus_b200/workload.py: subject histo file, sorted HashList, sorted pulled mate-1 names)"""
+    import hashlib
+    from rufus_b200 import workload
+    hl = sorted(open(os.path.join(workdir, "HashList")).read().splitlines())
+    names = sorted(open(os.path.join(workdir, "out.Mutations.Mate1.fastq")).read().splitlines()[0::4])
+    return {"histo_md5": hashlib.md5(open(os.path.join(workdir, "Child.Jhash.histo"), "rb").read()).hexdigest(),
+            "hashlist_md5": workload._md5(hl), "hashlist_lines": len(hl),
+            "pulled_md5": workload._md5(names), "pulled_pairs": len(names)}
+
+
+def cpu_reference_pass(trio, n_pairs, workdir, threads, fq=None):
     """One pass of the reference's own commands on the first n_pairs pairs
-    of every sample. Returns (seconds, bases, kind, info)."""
+    of every sample (FASTQ files `fq` from write_reference_fastq, written here when absent: untimed either way).
+    Returns (seconds, bases, kind, info)."""
     from rufus_b200 import synth
     refbin = os.path.join(ROOT, "oracle", "_ref")
     jf = os.path.join(refbin, "jellyfish")
     have_ref = os.path.exists(jf) and os.path.exists(os.path.join(refbin, "RUFUS.Filter"))
     bases = 0
     if have_ref:
-        fq = {}
-        for s in synth.SAMPLES:     # untimed: materialise the FASTQ files the reference reads
-            s1, q1, s2, q2 = (a[:n_pairs] for a in trio[s])
-            p1, p2 = os.path.join(workdir, f"{s}.m1.fq"), os.path.join(workdir, f"{s}.m2.fq")
-            open(p1, "wb").write(synth.fastq_bytes(s1, q1, prefix=s[0]))
-            open(p2, "wb").write(synth.fastq_bytes(s2, q2, prefix=s[0]))
-            fq[s] = (p1, p2)
-            bases += 2 * n_pairs * READ_LEN
+        if fq is None:
+            fq = write_reference_fastq(trio, n_pairs, workdir)
+        bases = len(synth.SAMPLES) * 2 * n_pairs * READ_LEN
         t0 = time.time()
         T = max(1, threads)
         for s in synth.SAMPLES:
@@ -153,9 +180,8 @@ def cpu_reference_pass(trio, n_pairs, workdir, threads):
         subprocess.run(f"{refbin}/RUFUS.Filter HashList {fq['Child'][0]} {fq['Child'][1]} out {K} {MINQ} {THRESH} {T} "
                        "> /dev/null", shell=True, check=True, cwd=workdir, executable="/bin/bash")
         dt = time.time() - t0
-        n_hash = sum(1 for _ in open(os.path.join(workdir, "HashList")))
-        n_pull = sum(1 for _ in open(os.path.join(workdir, "out.Mutations.Mate1.fastq"))) // 4
-        return dt, bases, "reference", {"hashlist": n_hash, "pulled": n_pull, "cores": T}
+        dg = reference_output_digests(workdir)
+        return dt, bases, "reference", {"hashlist": dg["hashlist_lines"], "pulled": dg["pulled_pairs"], "cores": T, "digests": dg}
     # fall back to the C port of the reference algorithm (single thread)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -246,26 +272,77 @@ def cli_leg(trio):
     return out
 
 
+def reference_sample_pairs(args, world):
+    """pairs/sample the reference's commands are run on. N = 1: the WHOLE configured workload (C2: 500 k pairs per
+    sample, ~8 s per pass on 16 cores), so the reference arm and the CUDA arm run the same config at the same size and
+    the reference's outputs can be checked against the committed digests in the same run. N > 1: the union of the rank
+    slices is N times that, so the arm stays a bounded sample (--ref-pairs, default 100 k pairs of rank 0's slice)."""
+    if args.ref_pairs > 0:
+        return min(args.ref_pairs, args.pairs)
+    return args.pairs if world == 1 and have_reference_binaries() else min(100_000, args.pairs)   # (else: the 1-thread C port)
+
+
+def reference_parity(info, args, world, n_pairs):
+    """the digests of the reference's OWN outputs in this run against tests/golden/bench_digests.json (only when the
+    pass covered the whole N = 1 workload: the committed digests are those of the full config)"""
+    from rufus_b200 import workload
+    dg = (info or {}).get("digests")
+    if dg is None or world != 1 or n_pairs != args.pairs:
+        return None
+    exp = workload.expected(1, seed=args.seed, pairs=args.pairs, genome_unit=args.genome, k=K)
+    if exp is None:
+        return dict(dg, ok=None, reference="no committed digests for this workload")
+    bad = [f for f in ("histo_md5", "hashlist_md5", "pulled_md5") if exp.get(f) != dg[f]]
+    return dict(dg, ok=not bad, mismatch=bad,
+                reference=workload.digest_key(1, seed=args.seed, pairs=args.pairs, genome_unit=args.genome, k=K))
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    n_pairs = min(args.ref_pairs, args.pairs)
+    n_pairs = reference_sample_pairs(args, world)
     trio = make_data(args, 0, world)
     threads = os.cpu_count() or 1
     times, kind, info, bases = [], None, None, 0
-    for i in range(args.warmup + args.steps):
+    par, shrunk = None, ""
+    have_ref = have_reference_binaries()
+    fqdir = tempfile.mkdtemp(prefix="rg_ref_fq_")
+
+    def one_pass(n, fq):
         wd = tempfile.mkdtemp(prefix="rg_ref_")
         try:
-            dt, bases, kind, info = cpu_reference_pass(trio, n_pairs, wd, threads)
+            return cpu_reference_pass(trio, n, wd, threads, fq=fq)
         finally:
             shutil.rmtree(wd, ignore_errors=True)
-        log(f"reference pass {i}: {dt:.2f}s")
-        if i >= args.warmup:
-            times.append(dt)
+
+    try:
+        fq = write_reference_fastq(trio, n_pairs, fqdir) if have_ref else None
+        i = 0
+        while i < args.warmup + args.steps:
+            dt, bases, kind, info = one_pass(n_pairs, fq)
+            log(f"reference pass {i}: {dt:.2f}s ({n_pairs} pairs/sample)")
+            if par is None:
+                par = reference_parity(info, args, world, n_pairs)
+            # the whole run has to end within a few minutes whatever the host: when W + K passes over the whole workload
+            # would take longer than --ref-budget seconds, this pass was a calibration (its outputs still checked against
+            # the digests) and the W + K passes run on the bounded sample instead
+            if i == 0 and n_pairs > 100_000 and args.ref_pairs == 0 and dt * (args.warmup + args.steps) > args.ref_budget:
+                shrunk = (f"; one calibration pass over the whole workload took {dt:.1f}s on this host, "
+                          f"x{args.warmup + args.steps} passes > {args.ref_budget:.0f}s budget")
+                n_pairs = 100_000
+                fq = write_reference_fastq(trio, n_pairs, fqdir) if have_ref else None
+                continue
+            if i >= args.warmup:
+                times.append(dt)
+            i += 1
+    finally:
+        shutil.rmtree(fqdir, ignore_errors=True)
     ms = 1e3 * sum(times) / len(times)
     val = bases / (ms / 1e3) / 1e9
-    sample = (f"first {n_pairs} of the {args.pairs} pairs/sample of rank 0's slice ({bases / 1e6:.0f} Mbases per pass), "
-              f"jellyfish -s 256M -t {info['cores']}, per-base normalised")
+    whole = world == 1 and n_pairs == args.pairs
+    sample = ((f"the whole workload: {n_pairs} pairs/sample" if whole else
+               f"first {n_pairs} of the {args.pairs} pairs/sample of rank 0's slice, per-base normalised")
+              + f" ({bases / 1e6:.0f} Mbases per pass), jellyfish -s 256M -t {info['cores']}" + shrunk)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gbases/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -273,6 +350,8 @@ def run_reference_arm(args, rank, world):
            "cpu_baseline": {"value": val, "unit": "Gbases/s", "cores": info["cores"], "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if par is not None:
+        out["parity"] = par        # the reference's outputs ARE the committed digests (same run, same box)
     print(json.dumps(out), flush=True)
 
 
@@ -503,7 +582,10 @@ def main():
     ap.add_argument("--pairs", type=int, default=500_000, help="read pairs per sample per GPU")
     ap.add_argument("--genome", type=int, default=5_000_000, help="genome bases per GPU (the genome is N times that)")
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--ref-pairs", type=int, default=100_000, help="pairs/sample of the CPU baseline sample")
+    ap.add_argument("--ref-pairs", type=int, default=0,
+                    help="pairs/sample the reference's commands run on (0: the whole workload at N=1, 100 k of rank 0's slice at N>1)")
+    ap.add_argument("--ref-budget", type=float, default=420.0,
+                    help="--impl reference: seconds the W + K passes may take before the arm falls back to the bounded sample")
     ap.add_argument("--mode", default="tiled", choices=["tiled", "direct"])
     ap.add_argument("--est-scale", type=float, default=1.0, help="scale the distinct k-mer estimate (table load factor)")
     ap.add_argument("--p2p-groups", type=int, default=0, help="hash-prefix groups per shard of the peer-to-peer partition")
@@ -712,17 +794,22 @@ def main():
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                       "steps": e2e_steps, "parity_ok": e2e_ok, "note": note}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    # ---- CPU baseline beside it (rank 0, N = 1 only): ONE pass of the reference's commands over the whole workload
+    # (C2: ~8 s wall on 16 cores), its outputs checked against the same committed digests as the CUDA path's
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         wd = tempfile.mkdtemp(prefix="rg_cpu_")
+        n_ref = reference_sample_pairs(args, world)
         try:
-            dt, b, kind, info = cpu_reference_pass(trio, min(args.ref_pairs, args.pairs), wd, os.cpu_count() or 1)
+            dt, b, kind, info = cpu_reference_pass(trio, n_ref, wd, os.cpu_count() or 1)
         finally:
             shutil.rmtree(wd, ignore_errors=True)
+        what = "the whole workload" if n_ref == args.pairs else f"first {n_ref} pairs/sample of the same workload"
         out["cpu_baseline"] = {"value": b / dt / 1e9, "unit": "Gbases/s", "cores": info["cores"], "kind": kind,
-                               "sample": f"first {args.ref_pairs} pairs/sample ({b / 1e6:.0f} Mbases) of the same "
-                                         f"workload, {dt:.1f}s wall, jellyfish -s 256M; hashlist {info['hashlist']}, "
-                                         f"pulled {info['pulled']}"}
+                               "sample": f"{what} ({b / 1e6:.0f} Mbases), one pass, {dt:.1f}s wall, jellyfish -s 256M; "
+                                         f"hashlist {info['hashlist']}, pulled {info['pulled']}"}
+        par = reference_parity(info, args, world, n_ref)
+        if par is not None:
+            out["cpu_baseline"]["parity"] = par
     if rank == 0 and world == 1 and args.cli:
         ctx.close()
         ctx = None

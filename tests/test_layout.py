@@ -38,9 +38,10 @@ def test_product_code_never_touches_the_oracle():
 def test_bench_uses_the_oracle_only_for_the_cpu_baseline():
     """every mention of oracle/ in bench.py sits inside a function that times the REFERENCE'S side: cpu_reference_pass
     (cpu_baseline leg and --impl reference), cpu_reference_big (the large configs' cpu_baseline) and cli_leg (the
-    reference's stage commands next to ours). Nothing on the measured CUDA path touches it."""
+    reference's stage commands next to ours); have_reference_binaries only looks whether oracle/_ref was built. Nothing on
+    the measured CUDA path touches it."""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    allowed = ("cpu_reference_pass", "cpu_reference_big", "cli_leg")
+    allowed = ("cpu_reference_pass", "cpu_reference_big", "cli_leg", "have_reference_binaries")
     outside, pos = [], 0
     for m in re.finditer(r"^def (\w+)\(.*?(?=^def |\Z)", src, re.S | re.M):
         if m.group(1) in allowed:
