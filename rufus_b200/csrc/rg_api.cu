@@ -596,6 +596,24 @@ static int push_piece(rg_table* t, const char* dev, uint64_t n_bytes) {
   return t->mode == RG_MODE_TILED ? rg_launch_partition(t, ep) : rg_launch_count_direct(t, ep);
 }
 
+// device temporaries of one entry point: freed on every way out (an RG_CUDA_OK that returns early included)
+struct DevTemps {
+  void* p[4] = {nullptr, nullptr, nullptr, nullptr};
+  int n = 0;
+  DevTemps() = default;
+  DevTemps(const DevTemps&) = delete;
+  DevTemps& operator=(const DevTemps&) = delete;
+  ~DevTemps() {
+    for (int i = 0; i < n; ++i) cudaFree(p[i]);
+  }
+  template <typename T>
+  cudaError_t alloc(T** out, size_t bytes) {
+    const cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaSuccess && n < 4) p[n++] = *out;
+    return e;
+  }
+};
+
 extern "C" {
 
 rg_table* rg_count_begin(rg_ctx* ctx, int k, int canonical, uint64_t est_distinct, int mode) {
@@ -1149,8 +1167,9 @@ int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* k
   cudaSetDevice(ctx->device);
   uint64_t* d_keys = nullptr;
   uint32_t* d_counts = nullptr;
-  RG_CUDA_OK(cudaMalloc(&d_keys, (cap ? cap : 1) * 8));
-  RG_CUDA_OK(cudaMalloc(&d_counts, (cap ? cap : 1) * 4));
+  DevTemps tmp;
+  RG_CUDA_OK(tmp.alloc(&d_keys, (cap ? cap : 1) * 8));
+  RG_CUDA_OK(tmp.alloc(&d_counts, (cap ? cap : 1) * 4));
   int64_t rc = rg_table_finish(t);
   if (rc == 0) rc = rg_launch_dump(t, min_count ? min_count : 1, max_count, d_keys, d_counts, cap, ctx->d_scratch);
   uint64_t n = 0;
@@ -1164,8 +1183,6 @@ int64_t rg_dump(rg_table* t, uint64_t min_count, uint64_t max_count, uint64_t* k
       rc = copy_out(ctx, n, d_keys, d_counts, keys_host, counts_host);
     }
   }
-  cudaFree(d_keys);
-  cudaFree(d_counts);
   return rc;
 }
 
@@ -1227,8 +1244,9 @@ int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_co
   cudaSetDevice(ctx->device);
   uint64_t* dk = nullptr;
   uint32_t* dc = nullptr;
-  RG_CUDA_OK(cudaMalloc(&dk, n * 8));
-  RG_CUDA_OK(cudaMalloc(&dc, n * 4));
+  DevTemps tmp;
+  RG_CUDA_OK(tmp.alloc(&dk, n * 8));
+  RG_CUDA_OK(tmp.alloc(&dc, n * 4));
   int rc = rg_table_finish(t);
   if (rc == 0) rc = RG_ERR_CUDA;
   if (rc == RG_ERR_CUDA && cudaMemcpyAsync(dk, keys_host, n * 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess) {
@@ -1239,8 +1257,6 @@ int rg_query(rg_table* t, const uint64_t* keys_host, uint64_t n, uint64_t min_co
       rc = RG_ERR_CUDA;
     }
   }
-  cudaFree(dk);
-  cudaFree(dc);
   return rc;
 }
 
@@ -1334,16 +1350,15 @@ int64_t rg_subtract(rg_table* subj, uint64_t subj_min, rg_table* const* others, 
   cudaSetDevice(ctx->device);
   uint64_t* dk = nullptr;
   uint32_t* dc = nullptr;
-  RG_CUDA_OK(cudaMalloc(&dk, (cap ? cap : 1) * 8));
-  RG_CUDA_OK(cudaMalloc(&dc, (cap ? cap : 1) * 4));
+  DevTemps tmp;
+  RG_CUDA_OK(tmp.alloc(&dk, (cap ? cap : 1) * 8));
+  RG_CUDA_OK(tmp.alloc(&dc, (cap ? cap : 1) * 4));
   int64_t n = rg_subtract_dev(subj, subj_min, others, other_min, n_others, floor, min_cov, max_cov, dk, dc, cap);
   if (n == RG_ERR_SMALL && needed) *needed = ctx->h_scratch[8];
   if (n >= 0) {
     if (needed) *needed = (uint64_t)n;
     n = copy_out(ctx, (uint64_t)n, dk, dc, keys_host, counts_host);
   }
-  cudaFree(dk);
-  cudaFree(dc);
   return n;
 }
 
@@ -1364,9 +1379,10 @@ int64_t rg_build_select(rg_table* subj, int64_t min_subject, int64_t max_subject
   const uint64_t lo = min_subject > 1 ? (uint64_t)min_subject : 1, hi = (uint64_t)max_subject;
   uint64_t* dk = nullptr;
   uint32_t *dc = nullptr, *ds = nullptr;
-  RG_CUDA_OK(cudaMalloc(&dk, (cap ? cap : 1) * 8));
-  RG_CUDA_OK(cudaMalloc(&dc, (cap ? cap : 1) * 4));
-  RG_CUDA_OK(cudaMalloc(&ds, (cap ? cap : 1) * 4));
+  DevTemps tmp;
+  RG_CUDA_OK(tmp.alloc(&dk, (cap ? cap : 1) * 8));
+  RG_CUDA_OK(tmp.alloc(&dc, (cap ? cap : 1) * 4));
+  RG_CUDA_OK(tmp.alloc(&ds, (cap ? cap : 1) * 4));
   int64_t n = rg_launch_build_select(subj, lo, hi, ot, (uint64_t)max_control_sum, dk, dc, ds, cap, ctx->d_scratch);
   uint64_t got = 0;
   if (n == 0) n = read_scalars(ctx, ctx->d_scratch, 1, &got);
@@ -1384,9 +1400,6 @@ int64_t rg_build_select(rg_table* subj, int64_t min_subject, int64_t max_subject
       }
     }
   }
-  cudaFree(dk);
-  cudaFree(dc);
-  cudaFree(ds);
   return n;
 }
 
