@@ -324,7 +324,20 @@ static int table_grow(rg_table* t, uint32_t new_tiles, uint64_t new_ovf = 0) {
   t->keys = nullptr;
   t->counts = nullptr;
   int rc = table_alloc_tiles(t, new_tiles, new_ovf);
-  if (rc) return rc;
+  if (rc) {
+    // no room for the larger table next to the old one: the table stays exactly what it was (table_alloc_tiles sets
+    // the geometry only after both allocations), the caller gets a message that says what was being attempted
+    const std::string why = rg_last_error();
+    cudaFree(t->keys);
+    cudaFree(t->counts);
+    t->keys = old_keys;
+    t->counts = old_counts;
+    (void)cudaGetLastError();       // (a failed cudaMalloc leaves its error behind for the next launch check)
+    rg_set_error("count: cannot grow the table to " + std::to_string(new_tiles) + " tiles (" +
+                 std::to_string(((((uint64_t)new_tiles << RG_TILE_BITS) + new_ovf) * 12) >> 20) +
+                 " MiB next to the " + std::to_string((old_slots * 12) >> 20) + " MiB it holds): " + why);
+    return rc;
+  }
   // bucket staging is sized per tile count: drop it, it is rebuilt on the next push
   drop_buckets(t);
   RG_CUDA_OK(cudaMemsetAsync(t->d_status, 0, RG_ST_WORDS * sizeof(uint64_t), ctx->stream));
