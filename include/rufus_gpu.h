@@ -149,6 +149,10 @@ int rg_table_p2p_import(rg_table* t, uint32_t rank, const void* handle64);
 int rg_tables_p2p_attach(rg_table* const* tabs, int n);
 /* number of CUDA devices visible to the process (0 without a driver) */
 int rg_device_count(void);
+/* free and total bytes of the context's device (cudaMemGetInfo): what a streaming caller sizes its table budget
+ * from — `jellyfish count --disk` writes the table out as an intermediate file before it would outgrow the device
+ * (hash_counter.hpp:182-202) */
+int rg_device_memory(rg_ctx* ctx, uint64_t* free_bytes, uint64_t* total_bytes);
 int rg_count_p2p_begin(rg_table* t);
 /* max_ctas: CTAs of the scatter kernel (0 = one per SM). It is NVLink-bound: with fewer CTAs it leaves
  * SMs to the finish kernels of the previous sample running on another stream. */

@@ -79,6 +79,7 @@ def lib():
         "rg_extract_partition_dev": (i32, [vp, vp, u64, u32, vp, vp]),
         "rg_key_shard": (u32, [u64, i32, i32, u32, u32]),
         "rg_device_count": (i32, []),
+        "rg_device_memory": (i32, [vp, vp, vp]),
         "rg_dump_slice_dev": (i64, [vp, u64, u32, u32, vp, vp, u64, vp]),
         "rg_synth_pairs_dev": (i32, [vp, vp, vp, vp, vp, vp]),
         "rg_synth_pairs_host": (i32, [vp, vp, vp, vp, vp]),

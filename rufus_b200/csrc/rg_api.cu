@@ -816,6 +816,16 @@ int rg_device_count(void) {
   return n;
 }
 
+int rg_device_memory(rg_ctx* ctx, uint64_t* free_bytes, uint64_t* total_bytes) {
+  if (!ctx) return RG_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  size_t fr = 0, tot = 0;
+  RG_CUDA_OK(cudaMemGetInfo(&fr, &tot));
+  if (free_bytes) *free_bytes = (uint64_t)fr;
+  if (total_bytes) *total_bytes = (uint64_t)tot;
+  return 0;
+}
+
 int rg_count_p2p_begin(rg_table* t) {
   if (!t || !t->p2p_block) return RG_ERR_ARG;
   cudaSetDevice(t->ctx->device);

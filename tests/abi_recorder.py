@@ -7,6 +7,7 @@ few that matter here RECORD their arguments —
   rg_filter_pairs   folds sequences, qualities and offsets of both mates into a running digest (printed on stderr) and
                     answers a fixed pattern: keep every pair whose index in the call is not 1 mod 3
   rg_filter_single  same, hits = index mod 4
+  rg_table_write_jhash  prints its arguments and (with $RG_RECORD_PARTS) copies the next canned part file to the path
 Nothing under rufus_b200/ or tools/ knows about it (tests/test_layout.py), and the real library is never replaced in
 the tree."""
 import os
@@ -40,6 +41,43 @@ int rg_count_push(void*, const char* s, uint64_t n) {
   fwrite(s, 1, n, f);
   fclose(f);
   fprintf(stderr, "push %llu\n", (unsigned long long)n);
+  return 0;
+}
+// the --disk path of `jellyfish count`: the table "holds" $RG_RECORD_DISTINCT k-mers, and every .Jhash it is asked to write
+// is a copy of the next canned file $RG_RECORD_PARTS/part<N> (made by the reference's binary in the test)
+int rg_device_memory(void*, uint64_t* fr, uint64_t* tot) {
+  if (fr) *fr = 1ull << 36;
+  if (tot) *tot = 1ull << 37;
+  return 0;
+}
+int rg_table_stats(void*, uint64_t* d, uint64_t* o, uint64_t* s) {
+  const char* e = getenv("RG_RECORD_DISTINCT");
+  if (d) *d = e ? strtoull(e, 0, 10) : 0;
+  if (o) *o = 0;
+  if (s) *s = 0;
+  return 0;
+}
+int rg_table_clear(void*) {
+  fprintf(stderr, "clear\n");
+  return 0;
+}
+long rg_table_write_jhash(void*, const char* path, uint64_t lo, uint64_t hi, uint64_t size, uint32_t cl, const char* const*, int) {
+  static int call = 0;
+  fprintf(stderr, "write_jhash %s min=%llu max=%llu size=%llu counter_len=%u\n", path, (unsigned long long)lo,
+          (unsigned long long)hi, (unsigned long long)size, cl);
+  if (const char* dir = getenv("RG_RECORD_PARTS")) {
+    char src[4096];
+    snprintf(src, sizeof src, "%s/part%d", dir, call);
+    FILE* a = fopen(src, "rb");
+    FILE* b = fopen(path, "wb");
+    if (!a || !b) return -4;
+    char buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, a)) > 0) fwrite(buf, 1, n, b);
+    fclose(a);
+    fclose(b);
+  }
+  ++call;
   return 0;
 }
 void* rg_set_from_hashlist_text(void*, const char*, uint64_t, int, int) { return (void*)0x3000; }

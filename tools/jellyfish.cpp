@@ -7,6 +7,11 @@
 //        Jellyfish 2.2.5 binary/sorted (count_main.cc:214-354). An extension: IN may also be a BAM file, which
 //        is decoded in process on T threads and counted as `samtools view -F 3328 IN | PassThroughSamCheck`
 //        would present it (tools/rg_bam_input.hpp)
+//        --disk (hash_counter.hpp:182-202, count_main.cc:316-338): a table that would outgrow the device is written
+//        out as the intermediate file OUT<N> and counting goes on with an empty table; the parts are merged (counts
+//        summed, then -L/-U) and unlinked at the end (tools/rg_jf_parts.hpp). RG_COUNT_SPILL_DISTINCT=<n> sets the
+//        number of distinct k-mers a table may hold (default: device memory / 128 bytes); --no-merge / --no-unlink
+//        keep the parts, as they do in Jellyfish.
 //   jellyfish histo [-f] [-l low] [-h high] [-o OUT] DB          (histo_main.cc:46-110)
 //   jellyfish dump  [-c] [-t] [-L min] [-U max] [-o OUT] DB      (dump_main.cc)
 //   jellyfish query [-s FASTA]... [-o OUT] DB [MER...]           (query_main.cc:44-129)
@@ -23,6 +28,9 @@
 
 #include "rg_bam_input.hpp"
 #include "rg_cli.hpp"
+#include "rg_jf_parts.hpp"
+
+[[noreturn]] void rgparts::fail(const std::string& m) { die("jellyfish count: " + m); }
 
 [[noreturn]] void rgbam::fail(const std::string& m) {   // (raised on a pipeline thread: leave without unwinding the others)
   fprintf(stderr, "jellyfish count: BAM input: %s\n", m.c_str());
@@ -242,6 +250,7 @@ struct MultiCount {
 static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   int k = 0, canonical = 0;
   unsigned threads = 1;
+  bool no_merge = false, no_unlink = false;
   uint64_t size = 0, lower = 0, upper = 0;
   uint32_t out_counter_len = 4;
   const char* out = "mer_counts.jf";
@@ -251,6 +260,8 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
     const char* v = nullptr;
     if (!strcmp(a, "-C") || !strcmp(a, "--canonical")) canonical = 1;
     else if (!strcmp(a, "--disk") || !strcmp(a, "--text") || !strcmp(a, "--no-write")) { if (a[2] == 't') die("--text output is not supported"); }
+    else if (!strcmp(a, "--no-merge")) no_merge = true;
+    else if (!strcmp(a, "--no-unlink")) no_unlink = true;
     else if (opt_value(a, "-m", "--mer-len", i, argc, argv, &v)) k = atoi(v);
     else if (opt_value(a, "-s", "--size", i, argc, argv, &v)) size = parse_size(v);
     else if (opt_value(a, "-t", "--threads", i, argc, argv, &v)) threads = (unsigned)std::max(1, std::min(64, atoi(v)));   // BAM inputs decode on this many threads
@@ -313,12 +324,42 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   size_t chunk = 8u << 20;
   ByteBuf fill, inflight;
   fill.reserve(chunk + (1u << 20));
+  // --disk (hash_counter.hpp:182-202): a table about to hold more than `spill_limit` distinct k-mers is written out as
+  // the intermediate file <out><N> (every count, no -L/-U: they apply to the summed counts) and emptied; counting goes
+  // on. The limit leaves room for the table (at most 60 % loaded and grown by half: up to 30 bytes per k-mer), the copy
+  // it is re-hashed into while it grows, and the 48 bytes per record the .Jhash writer needs while it sorts: device
+  // memory / 128 bytes (1.4 G distinct k-mers per part on 180 GB; a 30x human sample leaves ~9 parts).
+  // No k-mer is looked at before the bytes pushed since the table was last empty could exceed the limit, so an input
+  // that fits — everything below 1.4 Gbases, whatever it holds — runs exactly the path it ran without this.
+  uint64_t spill_limit = 0, since_empty = 0;
+  if (const char* e = getenv("RG_COUNT_SPILL_DISTINCT")) {
+    spill_limit = parse_size(e);
+  } else {
+    uint64_t fr = 0, tot = 0;
+    if (rg_device_memory(ctx, &fr, &tot) == 0) spill_limit = tot / 128;
+  }
+  std::vector<std::string> parts;
+  auto spill = [&]() {
+    if (out_counter_len != 4) die("jellyfish count: --out-counter-len with intermediate files is not supported");
+    const std::string part = std::string(out) + std::to_string(parts.size());   // (count_main.cc: <output><N>)
+    check(rg_table_write_jhash(t, part.c_str(), 0, 0, size, 4, full_argv + 1, full_argc - 1), "count (intermediate file)");
+    check(rg_table_clear(t), "count");
+    parts.push_back(part);
+    since_empty = 0;
+  };
   auto flush = [&](ByteBuf& b) {
     check(rg_count_end(t), "count");                 // the previous chunk (in `inflight`) is done; spills resolved
+    if (spill_limit && since_empty && since_empty + b.size() > spill_limit) {
+      uint64_t distinct = 0;
+      check(rg_table_stats(t, &distinct, nullptr, nullptr), "count");
+      if (distinct + b.size() > spill_limit) spill();
+      else since_empty = distinct;                   // (what the table holds: a tighter bound than the bytes pushed)
+    }
     check(rg_table_reserve(t, b.size()), "count");   // room for this chunk's k-mers, whatever they are
     inflight.swap(b);
     b.clear();
     check(rg_count_push(t, inflight.data(), inflight.size()), "count");   // asynchronous
+    since_empty += inflight.size();
     chunk = std::min<size_t>(chunk * 4, 128u << 20);
     b.reserve(chunk + (1u << 20));
   };
@@ -330,6 +371,17 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   }
   if (!fill.empty()) flush(fill);
   check(rg_count_end(t), "count");
+  if (!parts.empty()) {
+    // count_main.cc:322-337: the table's last state is one more part; the stock merge sums the parts, then -L/-U
+    if (since_empty) spill();
+    rg_table_free(t);
+    rg_shutdown(ctx);
+    if (no_merge) return 0;
+    rgparts::merge(parts, out, lower, upper);
+    if (!no_unlink)
+      for (const std::string& p : parts) unlink(p.c_str());
+    return 0;
+  }
   check(rg_table_write_jhash(t, out, lower, upper, size, out_counter_len, full_argv + 1, full_argc - 1), "count");
   if (upper == 0) {
     std::vector<uint64_t> rows(rg_histo_rows(1, 10000));
@@ -338,6 +390,27 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
   }
   rg_table_free(t);
   rg_shutdown(ctx);
+  return 0;
+}
+
+// `jellyfish rg-merge-parts [-L min] [-U max] -o OUT PART...`: the merge `count --disk` runs over its intermediate files,
+// on its own (parts kept with --no-merge; no GPU involved)
+static int merge_parts_main(int argc, char** argv) {
+  uint64_t lower = 0, upper = 0;
+  const char* out = nullptr;
+  std::vector<std::string> parts;
+  for (int i = 1; i < argc; ++i) {
+    const char* a = argv[i];
+    const char* v = nullptr;
+    if (opt_value(a, "-o", "--output", i, argc, argv, &v)) out = v;
+    else if (opt_value(a, "-L", "--lower-count", i, argc, argv, &v)) lower = parse_size(v);
+    else if (opt_value(a, "-U", "--upper-count", i, argc, argv, &v)) upper = parse_size(v);
+    else if (a[0] == '-' && a[1] != 0) die(std::string("unknown option ") + a);
+    else parts.push_back(a);
+  }
+  if (!out || parts.empty()) die("Usage: jellyfish rg-merge-parts [-L min] [-U max] -o OUT PART...");
+  const uint64_t n = rgparts::merge(parts, out, lower, upper);
+  fprintf(stderr, "%llu records\n", (unsigned long long)n);
   return 0;
 }
 
@@ -583,6 +656,7 @@ int main(int argc, char** argv) {
   if (cmd == "dump") return dump_main(argc - 1, argv + 1);
   if (cmd == "query") return query_main(argc - 1, argv + 1);
   if (cmd == "merge") return merge_main(argc - 1, argv + 1);
+  if (cmd == "rg-merge-parts") return merge_parts_main(argc - 1, argv + 1);
   if (cmd == "--version" || cmd == "-V") { printf("jellyfish 2.2.5 (%s)\n", rg_version()); return 0; }
   die("Unknown command '" + cmd + "'");
 }
