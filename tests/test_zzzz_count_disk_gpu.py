@@ -52,3 +52,33 @@ def test_spilled_count_equals_the_plain_count(tmp_path):
         subprocess.run([REF, "count", "-m", "25", "-C", "-L", "2", "-s", "16M", "-t", "4", "-o", "ref.Jhash", "in.fa"], cwd=d,
                        check=True, timeout=600)
         assert records(os.path.join(d, "ref.Jhash")) == want
+
+
+@pytest.mark.parametrize("tiled", [False, True])
+def test_clear_really_empties_the_table(tiled):
+    """rg_table_clear between two counts (what the spill does between parts, and what every bench step does): nothing of
+    the first input is left for readers or for a SMALL second push, which goes straight into global memory instead of
+    through the tile insert that rewrites whole tiles (round-1 advice: the shortcut that only reset a flag)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    from rufus_b200 import api
+    ctx = api.Context(0)
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    big = acgt[rng.integers(0, 4, (20_000, 150))]
+    small = acgt[rng.integers(0, 4, (300, 150))]
+    offs = lambda a: np.arange(a.shape[0] + 1, dtype=np.uint64) * 150
+    t = api.KmerTable(ctx, 25, True, est_distinct=4_000_000, mode=api.MODE_TILED if tiled else api.MODE_DIRECT)
+    t.push_reads(big.reshape(-1), offs(big))
+    t.end(trim=False)
+    assert t.stats()["distinct"] > 2_000_000
+    t.clear()
+    assert t.stats()["distinct"] == 0 and t.dump()[0].size == 0 and int(t.histo().sum()) == 0
+    t.push_reads(small.reshape(-1), offs(small))
+    t.end()
+    keys, counts = t.dump()
+    ok, oc = oracle.count(small.reshape(-1), offs(small), 25, True, 1)
+    assert np.array_equal(keys, ok) and np.array_equal(counts, oc)
+    t.free()
+    ctx.close()
