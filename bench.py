@@ -109,6 +109,30 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """N > 1 (one process per GPU under torchrun, which binds nothing): run this rank on the CPUs NVML reports as local to
+    its GPU, BEFORE any pinned host buffer is allocated, so that the end-to-end leg's host->device copies read memory of
+    the socket the GPU hangs off instead of crossing the inter-socket link with seven other ranks. Best effort: any
+    failure (no NVML, a cpuset that leaves fewer than four CPUs) leaves the affinity as it was. Returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = ((os.cpu_count() or 1) + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        local = {64 * i + b for i, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = local & allowed
+        if len(want) < 4:
+            return f"kept ({len(want)} of the GPU's CPUs in this process's cpuset)"
+        if want == allowed:
+            return f"already local ({len(want)} CPUs)"
+        os.sched_setaffinity(0, want)
+        return f"{len(want)} CPUs local to GPU {gpu_index} (of {len(allowed)})"
+    except Exception as e:          # noqa: BLE001 - measurement hygiene only, never fatal
+        return f"kept ({type(e).__name__})"
+
+
 # --------------------------------------------------------------------------- data
 def make_data(args, rank, world):
     """this rank's reads of the benchmark workload (rufus_b200/workload.py: genome = unit x world, slice = rank)"""
@@ -611,6 +635,7 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
 
+    cpu_binding = bind_to_gpu_cpus(local_rank) if world > 1 else "none (single process)"
     import torch
     from rufus_b200 import api, pipeline, synth
     if not torch.cuda.is_available():
@@ -726,7 +751,8 @@ def main():
 
     out = {"metric": METRIC, "value": value, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, world),
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": dict(workload_config(args, world), cpu_binding=cpu_binding),
            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "kernels_ms": kern,
            "result": {"n_mutant_kmers": r["n_mutant"], "n_pulled_pairs_rank0": r["n_kept"]}, "parity": parity}
 
