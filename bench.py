@@ -761,7 +761,15 @@ def main():
     # rg_filter_pairs, H2D pipelined against the kernels). N > 1: the sharded pipeline fed from host buffers.
     if not args.no_e2e:
         e2e_steps = max(3, args.steps // 2)
+        e2e_binding, saved_cpus = cpu_binding, None
         if world == 1:
+            # the pinned buffers of this leg are allocated (and first touched) on the CPUs next to the GPU; the previous
+            # affinity is restored after the leg, before the CPU baseline runs the reference's binaries on every core
+            try:
+                saved_cpus = os.sched_getaffinity(0)
+            except Exception:           # noqa: BLE001
+                saved_cpus = None
+            e2e_binding = bind_to_gpu_cpus(local_rank) if saved_cpus else "kept"
             pipe.free()
             del pipe
             torch.cuda.empty_cache()
@@ -816,9 +824,14 @@ def main():
             t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item())
+        if saved_cpus:
+            try:
+                os.sched_setaffinity(0, saved_cpus)
+            except Exception:           # noqa: BLE001
+                pass
         out["e2e"] = {"value": bases_per_step * world / (ms_e2e / 1e3) / 1e9, "unit": "Gbases/s",
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
-                      "steps": e2e_steps, "parity_ok": e2e_ok, "note": note}
+                      "steps": e2e_steps, "parity_ok": e2e_ok, "note": note, "cpu_binding": e2e_binding}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): ONE pass of the reference's commands over the whole workload
     # (C2: ~8 s wall on 16 cores), its outputs checked against the same committed digests as the CUDA path's
