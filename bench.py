@@ -118,10 +118,10 @@ def bind_to_gpu_cpus(gpu_index):
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        words = ((os.cpu_count() or 1) + 63) // 64
+        allowed = os.sched_getaffinity(0)
+        words = max(max(allowed), (os.cpu_count() or 1) - 1) // 64 + 1      # (a cpuset names HOST cpu numbers)
         masks = pynvml.nvmlDeviceGetCpuAffinity(h, words)
         local = {64 * i + b for i, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1}
-        allowed = os.sched_getaffinity(0)
         want = local & allowed
         if len(want) < 4:
             return f"kept ({len(want)} of the GPU's CPUs in this process's cpuset)"
