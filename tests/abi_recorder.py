@@ -33,7 +33,7 @@ const char* rg_last_error() { return "recorder"; }
 void* rg_host_alloc(uint64_t n) { return malloc(n ? n : 1); }
 void rg_host_free(void* p) { free(p); }
 void* rg_count_begin(void*, int, int, uint64_t, int) { return (void*)0x2000; }
-uint64_t rg_histo_rows(uint64_t, uint64_t) { return 10001; }
+uint64_t rg_histo_rows(uint64_t low, uint64_t high) { return (high + 1) + 1 - (low > 1 ? low - 1 : 0); }   // (histo_main.cc:64-68)
 int rg_count_push(void*, const char* s, uint64_t n) {
   char path[4096];
   snprintf(path, sizeof path, "%s/pushes.bin", getenv("RG_RECORD_DIR"));

@@ -121,6 +121,10 @@ def test_count_spills_merges_and_unlinks(inputs, tmp_path):
     sh(f"{JF} rg-merge-parts -L 2 -o expect part0 part1", parts_dir)
     assert records(os.path.join(d, "out.Jhash")) == records(os.path.join(parts_dir, "expect"))
     assert not os.path.exists(os.path.join(d, "out.Jhash0")) and not os.path.exists(os.path.join(d, "out.Jhash1"))
+    # the merge also leaves the histogram next to the file (as an unspilled count does): `histo -f` needs no GPU and
+    # prints what the reference's histo prints for the merged file
+    h = subprocess.run([JF, "histo", "-f", "out.Jhash"], cwd=d, capture_output=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert h.returncode == 0 and h.stdout == sh(f"{REF} histo -f expect", parts_dir).stdout and h.stdout.count(b"\n") == 10002
     # --no-merge keeps the parts and writes no final file (count_main.cc:325)
     os.remove(os.path.join(d, "out.Jhash"))
     r = _count(env, d, {"RG_COUNT_SPILL_DISTINCT": "10M", "RG_RECORD_PARTS": parts_dir}, "--no-merge", "big.fa")

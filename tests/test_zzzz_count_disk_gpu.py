@@ -39,7 +39,10 @@ def test_spilled_count_equals_the_plain_count(tmp_path):
     want = records(os.path.join(d, "plain.Jhash"))
     assert len(want) // 11 > 250_000
     assert records(os.path.join(d, "spilled.Jhash")) == want
-    assert not [p for p in os.listdir(d) if p.startswith("spilled.Jhash") and p != "spilled.Jhash"]     # parts unlinked
+    assert not [p for p in os.listdir(d) if p.startswith("spilled.Jhash") and p not in ("spilled.Jhash", "spilled.Jhash.rg_histo")]   # parts unlinked
+    # both counts leave the histogram next to the file (histo_kernel for the plain one, the merge for the spilled one)
+    histo = lambda f: subprocess.run([JF, "histo", "-f", f], cwd=d, check=True, capture_output=True).stdout
+    assert histo("spilled.Jhash") == histo("plain.Jhash") and histo("plain.Jhash").count(b"\n") == 10002
     # the parts themselves: kept by --no-merge, more than one, and no final file
     subprocess.run(base + ["--no-merge", "-o", "kept.Jhash", "in.fa"], cwd=d, check=True, env=env, timeout=300)
     parts = sorted(p for p in os.listdir(d) if p.startswith("kept.Jhash"))

@@ -377,7 +377,9 @@ static int count_main(int argc, char** argv, int full_argc, char** full_argv) {
     rg_table_free(t);
     rg_shutdown(ctx);
     if (no_merge) return 0;
-    rgparts::merge(parts, out, lower, upper);
+    std::vector<uint64_t> rows(upper == 0 ? rg_histo_rows(1, 10000) : 0, 0);   // (the sidecar, as after an unspilled count)
+    rgparts::merge(parts, out, lower, upper, &rows);
+    if (upper == 0) write_histo_sidecar(out, rows);
     if (!no_unlink)
       for (const std::string& p : parts) unlink(p.c_str());
     return 0;

@@ -138,7 +138,10 @@ static inline bool advance(Part& p, const PosTable& pt) {
 
 // parts -> out: header of the first part, then every k-mer once with the sum of its counts (saturating at 2^32-1 on
 // disk, binary_dumper.hpp:44-48) when lower <= sum and (upper == 0 or sum <= upper). Returns the records written.
-static inline uint64_t merge(const std::vector<std::string>& paths, const std::string& out, uint64_t lower, uint64_t upper) {
+// `histo` (optional, R rows): the records written, by count — row min(count, R-1), the histogram `jellyfish histo -l 1
+// -h R-2` computes from the file (histo_main.cc:64-84).
+static inline uint64_t merge(const std::vector<std::string>& paths, const std::string& out, uint64_t lower, uint64_t upper,
+                             std::vector<uint64_t>* histo = nullptr) {
   if (paths.empty()) fail("no intermediate files to merge");
   std::vector<Part> parts(paths.size());
   for (size_t i = 0; i < paths.size(); ++i) {
@@ -177,6 +180,7 @@ static inline uint64_t merge(const std::vector<std::string>& paths, const std::s
       for (unsigned b = 0; b < 4; ++b) r[kb + b] = (unsigned char)(c >> (8 * b));
       ok = ok && fwrite(r, 1, kb + 4, o) == kb + 4;
       ++written;
+      if (histo && !histo->empty()) ++(*histo)[std::min<uint64_t>(c, histo->size() - 1)];
     }
   }
   for (Part& p : parts) p.close();
