@@ -576,9 +576,9 @@ static int query_main(int argc, char** argv) {
   for (const char* path : seq_files) {
     FILE* in = fopen(path, "rb");
     if (!in) die(std::string("Failed to open input file '") + path + "'");
-    ByteBuf seq;
+    HeapBuf seq;
     std::vector<uint64_t> keys;
-    read_sequences(in, path, seq, 64u << 20, [&](ByteBuf& b) {
+    read_sequences(in, path, seq, 64u << 20, [&](HeapBuf& b) {
       keys.clear();
       kmers_of(b, k, d.info.canonical, keys);
       answer(keys);

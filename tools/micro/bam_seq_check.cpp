@@ -17,15 +17,7 @@
   _exit(1);
 }
 
-struct HeapBuf {
-  std::string s;
-  bool empty() const { return s.empty(); }
-  char back() const { return s.back(); }
-  void push_back(char c) { s.push_back(c); }
-  void append(const char* p, size_t n) { s.append(p, n); }
-  size_t size() const { return s.size(); }
-  void clear() { s.clear(); }
-};
+// (HeapBuf: tools/rg_cli.hpp)
 
 int main(int argc, char** argv) {
   unsigned threads = 1;

@@ -82,6 +82,23 @@ struct ByteBuf {
   const char* end() const { return p + n; }
 };
 
+// the same interface over ordinary heap memory, for bytes that never travel to the device as they are (the FASTA of
+// `jellyfish query -s`: a few MB whose k-mers are uploaded as packed keys; pinning and unpinning a growing buffer five
+// times costs more than reading it)
+struct HeapBuf {
+  std::string s;
+  void reserve(size_t want) { s.reserve(want); }
+  const char* data() const { return s.data(); }
+  size_t size() const { return s.size(); }
+  bool empty() const { return s.empty(); }
+  char back() const { return s.back(); }
+  void clear() { s.clear(); }
+  void push_back(char c) { s.push_back(c); }
+  void append(const char* p, size_t len) { s.append(p, len); }
+  const char* begin() const { return s.data(); }
+  const char* end() const { return s.data() + s.size(); }
+};
+
 // buffered line reader over a FILE* (regular file, FIFO or stdin)
 struct LineReader {
   FILE* f = nullptr;
