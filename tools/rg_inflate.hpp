@@ -3,8 +3,9 @@
 // (profiles/r2_host_ingest.txt): zlib's decoder refills its bit buffer a byte at a time and goes back to its
 // state machine for every symbol; this one keeps a 64-bit bit buffer refilled with one unaligned load, resolves a
 // symbol with one lookup in an 11-bit (litlen) / 8-bit (distance) table (+ one sub-table lookup for longer codes),
-// decodes up to three literals per refill and copies matches eight bytes at a time. The caller checks the gzip
-// CRC-32 of every member, so a decoder bug cannot pass silently.
+// decodes up to three literals per refill, looks the next symbol's entry up before it copies a match (the load overlaps
+// the copy) and copies the first 24 bytes of a match without a loop test (a BAM's matches average 13 bytes). The caller
+// checks the gzip CRC-32 of every member, so a decoder bug cannot pass silently.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -275,18 +276,37 @@ class Inflater {
     bb >>= (e & 63);                                                         \
     bc -= (e & 63);                                                          \
   } while (0)
+      // The entry of the NEXT symbol is looked up as soon as its bits are known — before the match copy, before the
+      // loop test — so that the table load's latency overlaps the copy / the refill instead of heading the next
+      // symbol's dependency chain. (A looked-up entry consumes nothing until RG_CONSUME: leaving the loop with one in
+      // hand is harmless.)
+#define RG_CONSUME(e, tab)                                                   \
+  do {                                                                       \
+    if (__builtin_expect(is_sub(e), 0)) {                                    \
+      bb >>= (e & 63);                                                       \
+      bc -= (e & 63);                                                        \
+      e = tab[((e >> 16) & 0x7FFF) + (bb & ((1u << ((e >> 8) & 31)) - 1))];  \
+    }                                                                        \
+    bb >>= (e & 63);                                                         \
+    bc -= (e & 63);                                                          \
+  } while (0)
+      uint32_t e;
+      RG_REFILL();
+      e = ll[bb & ll_mask];
       while (in <= in_fast_end && out <= out_fast_end) {
-        uint32_t e;
-        RG_REFILL();
-        RG_LOOKUP(e, ll, ll_mask);
+        RG_CONSUME(e, ll);
         if (is_literal(e)) {
           *out++ = (unsigned char)(e >> 16);
-          RG_LOOKUP(e, ll, ll_mask);
+          e = ll[bb & ll_mask];
+          RG_CONSUME(e, ll);
           if (is_literal(e)) {
             *out++ = (unsigned char)(e >> 16);
-            RG_LOOKUP(e, ll, ll_mask);
+            e = ll[bb & ll_mask];
+            RG_CONSUME(e, ll);
             if (is_literal(e)) {
               *out++ = (unsigned char)(e >> 16);
+              RG_REFILL();
+              e = ll[bb & ll_mask];
               continue;
             }
           }
@@ -311,16 +331,37 @@ class Inflater {
         bb >>= xb;
         bc -= xb;
         if (__builtin_expect(dist > (size_t)(out - out_begin), 0)) return false;
+        RG_REFILL();
+        e = ll[bb & ll_mask];                 // the next symbol's entry, while the copy runs
         const unsigned char* src = out - dist;
         unsigned char* const stop = out + length;
         if (dist >= 8) {
-          do {
-            memcpy(out, src, 8);
-            out += 8;
-            src += 8;
-          } while (out < stop);
+          // three words without a test (most matches of a BAM are shorter than 24 bytes: no loop branch to mispredict;
+          // the room for the overshoot is part of the 274 bytes the loop condition keeps free), then the rest
+          memcpy(out, src, 8);
+          memcpy(out + 8, src + 8, 8);
+          memcpy(out + 16, src + 16, 8);
+          if (__builtin_expect(length > 24, 0)) {
+            out += 24;
+            src += 24;
+            do {
+              memcpy(out, src, 8);
+              out += 8;
+              src += 8;
+            } while (out < stop);
+          }
         } else if (dist == 1) {
-          memset(out, *src, length);
+          // a run of one byte (quality strings): whole words of it
+          const uint64_t v = 0x0101010101010101ull * *src;
+          memcpy(out, &v, 8);
+          memcpy(out + 8, &v, 8);
+          if (__builtin_expect(length > 16, 0)) {
+            out += 16;
+            do {
+              memcpy(out, &v, 8);
+              out += 8;
+            } while (out < stop);
+          }
         } else {
           do *out++ = *src++; while (out < stop);
         }
@@ -331,6 +372,7 @@ class Inflater {
       bitcnt_ = bc;
 #undef RG_REFILL
 #undef RG_LOOKUP
+#undef RG_CONSUME
     }
     // ---- careful loop: the ends of the input and of the output
     for (;;) {
