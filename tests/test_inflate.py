@@ -142,3 +142,13 @@ def test_truncated_and_corrupted_streams_never_crash_and_never_disagree_with_zli
     assert all(g == r for g, r in both)
     # whatever zlib accepts as a complete stream of exactly n bytes, the fast decoder accepts too
     assert all(g is not None for g, r in zip(got, ref) if r is not None)
+
+
+def test_crc32_by_carryless_multiplication_equals_zlib(tmp_path):
+    """tools/rg_crc32.hpp (what checks every BGZF member's inflated bytes) against zlib's crc32: 60 000 pseudo-random
+    slices — shorter than one 64-byte fold, not a multiple of 16, tens of kilobytes, every alignment"""
+    import numpy as np
+    f = tmp_path / "bytes.bin"
+    f.write_bytes(np.random.default_rng(5).integers(0, 256, 300_000, dtype=np.uint8).tobytes())
+    r = subprocess.run([EXE, "--crc", str(f)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "60000 cases, 0 bad", r.stdout + r.stderr

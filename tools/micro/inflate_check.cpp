@@ -2,6 +2,7 @@
 //   inflate_check CASES            CASES = repeated [u32 comp_len][u32 out_len][comp bytes]; writes, per case, one
 //                                  status byte (1 = inflated, 0 = rejected) followed by the inflated bytes when 1
 //   inflate_check --time FILE.bam  inflates every BGZF member of the file with rg::Inflater and with zlib
+//   inflate_check --crc FILE       rg::crc32_of against zlib's crc32 on pseudo-random slices of the file
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -10,6 +11,9 @@
 #include <chrono>
 #include <vector>
 
+#include <algorithm>
+
+#include "../rg_crc32.hpp"
 #include "../rg_inflate.hpp"
 
 static std::vector<unsigned char> slurp(const char* path) {
@@ -57,6 +61,24 @@ int main(int argc, char** argv) {
     }
     printf("%s: %.1f MB inflated, rg::Inflater %.3f s (%.0f MB/s), zlib %s %.3f s (%.0f MB/s), mismatching members: %zu\n", argv[2],
            total / 1e6, t_mine, total / 1e6 / t_mine, zlibVersion(), t_zlib, total / 1e6 / t_zlib, bad);
+    return bad ? 1 : 0;
+  }
+  if (argc == 3 && !strcmp(argv[1], "--crc")) {
+    // rg::crc32_of (tools/rg_crc32.hpp: carry-less-multiply folding where the CPU has it) against zlib's crc32 on
+    // pseudo-random slices of the file: every length class (below one fold, not a multiple of 16, many folds), every
+    // alignment
+    const std::vector<unsigned char> d = slurp(argv[2]);
+    unsigned s = 12345;
+    size_t bad = 0, cases = 0;
+    for (int it = 0; it < 60000 && d.size() > 1; ++it) {
+      s = s * 1664525u + 1013904223u;
+      const size_t off = (s >> 8) % d.size();
+      s = s * 1664525u + 1013904223u;
+      const size_t n = std::min<size_t>(d.size() - off, (s >> 8) % (it % 3 == 0 ? 300 : 70000));
+      bad += rg::crc32_of(d.data() + off, n) != (uint32_t)crc32(crc32(0L, Z_NULL, 0), d.data() + off, (uInt)n);
+      ++cases;
+    }
+    printf("%zu cases, %zu bad\n", cases, bad);
     return bad ? 1 : 0;
   }
   if (argc != 2) return 2;

@@ -29,6 +29,7 @@
 #include <utility>
 #include <vector>
 
+#include "rg_crc32.hpp"
 #include "rg_inflate.hpp"
 
 namespace rgbam {
@@ -197,7 +198,7 @@ struct Pipeline {
     if (m.isize == 0) return;
     const unsigned char* comp = b.raw.p + m.off;
     static const bool zlib_only = getenv("RG_BAMVIEW_ZLIB") != nullptr;   // measurement knob: zlib's inflate in the same pipeline
-    if (!zlib_only && inf.run(comp, m.clen, out, m.isize) && (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, m.isize) == m.crc) return;
+    if (!zlib_only && inf.run(comp, m.clen, out, m.isize) && rg::crc32_of(out, m.isize) == m.crc) return;
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) fail("zlib init failed");
@@ -208,7 +209,7 @@ struct Pipeline {
     const int rc = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
     if (rc != Z_STREAM_END || zs.total_out != m.isize) fail("corrupt BGZF block (inflate)");
-    if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), out, m.isize) != m.crc) fail("corrupt BGZF block (crc)");
+    if (rg::crc32_of(out, m.isize) != m.crc) fail("corrupt BGZF block (crc)");
   }
 
   void worker() {
