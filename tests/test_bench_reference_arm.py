@@ -41,3 +41,34 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_leave_without_work():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cpu_binding_logic_with_a_stand_in_nvml():
+    """bench.bind_to_gpu_cpus against a fake pynvml (the build container has no NVML): binds to the GPU's CPUs inside the
+    cpuset, keeps the affinity when fewer than four of them are allowed, never raises"""
+    code = r'''
+import importlib.util, os, sys, types
+allowed = sorted(os.sched_getaffinity(0))
+fake = types.ModuleType("pynvml")
+fake.nvmlInit = lambda: None
+fake.nvmlDeviceGetHandleByIndex = lambda i: i
+mask = {"v": 0}
+fake.nvmlDeviceGetCpuAffinity = lambda h, n: [(mask["v"] >> (64 * w)) & (2 ** 64 - 1) for w in range(n)]
+sys.modules["pynvml"] = fake
+sys.argv = ["bench.py"]
+spec = importlib.util.spec_from_file_location("bench", sys.argv[1] if False else os.environ["BENCH_PY"])
+b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+if len(allowed) >= 5:
+    want = allowed[:4]
+    mask["v"] = sum(1 << c for c in want)
+    print(b.bind_to_gpu_cpus(0)); assert sorted(os.sched_getaffinity(0)) == want
+    mask["v"] = sum(1 << c for c in want[:2])
+    print(b.bind_to_gpu_cpus(0)); assert sorted(os.sched_getaffinity(0)) == want        # two CPUs: kept
+def boom(h, n): raise RuntimeError("no nvml")
+fake.nvmlDeviceGetCpuAffinity = boom
+print(b.bind_to_gpu_cpus(0))
+print("OK")
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, BENCH_PY=os.path.join(ROOT, "bench.py")))
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+    assert "kept (RuntimeError)" in r.stdout
