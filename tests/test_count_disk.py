@@ -150,3 +150,29 @@ def test_count_that_fits_never_looks(inputs, tmp_path):
     assert r.returncode == 0, r.stderr
     log = [l for l in r.stderr.decode().splitlines() if l.split()[0] in ("push", "write_jhash", "clear")]
     assert [l.split()[0] for l in log] == ["push", "push", "write_jhash"], log
+
+
+def test_merge_differential_fuzz(inputs, tmp_path):
+    """random k (other key widths), -C or not, table size, -L/-U, number of parts: pieces counted by the reference's binary and
+    merged by us = the reference's count of the whole, record for record"""
+    import random
+    d, rng = str(tmp_path), random.Random(9)
+    recs = open(os.path.join(str(inputs), "a.fq"), "rb").read().split(b"\n@")
+    recs = [recs[0]] + [b"@" + r for r in recs[1:]]
+    for it in range(4):
+        k, nparts, canon = rng.choice([15, 21, 25, 31]), rng.randrange(2, 7), rng.choice(["-C", ""])
+        sz, L, U = rng.choice(["1M", "4M", "16M"]), rng.choice([1, 2, 3]), rng.choice([0, 0, 50])
+        sub = rng.sample(recs, 1200)
+        cuts = sorted(rng.sample(range(1, 1200), nparts - 1)) + [1200]
+        files, prev = [], 0
+        for i, c in enumerate(cuts):
+            open(os.path.join(d, f"f{i}.fq"), "wb").write(b"\n".join(sub[prev:c]) + b"\n")
+            files.append(f"f{i}.fq")
+            prev = c
+        for i, fn in enumerate(files):
+            sh(f"{REF} count -m {k} {canon} -s {sz} -t 2 -o p{i} {fn}", d)
+        u = f"-U {U}" if U else ""
+        sh(f"{REF} count -m {k} {canon} -L {L} {u} -s {sz} -t 2 -o whole " + " ".join(files), d)
+        sh(f"{JF} rg-merge-parts -L {L} {u} -o merged " + " ".join(f"p{i}" for i in range(len(files))), d)
+        assert records(os.path.join(d, "merged")) == records(os.path.join(d, "whole")), (it, k, nparts, canon, sz, L, U)
+        assert len(records(os.path.join(d, "whole"))) > 0
